@@ -1,0 +1,144 @@
+/*
+ * r3d_b200 -- C ABI of the B200-native R3D token-fuser / effective-rank path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch types.  Every
+ * pointer is a DEVICE pointer unless the name ends in `_host`.  Every call is
+ * asynchronous on `stream` (a cudaStream_t passed as void*), re-entrant, and
+ * keeps no global mutable state except the thread-local last-error string.
+ * Return value: 0 on success, non-zero on error (r3d_last_error() explains).
+ *
+ * Reference citations are relative to the reference repository root
+ * (olivesgatech/R3D): each entry point names the reference lines it replaces.
+ *
+ * dtype codes: R3D_F32 = 0 (float), R3D_BF16 = 1 (__nv_bfloat16).
+ * blend codes: R3D_BLEND_SWAP = 0, R3D_BLEND_SCALE = 1, R3D_BLEND_CONVEX = 2.
+ */
+#ifndef R3D_B200_H
+#define R3D_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define R3D_F32 0
+#define R3D_BF16 1
+
+#define R3D_BLEND_SWAP 0   /* model/futr_safuser_tokenfusion.py:59-60          */
+#define R3D_BLEND_SCALE 1  /* model/futr_safuser_tokenfusion_vary.py:51-56     */
+#define R3D_BLEND_CONVEX 2 /* model/futr_safuser_batchnormalization.py:65-74   */
+
+/* ---- library ------------------------------------------------------------ */
+const char* r3d_last_error(void);
+int r3d_abi_version(void);
+/* Number of kernels this library has launched from the calling thread since
+ * the counter was last reset (bench.py's `gpu_launches`). */
+int64_t r3d_launch_count(int reset);
+
+/* ---- a1: channel score ---------------------------------------------------
+ * Replaces  x.abs().mean(dim=(0,1))  for both modalities in one launch:
+ * model/futr_safuser_tokenfusion.py:49-50, ..._vary.py:41-42.
+ * rgb, depth: (rows, C) row-major, rows = B*T.  partial: workspace of
+ * r3d_score_workspace_floats(rows, C) floats.  Stage 1 only: per-CTA column
+ * sums of |x| in a fixed order; r3d_bottomk() (or r3d_score_finalize) reduces
+ * them, again in a fixed order, so results are run-to-run bit-identical. */
+size_t r3d_score_workspace_floats(int64_t rows, int64_t C);
+int r3d_channel_score_partial(const void* rgb, const void* depth, int64_t rows, int64_t C, int dtype,
+                              float* partial, void* stream);
+/* sums_out (2, C): column sums of |x| (NOT divided) -- this is the buffer that is
+ * all-reduced across ranks in global-score mode; score_out (2, C) = sums / rows. */
+int r3d_score_finalize(const float* partial, int64_t rows, int64_t C, float* sums_out, float* score_out,
+                       void* stream);
+
+/* ---- a4: bottom-k -----------------------------------------------------------
+ * Replaces  torch.topk(score, k, dim=-1, largest=False)[1]  for `nvec` score
+ * vectors at once: model/futr_safuser_tokenfusion.py:52-54, ..._vary.py:44-46,
+ * ..._batchnormalization.py:58-60.  score: (nvec, C) float; idx_out: (nvec, k)
+ * int64, ascending by score, ties -> lower index, NaN last.  C <= 8192. */
+int r3d_bottomk(const float* score, int nvec, int64_t C, int64_t k, int64_t* idx_out, void* stream);
+
+/* ---- a3: BatchNorm1d front end of the BN variant ------------------------------
+ * Replaces  bn(x.permute(0,2,1)).permute(0,2,1)  batch statistics:
+ * model/futr_safuser_batchnormalization.py:45-46.  Two launches: per-CTA Welford
+ * partials, then a fixed-order Chan merge.  stats_out (2 modalities, 3, C):
+ * [mean, biased var, unbiased var].  */
+size_t r3d_bn_workspace_floats(int64_t rows, int64_t C);
+int r3d_bn_stats(const void* rgb, const void* depth, int64_t rows, int64_t C, int dtype, float* workspace,
+                 float* stats_out, void* stream);
+
+/* ---- a5/a6/a7: exchange + stack ---------------------------------------------
+ * Replaces clone x2 + index_put x2 + stack:
+ *   swap   model/futr_safuser_tokenfusion.py:56-62
+ *   scale  model/futr_safuser_tokenfusion_vary.py:48-57
+ *   convex model/futr_safuser_batchnormalization.py:62-75
+ * out: (rows, 2, C), same dtype.  idx_r / idx_d: k int64 channel indices each.
+ * alpha: (C) float or NULL (swap).  affine: NULL, or (2 modalities, 2, C) float
+ * [scale, shift] applied to the inputs first (x*scale + shift) -- the fused
+ * BatchNorm normalise of the BN variant. */
+int r3d_exchange_fwd(const void* rgb, const void* depth, const int64_t* idx_r, const int64_t* idx_d, int64_t k,
+                     const float* alpha, const float* affine, int blend, void* out, int64_t rows, int64_t C,
+                     int dtype, void* stream);
+
+/* ---- a8: backward of the exchange ---------------------------------------------
+ * Replaces autograd through the lines above.  g: (rows, 2, C).  d_rgb, d_depth:
+ * (rows, C) gradients w.r.t. the tensors that entered the blend (for the BN
+ * variant: w.r.t. the normalised tensors).  For blend != swap, rgb/depth (and
+ * `affine` if the forward used it) must be given and colsum_partial receives
+ * per-CTA column sums, reduced by r3d_exchange_bwd_finalize into
+ * colsums_out (5, C) = [d_alpha, sum dRhat, sum dRhat*Rhat_n, sum dDhat, sum dDhat*Dhat_n]
+ * (the last four only when `bn_norm` != NULL: the BatchNorm backward sums).
+ * bn_norm: (2 modalities, 2, C) float [rstd, -mean*rstd], so xn = x*rstd - mean*rstd. */
+size_t r3d_exchange_bwd_workspace_floats(int64_t rows, int64_t C);
+int r3d_exchange_bwd(const void* g, const void* rgb, const void* depth, const int64_t* idx_r, const int64_t* idx_d,
+                     int64_t k, const float* alpha, const float* affine, const float* bn_norm, int blend,
+                     void* d_rgb, void* d_depth, float* colsum_partial, int64_t rows, int64_t C, int dtype,
+                     void* stream);
+int r3d_exchange_bwd_finalize(const float* colsum_partial, int64_t rows, int64_t C, float* colsums_out, void* stream);
+/* BatchNorm backward, in place on d_rgb / d_depth (which hold dRhat / dDhat):
+ * dx = gamma*rstd * (dy - sum(dy)/N - xn * sum(dy*xn)/N). */
+int r3d_bn_bwd_apply(const void* rgb, const void* depth, const float* bn_norm, const float* gamma_r,
+                     const float* gamma_d, const float* colsums, void* d_rgb, void* d_depth, int64_t rows, int64_t C,
+                     int dtype, void* stream);
+
+/* ---- a12: effective rank -------------------------------------------------------
+ * No reference symbol; follows SURVEY.md appendix B.
+ * x: (B, T, C).  n = min(T, C), m = max(T, C).
+ * Workspace layout is private; query the size, hand in one device buffer. */
+size_t r3d_erank_workspace_bytes(int64_t B, int64_t T, int64_t C, int dtype);
+/* Forward: erank_out (B) float, sigma_out (B, n) float (solver order, not sorted),
+ * U_out (B, n, n) float eigenvectors of the Gram (column j <-> sigma j),
+ * Y_out (B, n, m) float = U^T A with A the (n, m) short-side-major view of x.
+ * sweeps_out: optional (B) int32 Jacobi sweeps used.  gram_impl: 0 = tcgen05
+ * tensor-core path, 1 = SIMT fp32 path (kept for A/B accuracy checks). */
+int r3d_erank_fwd(const void* x, int64_t B, int64_t T, int64_t C, int dtype, float rtol, int gram_impl,
+                  void* workspace, float* erank_out, float* sigma_out, float* U_out, float* Y_out,
+                  int32_t* sweeps_out, void* stream);
+/* Backward: dx (B, T, C) same dtype as x = d(sum_b g[b]*erank[b]) / dx;
+ * accumulate != 0 adds into dx instead of overwriting. */
+int r3d_erank_bwd(const float* g, const float* erank, const float* sigma, const float* U, const float* Y,
+                  int64_t B, int64_t T, int64_t C, int dtype, float rtol, void* workspace, void* dx,
+                  int accumulate, void* stream);
+/* Stage-level entry points (benchmarks and parity tests address stages directly). */
+int r3d_gram(const void* x, int64_t B, int64_t T, int64_t C, int dtype, int gram_impl, void* workspace,
+             float* G_out, void* stream);
+int r3d_jacobi_eigh(const float* G, int64_t B, int64_t n, void* workspace, float* lambda_out, float* U_out,
+                    int32_t* sweeps_out, int max_sweeps, void* stream);
+size_t r3d_jacobi_workspace_bytes(int64_t B, int64_t n);
+/* a13: per-token (short-side) informativeness  s_t = sum_j p_j U[t,j]^2. */
+int r3d_token_informativeness(const float* sigma, const float* U, int64_t B, int64_t n, float rtol,
+                              float* score_out, void* stream);
+
+/* ---- host-buffer convenience (what a non-Python caller binds; used for `e2e`) ----
+ * All pointers are HOST pointers (pinned for full speed); the call copies in,
+ * runs score -> bottom-k -> exchange on the given stream, copies the stacked
+ * result and the indices out, and synchronises the stream. */
+int r3d_token_fusion_host(const void* rgb_host, const void* depth_host, int64_t B, int64_t T, int64_t C,
+                          int dtype, int64_t k, void* out_host, int64_t* idx_r_host, int64_t* idx_d_host,
+                          void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* R3D_B200_H */

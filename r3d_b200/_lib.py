@@ -1,0 +1,80 @@
+"""ctypes binding of the C-ABI library (include/r3d_b200.h).
+
+There is no CPU fallback: if the shared object is missing or a tensor is not on
+a CUDA device the call raises.  The library is looked up in-tree
+(r3d_b200/csrc/libr3d_b200.so) so the GPU box loads exactly what was built here.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libr3d_b200.so")
+
+_lib = None
+
+# name -> (restype, argtypes); mirrors include/r3d_b200.h one to one
+SIGNATURES = {
+    "r3d_last_error": (c_char_p, []),
+    "r3d_abi_version": (c_int, []),
+    "r3d_launch_count": (c_int64, [c_int]),
+    "r3d_score_workspace_floats": (c_size_t, [c_int64, c_int64]),
+    "r3d_channel_score_partial": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p]),
+    "r3d_score_finalize": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
+    "r3d_bottomk": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p]),
+    "r3d_bn_workspace_floats": (c_size_t, [c_int64, c_int64]),
+    "r3d_bn_stats": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
+    "r3d_exchange_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int,
+                                 c_void_p, c_int64, c_int64, c_int, c_void_p]),
+    "r3d_exchange_bwd_workspace_floats": (c_size_t, [c_int64, c_int64]),
+    "r3d_exchange_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
+                                 c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p]),
+    "r3d_exchange_bwd_finalize": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
+    "r3d_bn_bwd_apply": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                 c_int64, c_int64, c_int, c_void_p]),
+    "r3d_erank_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int]),
+    "r3d_erank_fwd": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int, c_float, c_int, c_void_p, c_void_p,
+                              c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "r3d_erank_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int,
+                              c_float, c_void_p, c_void_p, c_int, c_void_p]),
+    "r3d_gram": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "r3d_jacobi_eigh": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                c_void_p]),
+    "r3d_jacobi_workspace_bytes": (c_size_t, [c_int64, c_int64]),
+    "r3d_token_informativeness": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_float, c_void_p, c_void_p]),
+    "r3d_token_fusion_host": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_int64, c_void_p,
+                                      c_void_p, c_void_p, c_void_p]),
+}
+
+
+class R3DError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load (once) and return the ctypes handle.  Raises if the library was not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise R3DError(
+                f"{LIB_PATH} not found: build it with `python -m r3d_b200.csrc.build` "
+                "(r3d_b200 has no CPU or eager fallback)")
+        h = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(h, name)      # AttributeError here = header/library drift
+            fn.restype = res
+            fn.argtypes = args
+        _lib = h
+    return _lib
+
+
+def check(rc: int):
+    if rc != 0:
+        msg = lib().r3d_last_error()
+        raise R3DError(f"r3d_b200 error {rc}: {msg.decode() if msg else '?'}")
+
+
+def launch_count(reset: bool = False) -> int:
+    return int(lib().r3d_launch_count(1 if reset else 0))

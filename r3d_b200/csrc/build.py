@@ -1,0 +1,80 @@
+"""Build libr3d_b200.so in-tree with nvcc for sm_100a (no torch headers involved).
+
+    python -m r3d_b200.csrc.build [--force] [--verbose]
+
+The library is a plain C-ABI shared object (include/r3d_b200.h); it links the
+static CUDA runtime and resolves the two driver entry points it needs
+(cuTensorMapEncodeTiled) through cudaGetDriverEntryPoint at run time, so it has
+no link-time dependency on libcuda and builds on a box without a GPU.
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SOURCES = ["fusion_kernels.cu", "erank_kernels.cu", "gram_tcgen05.cu", "block_kernels.cu"]
+HEADERS = ["common.cuh", os.path.join("..", "..", "include", "r3d_b200.h")]
+LIB = os.path.join(HERE, "libr3d_b200.so")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-lineinfo", "-std=c++17",
+    "--expt-relaxed-constexpr",
+    "-Xcompiler", "-fPIC",
+    "-Xptxas", "-v",
+]
+
+
+def _nvcc() -> str:
+    for c in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if c and (os.path.isabs(c) and os.path.exists(c) or not os.path.isabs(c)):
+            return c
+    raise RuntimeError("nvcc not found")
+
+
+def _stale() -> bool:
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(HERE, s) for s in SOURCES + HEADERS if os.path.exists(os.path.join(HERE, s))]
+    deps += [os.path.join(HERE, f) for f in os.listdir(HERE) if f.endswith(".cuh")]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not _stale():
+        return LIB
+    objs = []
+    logs = []
+    procs = []
+    for s in SOURCES:
+        src = os.path.join(HERE, s)
+        if not os.path.exists(src):
+            continue
+        obj = os.path.join(HERE, s.replace(".cu", ".o"))
+        cmd = [_nvcc(), *NVCC_FLAGS, "-c", src, "-o", obj]
+        procs.append((s, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for s, obj, p in procs:
+        out, _ = p.communicate()
+        logs.append(f"==== {s}\n{out}")
+        if p.returncode != 0:
+            sys.stderr.write(out)
+            raise RuntimeError(f"nvcc failed on {s}")
+        objs.append(obj)
+    cmd = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs, "-lcudart_static",
+           "-ldl", "-lrt", "-lpthread"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout)
+        raise RuntimeError("link failed")
+    with open(os.path.join(HERE, "build_ptxas.log"), "w") as f:
+        f.write("\n".join(logs))
+    if verbose:
+        print("\n".join(logs))
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

@@ -1,0 +1,682 @@
+// Effective-rank chain for sm_100a (no reference symbol exists,
+// the definition is SURVEY.md appendix B):
+//
+//   Gram on the smaller side  ->  block two-sided Jacobi eigensolver (fp32, shared
+//   memory inner solves + GEMM-shaped tile updates)  ->  Rayleigh refinement
+//   Y = U^T A, sigma_j = ||y_j|| / ||u_j||  ->  cut-off / normalise / entropy / exp.
+//   Backward: dX = U diag(coef) Y  (one GEMM, eigenvector outer products).
+//
+// Side choice: T < C -> G = X X^T (n = T);  T >= C -> G = X^T X (n = C).  The
+// channel side is preferred on ties because per-channel scale differences make
+// X^T X a graded matrix, which two-sided Jacobi resolves to relative accuracy.
+// No transposes are materialised: the GEMMs read X through (row, col) strides.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace r3d {
+
+constexpr int JB = 32;        // Jacobi block width
+constexpr int JM = 2 * JB;    // inner problem size (one block pair)
+constexpr int JMAX_SWEEPS = 32;
+
+// ------------------------------------------------------------------------------
+// Generic batched SIMT GEMM, fp32 accumulate:  C[b] = op(A[b]) * op(B[b])
+//   a(i,k) = TRANS_A ? A[k*lda + i] : A[i*lda + k]
+//   b(k,j) = TRANS_B ? B[j*ldb + k] : B[k*ldb + j]
+// optional kscale[b][k] multiplies a(i,k).  64x64x16 tiles, 4x4 per thread.
+// Used for Y = U^T A and the backward GEMM, and as the SIMT Gram (gram_impl = 1).
+// ------------------------------------------------------------------------------
+__device__ __forceinline__ float to_f(float v) { return v; }
+__device__ __forceinline__ float to_f(__nv_bfloat16 v) { return __bfloat162float(v); }
+__device__ __forceinline__ void from_f(float* p, float v, bool acc) { *p = acc ? (*p + v) : v; }
+__device__ __forceinline__ void from_f(__nv_bfloat16* p, float v, bool acc) {
+  *p = __float2bfloat16_rn(acc ? (__bfloat162float(*p) + v) : v);
+}
+
+template <typename TA, typename TB, typename TC, bool TRANS_A, bool TRANS_B>
+__global__ void __launch_bounds__(256) sgemm_batched_kernel(const TA* __restrict__ A, const TB* __restrict__ Bm,
+                                                            TC* __restrict__ Cm, int M, int N, int K, int64_t lda,
+                                                            int64_t ldb, int64_t ldc, int64_t strideA,
+                                                            int64_t strideB, int64_t strideC,
+                                                            const float* __restrict__ kscale, int64_t strideS,
+                                                            int accumulate) {
+  __shared__ float As[16][64 + 4];
+  __shared__ float Bs[16][64 + 4];
+  const int bz = blockIdx.z;
+  A += int64_t(bz) * strideA;
+  Bm += int64_t(bz) * strideB;
+  Cm += int64_t(bz) * strideC;
+  if (kscale) kscale += int64_t(bz) * strideS;
+  const int i_base = blockIdx.y * 64, j_base = blockIdx.x * 64;
+  const int tid = threadIdx.x;
+  const int ti = tid / 16, tj = tid % 16;
+  float acc[4][4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+#pragma unroll
+    for (int v = 0; v < 4; ++v) acc[u][v] = 0.f;
+
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    // ---- stage A tile (64 x 16) into As[k][i] ----
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      int idx = tid + e * 256;
+      int i, k;
+      if (TRANS_A) { i = idx % 64; k = idx / 64; } else { k = idx % 16; i = idx / 16; }
+      const int gi = i_base + i, gk = k0 + k;
+      float v = 0.f;
+      if (gi < M && gk < K) {
+        v = to_f(TRANS_A ? A[int64_t(gk) * lda + gi] : A[int64_t(gi) * lda + gk]);
+        if (kscale) v *= kscale[gk];
+      }
+      As[k][i] = v;
+    }
+    // ---- stage B tile (16 x 64) into Bs[k][j] ----
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      int idx = tid + e * 256;
+      int j, k;
+      if (TRANS_B) { k = idx % 16; j = idx / 16; } else { j = idx % 64; k = idx / 64; }
+      const int gj = j_base + j, gk = k0 + k;
+      float v = 0.f;
+      if (gj < N && gk < K) v = to_f(TRANS_B ? Bm[int64_t(gj) * ldb + gk] : Bm[int64_t(gk) * ldb + gj]);
+      Bs[k][j] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[k][ti * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tj * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) acc[u][v] = fmaf(av[u], bv[v], acc[u][v]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int gi = i_base + ti * 4 + u;
+    if (gi >= M) continue;
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      const int gj = j_base + tj * 4 + v;
+      if (gj < N) from_f(Cm + int64_t(gi) * ldc + gj, acc[u][v], accumulate != 0);
+    }
+  }
+}
+
+template <typename TA, typename TB, typename TC>
+static int sgemm_launch(bool ta, bool tb, const TA* A, const TB* Bm, TC* Cm, int M, int N, int K, int64_t lda,
+                        int64_t ldb, int64_t ldc, int64_t sA, int64_t sB, int64_t sC, const float* kscale,
+                        int64_t sS, int accumulate, int batch, cudaStream_t st) {
+  dim3 grid((N + 63) / 64, (M + 63) / 64, batch);
+#define R3D_GEMM(TA_, TB_) \
+  sgemm_batched_kernel<TA, TB, TC, TA_, TB_><<<grid, 256, 0, st>>>(A, Bm, Cm, M, N, K, lda, ldb, ldc, sA, sB, sC, kscale, sS, accumulate)
+  if (ta && tb) R3D_GEMM(true, true);
+  else if (ta) R3D_GEMM(true, false);
+  else if (tb) R3D_GEMM(false, true);
+  else R3D_GEMM(false, false);
+#undef R3D_GEMM
+  R3D_LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------
+// Jacobi workspace layout (all per batch):
+//   Gp  (np, np)  padded symmetric working matrix        Vt (np, np) rows -> eigenvectors
+//   Qb  (nt, 64, 64) rotation products of the current round, nt = nb/2 tasks
+//   cnt (JMAX_SWEEPS) significant rotations per sweep     qflag (nt) task rotated anything
+//   nu  (1) absolute significance floor
+// ------------------------------------------------------------------------------
+struct JacobiWs {
+  float* Gp; float* Vt; float* Qb; int* cnt; int* qflag; float* nu;
+  int np, nb, nt;
+};
+
+static inline int jacobi_np(int64_t n) { return int(((n + JM - 1) / JM) * JM); }
+
+static size_t jacobi_ws_bytes(int64_t B, int64_t n) {
+  const size_t np = jacobi_np(n), nt = np / JM;
+  size_t f = size_t(B) * (2 * np * np + nt * JM * JM + 1);
+  size_t i = size_t(B) * (JMAX_SWEEPS + nt);
+  return f * 4 + i * 4 + 256;
+}
+
+static JacobiWs jacobi_carve(void* ws, int64_t B, int64_t n) {
+  JacobiWs w;
+  w.np = jacobi_np(n); w.nb = w.np / JB; w.nt = w.np / JM;
+  char* p = (char*)ws;
+  p = (char*)((uintptr_t(p) + 255) & ~uintptr_t(255));
+  const size_t np2 = size_t(w.np) * w.np;
+  w.Gp = (float*)p; p += size_t(B) * np2 * 4;
+  w.Vt = (float*)p; p += size_t(B) * np2 * 4;
+  w.Qb = (float*)p; p += size_t(B) * w.nt * JM * JM * 4;
+  w.nu = (float*)p; p += size_t(B) * 4;
+  w.cnt = (int*)p; p += size_t(B) * JMAX_SWEEPS * 4;
+  w.qflag = (int*)p;
+  return w;
+}
+
+// Gp <- zero-padded copy of G; Vt <- I; cnt <- 0; nu <- 2^-21 * max |diag|.
+__global__ void jacobi_init_kernel(const float* __restrict__ G, int n, int np, float* __restrict__ Gp,
+                                   float* __restrict__ Vt, int* __restrict__ cnt, float* __restrict__ nu) {
+  const int b = blockIdx.y;
+  const float* g = G + int64_t(b) * n * n;
+  float* gp = Gp + int64_t(b) * np * np;
+  float* vt = Vt + int64_t(b) * np * np;
+  const int64_t total = int64_t(np) * np;
+  for (int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; e < total; e += int64_t(gridDim.x) * blockDim.x) {
+    const int i = int(e / np), j = int(e % np);
+    gp[e] = (i < n && j < n) ? g[int64_t(i) * n + j] : 0.f;
+    vt[e] = (i == j) ? 1.f : 0.f;
+  }
+  if (blockIdx.x == 0) {
+    __shared__ float smax[256];
+    float m = 0.f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, fabsf(g[int64_t(i) * n + i]));
+    smax[threadIdx.x] = m;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+      if (threadIdx.x < s) smax[threadIdx.x] = fmaxf(smax[threadIdx.x], smax[threadIdx.x + s]);
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) nu[b] = smax[0] * 4.76837158e-7f;   // 4 * 2^-23
+    for (int i = threadIdx.x; i < JMAX_SWEEPS; i += blockDim.x) cnt[b * JMAX_SWEEPS + i] = 0;
+  }
+}
+
+// circle-method round robin over m (even) players: pair t of round r
+__device__ __forceinline__ void rr_pair(int m, int r, int t, int& a, int& b) {
+  if (m == 2) { a = 0; b = 1; return; }
+  int x, y;
+  if (t == 0) { x = r; y = m - 1; }
+  else { x = (r + t) % (m - 1); y = (r - t + (m - 1)) % (m - 1); }
+  a = min(x, y); b = max(x, y);
+}
+
+__device__ __forceinline__ int blk_row(int I, int J, int i) { return (i < JB) ? I * JB + i : J * JB + (i - JB); }
+
+// ------------------------------------------------------------------------------
+// Inner solver: one CTA diagonalises the 64x64 sub-block G[IJ, IJ] of one block
+// pair with parallel-ordered two-sided Jacobi in shared memory and emits the
+// accumulated rotation product Q (64x64).  32 disjoint rotations per step; the
+// rotation parameters come from one warp, column/row rotations from all 8 warps.
+// ------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) jacobi_inner_kernel(float* __restrict__ Gp, int np, int nb, int nt, int round,
+                                                           int sweep, int* __restrict__ cnt,
+                                                           int* __restrict__ qflag, float* __restrict__ Qb, float tol,
+                                                           const float* __restrict__ nu, int max_inner) {
+  const int b = blockIdx.y, t = blockIdx.x;
+  if (sweep > 0 && cnt[b * JMAX_SWEEPS + sweep - 1] == 0) return;   // this matrix converged
+  __shared__ float S[JM][JM + 1];
+  __shared__ float Q[JM][JM + 1];
+  __shared__ float rc[JB], rs[JB];
+  __shared__ int rp[JB], rq[JB];
+  __shared__ int s_any, s_sig, s_tot;
+  const int tid = threadIdx.x;
+  int I, J;
+  rr_pair(nb, round, t, I, J);
+  float* g = Gp + int64_t(b) * np * np;
+  for (int e = tid; e < JM * JM; e += 256) {
+    const int i = e / JM, j = e % JM;
+    S[i][j] = g[int64_t(blk_row(I, J, i)) * np + blk_row(I, J, j)];
+    Q[i][j] = (i == j) ? 1.f : 0.f;
+  }
+  if (tid == 0) { s_tot = 0; }
+  __syncthreads();
+  // symmetrise (the tile updates leave eps-level asymmetry)
+  for (int e = tid; e < JM * JM; e += 256) {
+    const int i = e / JM, j = e % JM;
+    if (i < j) {
+      const float v = 0.5f * (S[i][j] + S[j][i]);
+      S[i][j] = v; S[j][i] = v;
+    }
+  }
+  const float nu_abs = nu[b];
+  __syncthreads();
+
+  for (int it = 0; it < max_inner; ++it) {
+    if (tid == 0) s_sig = 0;
+    __syncthreads();
+    for (int s = 0; s < JM - 1; ++s) {
+      if (tid < JB) {
+        int p, q;
+        rr_pair(JM, s, tid, p, q);
+        const float app = S[p][p], aqq = S[q][q], apq = S[p][q];
+        const bool rot = (apq != 0.f) && (fabsf(apq) > tol * sqrtf(fabsf(app * aqq)));
+        const bool sig = rot && (fabsf(apq) > nu_abs);
+        float c = 1.f, sn = 0.f;
+        if (rot) {
+          const float zeta = (aqq - app) / (2.f * apq);
+          const float tt = (zeta >= 0.f ? 1.f : -1.f) / (fabsf(zeta) + sqrtf(1.f + zeta * zeta));
+          c = rsqrtf(1.f + tt * tt);
+          sn = tt * c;
+        }
+        rp[tid] = p; rq[tid] = q; rc[tid] = c; rs[tid] = sn;
+        const unsigned any = __ballot_sync(0xffffffffu, rot), sg = __ballot_sync(0xffffffffu, sig);
+        if (tid == 0) { s_any = (any != 0); s_sig += __popc(sg); s_tot += __popc(any); }
+      }
+      __syncthreads();
+      if (s_any) {
+        // columns of S and Q:  [x_p, x_q] <- [c x_p - s x_q, s x_p + c x_q]
+#pragma unroll
+        for (int u = 0; u < (JM * JB) / 256; ++u) {
+          const int item = tid + u * 256, r = item % JM, pr = item / JM;
+          const int p = rp[pr], q = rq[pr];
+          const float c = rc[pr], sn = rs[pr];
+          const float sp = S[r][p], sq = S[r][q];
+          S[r][p] = c * sp - sn * sq;
+          S[r][q] = sn * sp + c * sq;
+          const float qp = Q[r][p], qq = Q[r][q];
+          Q[r][p] = c * qp - sn * qq;
+          Q[r][q] = sn * qp + c * qq;
+        }
+        __syncthreads();
+        // rows of S
+#pragma unroll
+        for (int u = 0; u < (JM * JB) / 256; ++u) {
+          const int item = tid + u * 256, cc = item % JM, pr = item / JM;
+          const int p = rp[pr], q = rq[pr];
+          const float c = rc[pr], sn = rs[pr];
+          const float sp = S[p][cc], sq = S[q][cc];
+          S[p][cc] = c * sp - sn * sq;
+          S[q][cc] = sn * sp + c * sq;
+        }
+      }
+      __syncthreads();
+    }
+    const int sig_it = s_sig;   // stable: the step loop ended on a barrier
+    __syncthreads();
+    if (sig_it == 0) break;
+    if (tid == 0) atomicAdd(&cnt[b * JMAX_SWEEPS + sweep], sig_it);
+  }
+  float* qo = Qb + (int64_t(b) * nt + t) * JM * JM;
+  for (int e = tid; e < JM * JM; e += 256) qo[e] = Q[e / JM][e % JM];
+  if (tid == 0) qflag[b * nt + t] = (s_tot > 0);
+}
+
+// ------------------------------------------------------------------------------
+// Tile update of one round:  G[IJ_a, IJ_c] <- Q_a^T G[IJ_a, IJ_c] Q_c  (nt*nt tiles)
+// and Vt[IJ_a, slab] <- Q_a^T Vt[IJ_a, slab]  (nt * np/64 tiles).  64x64x64 products
+// from shared memory, 4x4 outputs per thread.
+// ------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) jacobi_update_kernel(float* __restrict__ Gp, float* __restrict__ Vt, int np,
+                                                            int nb, int nt, int round, int sweep,
+                                                            const int* __restrict__ cnt,
+                                                            const int* __restrict__ qflag,
+                                                            const float* __restrict__ Qb) {
+  const int b = blockIdx.y;
+  if (sweep > 0 && cnt[b * JMAX_SWEEPS + sweep - 1] == 0) return;
+  extern __shared__ float sm[];
+  float (*Tm)[JM + 4] = reinterpret_cast<float (*)[JM + 4]>(sm);
+  float (*Qa)[JM + 4] = reinterpret_cast<float (*)[JM + 4]>(sm + JM * (JM + 4));
+  float (*Qc)[JM + 4] = reinterpret_cast<float (*)[JM + 4]>(sm + 2 * JM * (JM + 4));
+  const int tid = threadIdx.x;
+  const int x = blockIdx.x;
+  const bool two_sided = x < nt * nt;
+  int a, c, slab = 0;
+  if (two_sided) { a = x / nt; c = x % nt; }
+  else { const int xx = x - nt * nt; const int nslab = np / JM; a = xx / nslab; slab = xx % nslab; c = a; }
+  const bool fa = qflag[b * nt + a] != 0, fc = two_sided && (qflag[b * nt + c] != 0);
+  if (!fa && !fc) return;
+  int Ia, Ja, Ic, Jc;
+  rr_pair(nb, round, a, Ia, Ja);
+  rr_pair(nb, round, c, Ic, Jc);
+  float* base = (two_sided ? Gp : Vt) + int64_t(b) * np * np;
+  const float* qa = Qb + (int64_t(b) * nt + a) * JM * JM;
+  const float* qc = Qb + (int64_t(b) * nt + c) * JM * JM;
+  for (int e = tid; e < JM * JM; e += 256) {
+    const int i = e / JM, j = e % JM;
+    const int gj = two_sided ? blk_row(Ic, Jc, j) : slab * JM + j;
+    Tm[i][j] = base[int64_t(blk_row(Ia, Ja, i)) * np + gj];
+    Qa[i][j] = qa[e];
+    if (two_sided) Qc[i][j] = qc[e];
+  }
+  __syncthreads();
+  const int ti = tid / 16, tj = tid % 16;
+  float acc[4][4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+#pragma unroll
+    for (int v = 0; v < 4; ++v) acc[u][v] = 0.f;
+  // T1[i][j] = sum_k Qa[k][i] * Tm[k][j]
+#pragma unroll 8
+  for (int k = 0; k < JM; ++k) {
+    const float4 av = *reinterpret_cast<const float4*>(&Qa[k][ti * 4]);
+    const float4 bv = *reinterpret_cast<const float4*>(&Tm[k][tj * 4]);
+    const float aa[4] = {av.x, av.y, av.z, av.w}, bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int v = 0; v < 4; ++v) acc[u][v] = fmaf(aa[u], bb[v], acc[u][v]);
+  }
+  if (two_sided) {
+    __syncthreads();   // everyone is done reading Tm
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      *reinterpret_cast<float4*>(&Tm[ti * 4 + u][tj * 4]) = make_float4(acc[u][0], acc[u][1], acc[u][2], acc[u][3]);
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int v = 0; v < 4; ++v) acc[u][v] = 0.f;
+    // out[i][j] = sum_k T1[i][k] * Qc[k][j]
+#pragma unroll 8
+    for (int k = 0; k < JM; ++k) {
+      const float4 bv = *reinterpret_cast<const float4*>(&Qc[k][tj * 4]);
+      const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float aa = Tm[ti * 4 + u][k];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) acc[u][v] = fmaf(aa, bb[v], acc[u][v]);
+      }
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int i = ti * 4 + u;
+    const int64_t gr = int64_t(blk_row(Ia, Ja, i)) * np;
+    const int j0 = tj * 4;
+    const int gj = two_sided ? blk_row(Ic, Jc, j0) : slab * JM + j0;   // 4 consecutive j stay inside one block
+    *reinterpret_cast<float4*>(&base[gr + gj]) = make_float4(acc[u][0], acc[u][1], acc[u][2], acc[u][3]);
+  }
+}
+
+// lambda = diag(Gp), Ut (n x n compact) = Vt[:n, :n]; sweeps = first sweep with zero significant rotations
+__global__ void jacobi_extract_kernel(const float* __restrict__ Gp, const float* __restrict__ Vt, int n, int np,
+                                      const int* __restrict__ cnt, int max_sweeps, float* __restrict__ lambda,
+                                      float* __restrict__ Ut, int* __restrict__ sweeps) {
+  const int b = blockIdx.y;
+  const float* gp = Gp + int64_t(b) * np * np;
+  const float* vt = Vt + int64_t(b) * np * np;
+  const int64_t total = int64_t(n) * n;
+  for (int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; e < total; e += int64_t(gridDim.x) * blockDim.x) {
+    const int i = int(e / n), j = int(e % n);
+    if (Ut) Ut[int64_t(b) * n * n + e] = vt[int64_t(i) * np + j];
+    if (i == j && lambda) lambda[int64_t(b) * n + i] = gp[int64_t(i) * np + i];
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0 && sweeps) {
+    int s = 0;
+    while (s < max_sweeps && cnt[b * JMAX_SWEEPS + s] != 0) ++s;
+    sweeps[b] = s + (s < max_sweeps ? 1 : 0);   // sweeps executed (the last one found nothing to do)
+  }
+}
+
+// ------------------------------------------------------------------------------
+// sigma_j = ||Y[j,:]|| / ||Ut[j,:]||   (one warp per row)
+// ------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) row_sigma_kernel(const float* __restrict__ Y, const float* __restrict__ Ut,
+                                                        int64_t rows_total, int n, int m,
+                                                        float* __restrict__ sigma) {
+  const int64_t row = int64_t(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (row >= rows_total) return;
+  const int lane = threadIdx.x & 31;
+  const float* y = Y + row * m;
+  const float* u = Ut + row * n;
+  float sy = 0.f, su = 0.f;
+  for (int c = lane; c < m; c += 32) { const float v = y[c]; sy = fmaf(v, v, sy); }
+  for (int c = lane; c < n; c += 32) { const float v = u[c]; su = fmaf(v, v, su); }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sy += __shfl_xor_sync(0xffffffffu, sy, o);
+    su += __shfl_xor_sync(0xffffffffu, su, o);
+  }
+  if (lane == 0) sigma[row] = (su > 0.f) ? sqrtf(sy / su) : 0.f;
+}
+
+// block-wide reductions for the per-sample spectrum kernels (blockDim = 256)
+__device__ __forceinline__ float block_reduce(float v, bool is_max, float* sh) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float w = __shfl_xor_sync(0xffffffffu, v, o);
+    v = is_max ? fmaxf(v, w) : (v + w);
+  }
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = sh[0];
+  for (int i = 1; i < 8; ++i) r = is_max ? fmaxf(r, sh[i]) : (r + sh[i]);
+  return r;
+}
+
+struct Spectrum { float smax, S, H, erank; };
+
+// cut-off / normalise / entropy / exp for one sample (all 256 threads participate)
+__device__ __forceinline__ Spectrum spectrum_stats(const float* __restrict__ sg, int n, float rtol, float* sh) {
+  float m = 0.f;
+  for (int j = threadIdx.x; j < n; j += 256) m = fmaxf(m, sg[j]);
+  const float smax = block_reduce(m, true, sh);
+  const float cut = rtol * smax;
+  float s = 0.f;
+  for (int j = threadIdx.x; j < n; j += 256) { const float v = sg[j]; if (v > cut) s += v; }
+  const float S = block_reduce(s, false, sh);
+  float h = 0.f;
+  if (S > 0.f) {
+    for (int j = threadIdx.x; j < n; j += 256) {
+      const float v = sg[j];
+      if (v > cut) { const float p = v / S; h -= p * logf(p); }
+    }
+  }
+  const float H = block_reduce(h, false, sh);
+  Spectrum r; r.smax = smax; r.S = S; r.H = H; r.erank = (S > 0.f) ? expf(H) : 0.f;
+  return r;
+}
+
+__global__ void __launch_bounds__(256) erank_entropy_kernel(const float* __restrict__ sigma, int n, float rtol,
+                                                            float* __restrict__ erank) {
+  __shared__ float sh[8];
+  const Spectrum sp = spectrum_stats(sigma + int64_t(blockIdx.x) * n, n, rtol, sh);
+  if (threadIdx.x == 0) erank[blockIdx.x] = sp.erank;
+}
+
+// coef_j = g * erank * (-(ln p_j + H) / S) / sigma_j  for kept j, else 0
+__global__ void __launch_bounds__(256) erank_coef_kernel(const float* __restrict__ sigma, const float* __restrict__ g,
+                                                         int n, float rtol, float* __restrict__ coef) {
+  __shared__ float sh[8];
+  const float* sg = sigma + int64_t(blockIdx.x) * n;
+  const Spectrum sp = spectrum_stats(sg, n, rtol, sh);
+  const float cut = rtol * sp.smax, gb = g[blockIdx.x];
+  for (int j = threadIdx.x; j < n; j += 256) {
+    const float v = sg[j];
+    float cf = 0.f;
+    if (v > cut && sp.S > 0.f) {
+      const float p = v / sp.S;
+      cf = gb * sp.erank * (-(logf(p) + sp.H) / sp.S) / v;
+    }
+    coef[int64_t(blockIdx.x) * n + j] = cf;
+  }
+}
+
+// a13: s_t = sum_j p_j Ut[j][t]^2 / ||Ut[j]||^2
+__global__ void __launch_bounds__(256) token_info_kernel(const float* __restrict__ sigma, const float* __restrict__ Ut,
+                                                         int n, float rtol, float* __restrict__ out) {
+  __shared__ float sh[8];
+  extern __shared__ float pj[];
+  const float* sg = sigma + int64_t(blockIdx.x) * n;
+  const float* u = Ut + int64_t(blockIdx.x) * n * n;
+  const Spectrum sp = spectrum_stats(sg, n, rtol, sh);
+  const float cut = rtol * sp.smax;
+  for (int j = threadIdx.x; j < n; j += 256) pj[j] = (sg[j] > cut && sp.S > 0.f) ? sg[j] / sp.S : 0.f;
+  __syncthreads();
+  // normalise p_j by the squared row norm of Ut (rows are unit up to fp32 drift)
+  for (int j = threadIdx.x >> 5; j < n; j += 8) {
+    float su = 0.f;
+    for (int c = threadIdx.x & 31; c < n; c += 32) { const float v = u[int64_t(j) * n + c]; su = fmaf(v, v, su); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) su += __shfl_xor_sync(0xffffffffu, su, o);
+    if ((threadIdx.x & 31) == 0 && su > 0.f) pj[j] /= su;
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < n; t += 256) {
+    float s = 0.f;
+    for (int j = 0; j < n; ++j) { const float v = u[int64_t(j) * n + t]; s = fmaf(pj[j] * v, v, s); }
+    out[int64_t(blockIdx.x) * n + t] = s;
+  }
+}
+
+int gram_tcgen05_launch(const void* x, int64_t B, int64_t T, int64_t C, int dtype, void* workspace, float* G,
+                        cudaStream_t st);   // gram_tcgen05.cu
+bool gram_tcgen05_supported(int64_t B, int64_t T, int64_t C, int dtype);
+
+}  // namespace r3d
+
+using namespace r3d;
+
+// ================================================================================
+// C ABI
+// ================================================================================
+static inline void side(int64_t T, int64_t C, int64_t& n, int64_t& m, bool& tside) {
+  tside = T < C;
+  n = tside ? T : C;
+  m = tside ? C : T;
+}
+
+extern "C" size_t r3d_jacobi_workspace_bytes(int64_t B, int64_t n) { return jacobi_ws_bytes(B, n); }
+
+extern "C" size_t r3d_erank_workspace_bytes(int64_t B, int64_t T, int64_t C, int dtype) {
+  int64_t n, m; bool ts; side(T, C, n, m, ts);
+  // G (B,n,n) + coef (B,n) + Jacobi workspace + tcgen05 Gram staging (hi/lo split of an fp32 input)
+  size_t bytes = size_t(B) * n * n * 4 + size_t(B) * n * 4 + jacobi_ws_bytes(B, n) + 1024;
+  if (dtype == R3D_F32) bytes += size_t(2) * B * T * C * 4;
+  return bytes;
+}
+
+template <typename T>
+static int gram_simt(const void* x, int64_t B, int64_t Tt, int64_t C, float* G, cudaStream_t st) {
+  int64_t n, m; bool ts; side(Tt, C, n, m, ts);
+  const T* X = (const T*)x;
+  // T-side: G = X X^T  (a(i,k)=X[i*C+k], b(k,j)=X[j*C+k]);  C-side: G = X^T X (a(i,k)=X[k*C+i], b(k,j)=X[k*C+j])
+  return sgemm_launch<T, T, float>(!ts, ts, X, X, G, int(n), int(n), int(m), C, C, n, Tt * C, Tt * C, n * n, nullptr,
+                                   0, 0, int(B), st);
+}
+
+extern "C" int r3d_gram(const void* x, int64_t B, int64_t T, int64_t C, int dtype, int gram_impl, void* workspace,
+                        float* G_out, void* stream) {
+  R3D_CHECK(x && G_out, "null pointer");
+  R3D_CHECK(B >= 1 && T >= 1 && C >= 1, "bad shape");
+  R3D_CHECK(dtype == R3D_F32 || dtype == R3D_BF16, "bad dtype %d", dtype);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (gram_impl == 0 && gram_tcgen05_supported(B, T, C, dtype))
+    return gram_tcgen05_launch(x, B, T, C, dtype, workspace, G_out, st);
+  return dtype == R3D_F32 ? gram_simt<float>(x, B, T, C, G_out, st) : gram_simt<__nv_bfloat16>(x, B, T, C, G_out, st);
+}
+
+static int jacobi_run(const float* G, int64_t B, int64_t n, void* workspace, float* lambda_out, float* U_out,
+                      int32_t* sweeps_out, int max_sweeps, cudaStream_t st) {
+  if (max_sweeps <= 0 || max_sweeps > JMAX_SWEEPS) max_sweeps = 16;
+  JacobiWs w = jacobi_carve(workspace, B, n);
+  const float tol = 1e-5f;
+  {
+    dim3 grid(std::min<int64_t>((int64_t(w.np) * w.np + 255) / 256, 64), (unsigned)B);
+    jacobi_init_kernel<<<grid, 256, 0, st>>>(G, int(n), w.np, w.Gp, w.Vt, w.cnt, w.nu);
+    R3D_LAUNCH_CHECK();
+  }
+  const size_t upd_smem = size_t(3) * JM * (JM + 4) * sizeof(float);
+  R3D_CUDA(cudaFuncSetAttribute(jacobi_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)upd_smem));
+  const int rounds = w.nb - 1;
+  const int upd_tiles = w.nt * w.nt + w.nt * (w.np / JM);
+  for (int sweep = 0; sweep < max_sweeps; ++sweep) {
+    for (int r = 0; r < rounds; ++r) {
+      jacobi_inner_kernel<<<dim3(w.nt, (unsigned)B), 256, 0, st>>>(w.Gp, w.np, w.nb, w.nt, r, sweep, w.cnt, w.qflag,
+                                                                  w.Qb, tol, w.nu, 8);
+      R3D_LAUNCH_CHECK();
+      jacobi_update_kernel<<<dim3(upd_tiles, (unsigned)B), 256, upd_smem, st>>>(w.Gp, w.Vt, w.np, w.nb, w.nt, r, sweep,
+                                                                               w.cnt, w.qflag, w.Qb);
+      R3D_LAUNCH_CHECK();
+    }
+  }
+  {
+    dim3 grid(std::min<int64_t>((n * n + 255) / 256, 64), (unsigned)B);
+    jacobi_extract_kernel<<<grid, 256, 0, st>>>(w.Gp, w.Vt, int(n), w.np, w.cnt, max_sweeps, lambda_out, U_out,
+                                                sweeps_out);
+    R3D_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+extern "C" int r3d_jacobi_eigh(const float* G, int64_t B, int64_t n, void* workspace, float* lambda_out, float* U_out,
+                               int32_t* sweeps_out, int max_sweeps, void* stream) {
+  R3D_CHECK(G && workspace, "null pointer");
+  R3D_CHECK(B >= 1 && n >= 1 && n <= 8192, "bad shape B=%lld n=%lld", (long long)B, (long long)n);
+  return jacobi_run(G, B, n, workspace, lambda_out, U_out, sweeps_out, max_sweeps, (cudaStream_t)stream);
+}
+
+template <typename T>
+static int refine_Y(const void* x, const float* Ut, int64_t B, int64_t Tt, int64_t C, float* Y, cudaStream_t st) {
+  int64_t n, m; bool ts; side(Tt, C, n, m, ts);
+  const T* X = (const T*)x;
+  // T-side: Y[j,c] = sum_r Ut[j,r] X[r,c]          (NN)
+  // C-side: Y[j,t] = sum_c Ut[j,c] X[t,c]          (NT)
+  return sgemm_launch<float, T, float>(false, !ts, Ut, X, Y, int(n), int(m), int(n), n, C, m, n * n, Tt * C, n * m,
+                                       nullptr, 0, 0, int(B), st);
+}
+
+extern "C" int r3d_erank_fwd(const void* x, int64_t B, int64_t T, int64_t C, int dtype, float rtol, int gram_impl,
+                             void* workspace, float* erank_out, float* sigma_out, float* U_out, float* Y_out,
+                             int32_t* sweeps_out, void* stream) {
+  R3D_CHECK(x && workspace && erank_out && sigma_out && U_out && Y_out, "null pointer");
+  R3D_CHECK(B >= 1 && T >= 1 && C >= 1, "bad shape");
+  R3D_CHECK(dtype == R3D_F32 || dtype == R3D_BF16, "bad dtype %d", dtype);
+  R3D_CHECK(rtol >= 0.f && rtol < 1.f, "rtol must be in [0, 1)");
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t n, m; bool ts; side(T, C, n, m, ts);
+  R3D_CHECK(n <= 8192, "min(T, C) = %lld exceeds 8192", (long long)n);
+  char* p = (char*)workspace;
+  p = (char*)((uintptr_t(p) + 255) & ~uintptr_t(255));
+  float* G = (float*)p; p += size_t(B) * n * n * 4;
+  p += size_t(B) * n * 4;   // coef slot (backward)
+  void* jws = p; p += jacobi_ws_bytes(B, n);
+  void* gws = p;            // tcgen05 staging
+  if (int e = r3d_gram(x, B, T, C, dtype, gram_impl, gws, G, st)) return e;
+  if (int e = jacobi_run(G, B, n, jws, nullptr, U_out, sweeps_out, 0, st)) return e;
+  if (int e = (dtype == R3D_F32 ? refine_Y<float>(x, U_out, B, T, C, Y_out, st)
+                                : refine_Y<__nv_bfloat16>(x, U_out, B, T, C, Y_out, st))) return e;
+  row_sigma_kernel<<<(unsigned)((B * n + 7) / 8), 256, 0, st>>>(Y_out, U_out, B * n, int(n), int(m), sigma_out);
+  R3D_LAUNCH_CHECK();
+  erank_entropy_kernel<<<(unsigned)B, 256, 0, st>>>(sigma_out, int(n), rtol, erank_out);
+  R3D_LAUNCH_CHECK();
+  return 0;
+}
+
+template <typename T>
+static int bwd_gemm(const float* Ut, const float* Y, const float* coef, int64_t B, int64_t Tt, int64_t C, void* dx,
+                    int accumulate, cudaStream_t st) {
+  int64_t n, m; bool ts; side(Tt, C, n, m, ts);
+  T* D = (T*)dx;
+  if (ts)   // dX[t,c] = sum_j Ut[j,t] coef_j Y[j,c]   : a(t,j)=Ut[j*n+t] (TRANS_A), b(j,c)=Y[j*m+c]
+    return sgemm_launch<float, float, T>(true, false, Ut, Y, D, int(Tt), int(C), int(n), n, m, C, n * n, n * m, Tt * C,
+                                         coef, n, accumulate, int(B), st);
+  // C-side: dX[t,c] = sum_j Y[j,t] coef_j Ut[j,c]     : a(t,j)=Y[j*m+t] (TRANS_A), b(j,c)=Ut[j*n+c]
+  return sgemm_launch<float, float, T>(true, false, Y, Ut, D, int(Tt), int(C), int(n), m, n, C, n * m, n * n, Tt * C,
+                                       coef, n, accumulate, int(B), st);
+}
+
+extern "C" int r3d_erank_bwd(const float* g, const float* erank, const float* sigma, const float* U, const float* Y,
+                             int64_t B, int64_t T, int64_t C, int dtype, float rtol, void* workspace, void* dx,
+                             int accumulate, void* stream) {
+  R3D_CHECK(g && sigma && U && Y && workspace && dx, "null pointer");
+  R3D_CHECK(dtype == R3D_F32 || dtype == R3D_BF16, "bad dtype %d", dtype);
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t n, m; bool ts; side(T, C, n, m, ts);
+  char* p = (char*)workspace;
+  p = (char*)((uintptr_t(p) + 255) & ~uintptr_t(255));
+  p += size_t(B) * n * n * 4;
+  float* coef = (float*)p;
+  erank_coef_kernel<<<(unsigned)B, 256, 0, st>>>(sigma, g, int(n), rtol, coef);
+  R3D_LAUNCH_CHECK();
+  return dtype == R3D_F32 ? bwd_gemm<float>(U, Y, coef, B, T, C, dx, accumulate, st)
+                          : bwd_gemm<__nv_bfloat16>(U, Y, coef, B, T, C, dx, accumulate, st);
+}
+
+extern "C" int r3d_token_informativeness(const float* sigma, const float* U, int64_t B, int64_t n, float rtol,
+                                         float* score_out, void* stream) {
+  R3D_CHECK(sigma && U && score_out, "null pointer");
+  R3D_CHECK(n >= 1 && n <= 8192, "bad n");
+  token_info_kernel<<<(unsigned)B, 256, size_t(n) * 4, (cudaStream_t)stream>>>(sigma, U, int(n), rtol, score_out);
+  R3D_LAUNCH_CHECK();
+  return 0;
+}

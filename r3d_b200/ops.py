@@ -1,0 +1,408 @@
+"""Host-side operators over the C ABI: thin, allocation + pointer plumbing only.
+
+PyTorch supplies device memory and the current stream; every computation is a
+hand-written sm_100a kernel in csrc/.  CPU tensors are rejected (no fallback).
+
+Public surface (also registered as ``torch.ops.r3d.*``):
+  channel_score, bottomk, exchange (autograd), token_fusion_bn (autograd),
+  erank (autograd), gram, jacobi_eigh, token_informativeness.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import R3DError, check
+
+BLEND_SWAP, BLEND_SCALE, BLEND_CONVEX = 0, 1, 2
+DEFAULT_RTOL = 1e-4
+_DT = {torch.float32: 0, torch.bfloat16: 1}
+
+
+def _p(t: Optional[torch.Tensor]):
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise R3DError("r3d_b200 operators run on CUDA tensors only (no CPU fallback); got device "
+                           f"{t.device}")
+
+
+def _dt(t: torch.Tensor) -> int:
+    if t.dtype not in _DT:
+        raise R3DError(f"dtype must be float32 or bfloat16, got {t.dtype}")
+    return _DT[t.dtype]
+
+
+def _btc(rgb: torch.Tensor, depth: torch.Tensor):
+    if rgb.dim() != 3 or depth.dim() != 3:
+        raise R3DError(f"expected (B, T, C) tensors, got {tuple(rgb.shape)} and {tuple(depth.shape)}")
+    if rgb.shape != depth.shape or rgb.dtype != depth.dtype or rgb.device != depth.device:
+        raise R3DError("rgb and depth must agree in shape, dtype and device: "
+                       f"{tuple(rgb.shape)} {rgb.dtype} {rgb.device} vs {tuple(depth.shape)} {depth.dtype} {depth.device}")
+    return rgb.contiguous(), depth.contiguous()
+
+
+# ---------------------------------------------------------------------------------
+# a1: channel score            (reference: model/futr_safuser_tokenfusion.py:49-50)
+# ---------------------------------------------------------------------------------
+def channel_score_sums(rgb: torch.Tensor, depth: torch.Tensor) -> torch.Tensor:
+    """Column sums of |x| for both modalities, (2, C) float32 (not divided by rows)."""
+    _need_cuda(rgb, depth)
+    rgb, depth = _btc(rgb, depth)
+    B, T, C = rgb.shape
+    rows = B * T
+    L = _lib.lib()
+    with torch.cuda.device(rgb.device):
+        ws = torch.empty(L.r3d_score_workspace_floats(rows, C), dtype=torch.float32, device=rgb.device)
+        sums = torch.empty(2, C, dtype=torch.float32, device=rgb.device)
+        check(L.r3d_channel_score_partial(_p(rgb), _p(depth), rows, C, _dt(rgb), _p(ws), _stream()))
+        check(L.r3d_score_finalize(_p(ws), max(rows, 1), C, _p(sums), None, _stream()))
+    return sums
+
+
+def channel_score(rgb: torch.Tensor, depth: torch.Tensor) -> torch.Tensor:
+    """(2, C) float32: row 0 = rgb.abs().mean((0,1)), row 1 = depth.abs().mean((0,1))."""
+    _need_cuda(rgb, depth)
+    rgb, depth = _btc(rgb, depth)
+    B, T, C = rgb.shape
+    rows = B * T
+    L = _lib.lib()
+    with torch.cuda.device(rgb.device):
+        ws = torch.empty(L.r3d_score_workspace_floats(rows, C), dtype=torch.float32, device=rgb.device)
+        score = torch.empty(2, C, dtype=torch.float32, device=rgb.device)
+        check(L.r3d_channel_score_partial(_p(rgb), _p(depth), rows, C, _dt(rgb), _p(ws), _stream()))
+        check(L.r3d_score_finalize(_p(ws), max(rows, 1), C, None, _p(score), _stream()))
+    return score
+
+
+# ---------------------------------------------------------------------------------
+# a4: bottom-k                 (reference: model/futr_safuser_tokenfusion.py:52-54)
+# ---------------------------------------------------------------------------------
+def bottomk(score: torch.Tensor, k: int) -> torch.Tensor:
+    """score (..., C) float32 -> (..., k) int64: ascending score, ties -> lower index."""
+    _need_cuda(score)
+    if score.dtype != torch.float32:
+        raise R3DError("bottomk scores must be float32")
+    C = score.shape[-1]
+    s2 = score.reshape(-1, C).contiguous()
+    out = torch.empty(s2.shape[0], k, dtype=torch.int64, device=score.device)
+    with torch.cuda.device(score.device):
+        check(_lib.lib().r3d_bottomk(_p(s2), s2.shape[0], C, k, _p(out), _stream()))
+    return out.reshape(*score.shape[:-1], k)
+
+
+# ---------------------------------------------------------------------------------
+# a5-a8: exchange / blend with autograd
+# ---------------------------------------------------------------------------------
+def _exchange_fwd_raw(rgb, depth, idx_r, idx_d, alpha, affine, blend):
+    B, T, C = rgb.shape
+    out = torch.empty(B, T, 2, C, dtype=rgb.dtype, device=rgb.device)
+    k = idx_r.numel()
+    with torch.cuda.device(rgb.device):
+        check(_lib.lib().r3d_exchange_fwd(_p(rgb), _p(depth), _p(idx_r), _p(idx_d), k, _p(alpha), _p(affine), blend,
+                                          _p(out), B * T, C, _dt(rgb), _stream()))
+    return out
+
+
+def _exchange_bwd_raw(g, rgb, depth, idx_r, idx_d, alpha, affine, bn_norm, blend):
+    B, T, two, C = g.shape
+    rows = B * T
+    L = _lib.lib()
+    d_rgb = torch.empty(B, T, C, dtype=g.dtype, device=g.device)
+    d_dep = torch.empty(B, T, C, dtype=g.dtype, device=g.device)
+    colsums = None
+    with torch.cuda.device(g.device):
+        ws = None
+        if blend != BLEND_SWAP:
+            ws = torch.empty(L.r3d_exchange_bwd_workspace_floats(rows, C), dtype=torch.float32, device=g.device)
+        check(L.r3d_exchange_bwd(_p(g), _p(rgb), _p(depth), _p(idx_r), _p(idx_d), idx_r.numel(), _p(alpha),
+                                 _p(affine), _p(bn_norm), blend, _p(d_rgb), _p(d_dep), _p(ws), rows, C, _dt(g),
+                                 _stream()))
+        if blend != BLEND_SWAP:
+            colsums = torch.zeros(5, C, dtype=torch.float32, device=g.device)
+            if bn_norm is None:
+                # only the d_alpha row was written by the kernel
+                ws[L.r3d_exchange_bwd_workspace_floats(rows, C) // 5:].zero_()
+            check(L.r3d_exchange_bwd_finalize(_p(ws), max(rows, 1), C, _p(colsums), _stream()))
+    return d_rgb, d_dep, colsums
+
+
+class _Exchange(torch.autograd.Function):
+    """exchange + stack (swap / alpha-scaled / convex), no BatchNorm front end."""
+
+    @staticmethod
+    def forward(ctx, rgb, depth, idx_r, idx_d, alpha, blend):
+        ctx.blend = blend
+        a = None if alpha is None else alpha.detach().reshape(-1).float().contiguous()
+        out = _exchange_fwd_raw(rgb, depth, idx_r, idx_d, a, None, blend)
+        if blend == BLEND_SWAP:
+            ctx.save_for_backward(idx_r, idx_d)
+        else:
+            ctx.save_for_backward(idx_r, idx_d, rgb, depth, a)
+        ctx.alpha_shape = None if alpha is None else alpha.shape
+        ctx.alpha_dtype = None if alpha is None else alpha.dtype
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous()
+        if ctx.blend == BLEND_SWAP:
+            idx_r, idx_d = ctx.saved_tensors
+            d_rgb, d_dep, _ = _exchange_bwd_raw(g, None, None, idx_r, idx_d, None, None, None, BLEND_SWAP)
+            return d_rgb, d_dep, None, None, None, None
+        idx_r, idx_d, rgb, depth, a = ctx.saved_tensors
+        d_rgb, d_dep, colsums = _exchange_bwd_raw(g, rgb, depth, idx_r, idx_d, a, None, None, ctx.blend)
+        d_alpha = colsums[0].reshape(ctx.alpha_shape).to(ctx.alpha_dtype)
+        return d_rgb, d_dep, None, None, d_alpha, None
+
+
+def exchange(rgb, depth, idx_r, idx_d, alpha=None, blend=BLEND_SWAP) -> torch.Tensor:
+    """(B,T,C) x2 + index sets -> stacked (B,T,2,C); differentiable in rgb, depth, alpha."""
+    _need_cuda(rgb, depth, idx_r, idx_d, alpha)
+    rgb, depth = _btc(rgb, depth)
+    _dt(rgb)
+    if blend != BLEND_SWAP and alpha is None:
+        raise R3DError("alpha is required for the scale / convex blends")
+    idx_r = idx_r.reshape(-1).to(torch.int64).contiguous()
+    idx_d = idx_d.reshape(-1).to(torch.int64).contiguous()
+    if idx_r.numel() != idx_d.numel():
+        raise R3DError("idx_r and idx_d must have the same length")
+    return _Exchange.apply(rgb, depth, idx_r, idx_d, alpha, blend)
+
+
+# ---------------------------------------------------------------------------------
+# a3 + a7: BatchNorm front end fused with the convex blend
+# (reference: model/futr_safuser_batchnormalization.py:45-46, 62-75)
+# ---------------------------------------------------------------------------------
+def bn_batch_stats(rgb, depth) -> torch.Tensor:
+    """(2 modalities, 3, C) float32: [mean, biased var, unbiased var] over the B*T rows."""
+    _need_cuda(rgb, depth)
+    rgb, depth = _btc(rgb, depth)
+    B, T, C = rgb.shape
+    L = _lib.lib()
+    with torch.cuda.device(rgb.device):
+        ws = torch.empty(L.r3d_bn_workspace_floats(B * T, C), dtype=torch.float32, device=rgb.device)
+        stats = torch.empty(2, 3, C, dtype=torch.float32, device=rgb.device)
+        check(L.r3d_bn_stats(_p(rgb), _p(depth), B * T, C, _dt(rgb), _p(ws), _p(stats), _stream()))
+    return stats
+
+
+class _TokenFusionBN(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, rgb, depth, alpha, w_r, b_r, w_d, b_d, mean, var, idx_r, idx_d, eps, batch_stats):
+        # mean/var: (2, C) statistics actually used for normalisation
+        rstd = torch.rsqrt(var + eps)
+        w = torch.stack([w_r.detach().float(), w_d.detach().float()])
+        b = torch.stack([b_r.detach().float(), b_d.detach().float()])
+        scale = w * rstd
+        affine = torch.stack([scale, b - mean * scale], dim=1).contiguous()        # (2, 2, C)
+        bn_norm = torch.stack([rstd, -mean * rstd], dim=1).contiguous()            # (2, 2, C)
+        a = alpha.detach().reshape(-1).float().contiguous()
+        out = _exchange_fwd_raw(rgb, depth, idx_r, idx_d, a, affine, BLEND_CONVEX)
+        ctx.save_for_backward(rgb, depth, a, affine, bn_norm, idx_r, idx_d, w)
+        ctx.batch_stats = batch_stats
+        ctx.alpha_shape = alpha.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        rgb, depth, a, affine, bn_norm, idx_r, idx_d, w = ctx.saved_tensors
+        g = g.contiguous()
+        d_rgb, d_dep, cs = _exchange_bwd_raw(g, rgb, depth, idx_r, idx_d, a, affine, bn_norm, BLEND_CONVEX)
+        d_alpha = cs[0].reshape(ctx.alpha_shape)
+        d_w_r, d_b_r, d_w_d, d_b_d = cs[2], cs[1], cs[4], cs[3]
+        B, T, C = rgb.shape
+        sums = cs if ctx.batch_stats else torch.zeros_like(cs)   # running stats: no dependence on the batch
+        with torch.cuda.device(g.device):
+            check(_lib.lib().r3d_bn_bwd_apply(_p(rgb), _p(depth), _p(bn_norm), _p(w[0].contiguous()),
+                                              _p(w[1].contiguous()), _p(sums), _p(d_rgb), _p(d_dep), B * T, C,
+                                              _dt(rgb), _stream()))
+        return d_rgb, d_dep, d_alpha, d_w_r, d_b_r, d_w_d, d_b_d, None, None, None, None, None, None
+
+
+def token_fusion_bn(rgb, depth, alpha, w_r, b_r, w_d, b_d, mean, var, idx_r, idx_d, eps=1e-5, batch_stats=True):
+    _need_cuda(rgb, depth, alpha, w_r, w_d, mean, var)
+    rgb, depth = _btc(rgb, depth)
+    return _TokenFusionBN.apply(rgb, depth, alpha, w_r, b_r, w_d, b_d, mean.float(), var.float(),
+                                idx_r.reshape(-1).contiguous(), idx_d.reshape(-1).contiguous(), eps, batch_stats)
+
+
+# ---------------------------------------------------------------------------------
+# a12: effective rank (no reference symbol)
+# ---------------------------------------------------------------------------------
+GRAM_TCGEN05, GRAM_SIMT = 0, 1
+
+
+def _erank_fwd_raw(x, rtol, gram_impl):
+    B, T, C = x.shape
+    n, m = min(T, C), max(T, C)
+    L = _lib.lib()
+    dev = x.device
+    with torch.cuda.device(dev):
+        ws = torch.empty(L.r3d_erank_workspace_bytes(B, T, C, _dt(x)), dtype=torch.uint8, device=dev)
+        er = torch.empty(B, dtype=torch.float32, device=dev)
+        sigma = torch.empty(B, n, dtype=torch.float32, device=dev)
+        U = torch.empty(B, n, n, dtype=torch.float32, device=dev)
+        Y = torch.empty(B, n, m, dtype=torch.float32, device=dev)
+        sweeps = torch.empty(B, dtype=torch.int32, device=dev)
+        check(L.r3d_erank_fwd(_p(x), B, T, C, _dt(x), rtol, gram_impl, _p(ws), _p(er), _p(sigma), _p(U), _p(Y),
+                              _p(sweeps), _stream()))
+    return er, sigma, U, Y, sweeps
+
+
+class _ERank(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, rtol, gram_impl):
+        er, sigma, U, Y, sweeps = _erank_fwd_raw(x, rtol, gram_impl)
+        ctx.save_for_backward(er, sigma, U, Y)
+        ctx.shape = x.shape
+        ctx.dtype = x.dtype
+        ctx.rtol = rtol
+        ctx.mark_non_differentiable(sigma, sweeps)
+        return er, sigma, sweeps
+
+    @staticmethod
+    def backward(ctx, g, _gs, _gw):
+        er, sigma, U, Y = ctx.saved_tensors
+        B, T, C = ctx.shape
+        L = _lib.lib()
+        dev = er.device
+        dt = _DT[ctx.dtype]
+        with torch.cuda.device(dev):
+            ws = torch.empty(L.r3d_erank_workspace_bytes(B, T, C, dt), dtype=torch.uint8, device=dev)
+            dx = torch.empty(B, T, C, dtype=ctx.dtype, device=dev)
+            gg = g.contiguous().float()
+            check(L.r3d_erank_bwd(_p(gg), _p(er), _p(sigma), _p(U), _p(Y), B, T, C, dt, ctx.rtol, _p(ws), _p(dx), 0,
+                                  _stream()))
+        return dx, None, None
+
+
+def erank(x: torch.Tensor, rtol: float = DEFAULT_RTOL, gram_impl: int = GRAM_TCGEN05, return_aux: bool = False):
+    """Per-sample effective rank of x (B, T, C) -> (B,) float32, differentiable in x.
+
+    exp(-sum p ln p), p = sigma / sum sigma over the singular values of each (T, C)
+    sample; sigma <= rtol * sigma_max are treated as zero."""
+    _need_cuda(x)
+    if x.dim() != 3:
+        raise R3DError(f"expected (B, T, C), got {tuple(x.shape)}")
+    _dt(x)
+    er, sigma, sweeps = _ERank.apply(x.contiguous(), float(rtol), int(gram_impl))
+    if return_aux:
+        return er, sigma, sweeps
+    return er
+
+
+def gram(x: torch.Tensor, gram_impl: int = GRAM_TCGEN05) -> torch.Tensor:
+    """(B, T, C) -> (B, n, n) float32 Gram on the smaller side (X X^T if T <= C else X^T X)."""
+    _need_cuda(x)
+    x = x.contiguous()
+    B, T, C = x.shape
+    n = min(T, C)
+    L = _lib.lib()
+    with torch.cuda.device(x.device):
+        ws = torch.empty(L.r3d_erank_workspace_bytes(B, T, C, _dt(x)), dtype=torch.uint8, device=x.device)
+        G = torch.empty(B, n, n, dtype=torch.float32, device=x.device)
+        check(L.r3d_gram(_p(x), B, T, C, _dt(x), gram_impl, _p(ws), _p(G), _stream()))
+    return G
+
+
+def jacobi_eigh(G: torch.Tensor, max_sweeps: int = 30) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Symmetric PSD (B, n, n) float32 -> (lambda (B, n), U (B, n, n), sweeps (B,)).  Solver order."""
+    _need_cuda(G)
+    if G.dtype != torch.float32 or G.dim() != 3 or G.shape[1] != G.shape[2]:
+        raise R3DError("jacobi_eigh expects (B, n, n) float32")
+    G = G.contiguous()
+    B, n, _ = G.shape
+    L = _lib.lib()
+    with torch.cuda.device(G.device):
+        ws = torch.empty(L.r3d_jacobi_workspace_bytes(B, n), dtype=torch.uint8, device=G.device)
+        lam = torch.empty(B, n, dtype=torch.float32, device=G.device)
+        U = torch.empty(B, n, n, dtype=torch.float32, device=G.device)
+        sw = torch.empty(B, dtype=torch.int32, device=G.device)
+        check(L.r3d_jacobi_eigh(_p(G), B, n, _p(ws), _p(lam), _p(U), _p(sw), max_sweeps, _stream()))
+    return lam, U, sw
+
+
+def token_informativeness(sigma: torch.Tensor, U: torch.Tensor, rtol: float = DEFAULT_RTOL) -> torch.Tensor:
+    """s_t = sum_j p_j U[t, j]^2 over the short side (B, n)."""
+    _need_cuda(sigma, U)
+    B, n = sigma.shape
+    out = torch.empty(B, n, dtype=torch.float32, device=sigma.device)
+    with torch.cuda.device(sigma.device):
+        check(_lib.lib().r3d_token_informativeness(_p(sigma.contiguous()), _p(U.contiguous()), B, n, rtol, _p(out),
+                                                   _stream()))
+    return out
+
+
+def token_fusion_host(rgb: torch.Tensor, depth: torch.Tensor, k: int):
+    """Host-buffer entry (pinned CPU tensors in, pinned CPU tensors out) through the
+    C ABI's r3d_token_fusion_host: the `e2e` measurement path."""
+    if rgb.is_cuda or depth.is_cuda:
+        raise R3DError("token_fusion_host takes host tensors")
+    B, T, C = rgb.shape
+    out = torch.empty(B, T, 2, C, dtype=rgb.dtype).pin_memory()
+    idx = torch.empty(2, max(k, 1), dtype=torch.int64).pin_memory()
+    check(_lib.lib().r3d_token_fusion_host(_p(rgb), _p(depth), B, T, C, _dt(rgb), k, _p(out), _p(idx[0]), _p(idx[1]),
+                                           _stream()))
+    return out, idx[:, :k]
+
+
+# ---------------------------------------------------------------------------------
+# torch.ops.r3d.* registration.  Thin wrappers over the functions above.
+# ---------------------------------------------------------------------------------
+def _register():
+    try:
+        from torch.library import custom_op
+    except Exception:  # pragma: no cover
+        return
+
+    @custom_op("r3d::channel_score", mutates_args=(), device_types="cuda")
+    def _cs(rgb: torch.Tensor, depth: torch.Tensor) -> torch.Tensor:
+        return channel_score(rgb, depth)
+
+    @_cs.register_fake
+    def _(rgb, depth):
+        return rgb.new_empty((2, rgb.shape[-1]), dtype=torch.float32)
+
+    @custom_op("r3d::bottomk", mutates_args=(), device_types="cuda")
+    def _bk(score: torch.Tensor, k: int) -> torch.Tensor:
+        return bottomk(score, k)
+
+    @_bk.register_fake
+    def _(score, k):
+        return score.new_empty((*score.shape[:-1], k), dtype=torch.int64)
+
+    @custom_op("r3d::exchange_fwd", mutates_args=(), device_types="cuda")
+    def _ef(rgb: torch.Tensor, depth: torch.Tensor, idx_r: torch.Tensor, idx_d: torch.Tensor,
+            alpha: Optional[torch.Tensor], blend_mode: int) -> torch.Tensor:
+        a = None if alpha is None else alpha.reshape(-1).float().contiguous()
+        return _exchange_fwd_raw(rgb.contiguous(), depth.contiguous(), idx_r.contiguous(), idx_d.contiguous(), a,
+                                 None, blend_mode)
+
+    @_ef.register_fake
+    def _(rgb, depth, idx_r, idx_d, alpha, blend_mode):
+        B, T, C = rgb.shape
+        return rgb.new_empty((B, T, 2, C))
+
+    @custom_op("r3d::erank", mutates_args=(), device_types="cuda")
+    def _er(x: torch.Tensor, rtol: float) -> torch.Tensor:
+        return _erank_fwd_raw(x.contiguous(), rtol, GRAM_TCGEN05)[0]
+
+    @_er.register_fake
+    def _(x, rtol):
+        return x.new_empty((x.shape[0],), dtype=torch.float32)
+
+
+_register()
