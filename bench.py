@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""bench.py -- fused clips/sec of the R3D token-fuser + effective-rank hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[1], the config the metric is quoted on): per GPU,
+B=64 clips of RGB+depth features, T=512 tokens, C=512 channels, bf16.  One "step" is
+one pass of the hot path over that batch, forward and backward:
+    erank(rgb), erank(depth)  [Gram -> block Jacobi -> refinement -> entropy/exp]
+    channel score -> [all-reduce] -> bottom-k -> exchange/stack           (forward)
+    exchange backward of an upstream gradient + d(mean erank)/dX accumulated (backward)
+N > 1: one process per GPU (torchrun), batch-sharded (weak scaling); the only
+collective is one all-reduce of the packed (2C + 2)-float score/erank statistic.
+
+`value`  : clips/s with inputs resident in HBM (CUDA events, max over ranks).
+`e2e`    : same metric with each step's inputs copied from pinned host memory and the
+           step's erank statistic read back, inside the timed region.
+`--impl reference`: the reference's CPU path (torch-CPU port of the reference fuser in
+           oracle/torch_port.py + the svdvals erank restatement) on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "fused clips/sec (eff-rank+token-fuse fwd/bwd)"
+UNIT = "clips/s"
+B, T, C = 64, 512, 512
+NSETS = 4   # rotating input sets: 4 x (67 MB inputs + 67 MB upstream grad) >> 126 MB L2
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-sample", type=int, default=16, help="clips per CPU-baseline step")
+    ap.add_argument("--gram", default="auto", choices=["auto", "tcgen05", "simt"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def synth_host(seed, b, dtype):
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    c = torch.arange(C, dtype=torch.float32)
+    rgb = torch.relu(torch.randn(b, T, C, generator=g)) * (1 + c / C)
+    dep = torch.relu(torch.randn(b, T, C, generator=g)) * (2 - c / C)
+    return torch.stack([rgb, dep]).to(dtype)      # (2, b, T, C)
+
+
+# ------------------------------------------------------------------------------------
+# CPU leg: the reference's own algorithm on the host cores (oracle port; "kind": "port")
+# ------------------------------------------------------------------------------------
+def cpu_step_factory(sample):
+    import torch
+    from oracle.torch_port import PortCMFuser, erank_torch
+    torch.set_num_threads(os.cpu_count() or 1)
+    fuser = PortCMFuser(C, depth=1, num_heads=8, variant="tokenfusion")
+    buf = synth_host(1234, sample, torch.bfloat16).float()     # fp32 on the bf16-rounded inputs
+    gst = torch.randn(sample, T, 2, C, generator=torch.Generator().manual_seed(4321))
+
+    def step():
+        rgb = buf[0].clone().requires_grad_(True)
+        dep = buf[1].clone().requires_grad_(True)
+        st = fuser.token_fusion(rgb, dep, "test")
+        er = torch.cat([erank_torch(rgb), erank_torch(dep)])
+        torch.autograd.backward([st, er], [gst, torch.full_like(er, 1.0 / er.numel())])
+        return float(er.detach().mean())
+
+    return step
+
+
+def run_cpu(steps, warmup, sample):
+    step = cpu_step_factory(sample)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return sample * steps / dt, dt / steps * 1e3
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    sample = args.cpu_sample
+    val, ms = run_cpu(args.steps, args.warmup, sample)
+    cores = torch.get_num_threads()
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"DARai RGB+depth fuser fwd+bwd, T={T}, C={C} (BASELINE.json configs[1]); CPU step = "
+                               f"{sample} clips of that shape", "B_per_step": sample, "T": T, "C": C},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{sample} clips/step x {args.steps} steps: torch-CPU port of the reference "
+                                   "token_fusion fwd+bwd + svdvals erank restatement fwd+bwd, fp32"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                       str(self.idx), "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.f.read().splitlines():
+            parts = [x.strip() for x in ln.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1])); mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        self.f.close()
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        if sm:
+            sm.sort()
+            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained":
+                d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+def stage_table(prof, steps, world):
+    """Per-stage algorithmic bytes / flops per launch -> achieved and fraction of peak."""
+    pk = peaks()
+    es = 2                       # bf16 inputs
+    N = B * T * C                # elements per modality per rank
+    n = min(T, C); m = max(T, C); nb2 = 2 * B
+    npad = ((n + 63) // 64) * 64
+    alg = {
+        "score_partial": ("hbm", 2 * N * es),
+        "exchange_fwd": ("hbm", 4 * N * es),
+        "exchange_bwd": ("hbm", 4 * N * es),
+        "gram": ("tensor", 2.0 * n * n * m * nb2),
+        "refine_y": ("tensor", 2.0 * n * n * m * nb2),
+        "bwd_gemm": ("tensor", 2.0 * n * n * m * nb2),
+        # one round: read+write every G and Vt tile once
+        "jacobi_update": ("hbm", nb2 * (2 * npad * npad * 4) * 2),
+        "sigma": ("hbm", nb2 * (n * m + n * n) * 4),
+    }
+    out = {}
+    for name, rec in prof.items():
+        launches = max(rec["launches"], 1)
+        avg_ms = rec["ms"] / launches
+        e = {"ms_per_step": rec["ms"] / steps, "launches_per_step": rec["launches"] / steps, "avg_launch_us": avg_ms * 1e3}
+        if name in alg and avg_ms > 0:
+            bound, work = alg[name]
+            if bound == "hbm":
+                ach = work / (avg_ms * 1e-3) / 1e9
+                e.update(bound="hbm", achieved=ach, unit="GB/s", peak=pk["hbm_gbs"], frac=ach / pk["hbm_gbs"])
+            else:
+                ach = work / (avg_ms * 1e-3) / 1e12
+                e.update(bound="tensor", achieved=ach, unit="TFLOP/s", peak=pk["bf16_tflops_sustained"],
+                         frac=ach / pk["bf16_tflops_sustained"])
+        out[name] = e
+    return out, pk
+
+
+def main_ours(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    import r3d_b200
+    from r3d_b200 import _lib, ops
+
+    dtype = torch.bfloat16
+    gram_impl = {"auto": ops.GRAM_TCGEN05, "tcgen05": ops.GRAM_TCGEN05, "simt": ops.GRAM_SIMT}[args.gram]
+    step = ops.FuserStep(B, T, C, dtype, dev, gram_impl=gram_impl)
+    host_in = [synth_host(1234 + rank * 100 + i, B, dtype).pin_memory() for i in range(NSETS)]
+    dev_in = [h.to(dev) for h in host_in]
+    gg = torch.Generator(device=dev).manual_seed(4321 + rank)
+    dev_g = [torch.randn(B, T, 2, C, generator=gg, device=dev).to(dtype) for _ in range(NSETS)]
+    stage_buf = torch.empty_like(dev_in[0])
+    er_host = torch.empty(2 * B, dtype=torch.float32).pin_memory()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    def resident(i):
+        step(dev_in[i % NSETS], dev_g[i % NSETS])
+
+    def end_to_end(i):
+        stage_buf.copy_(host_in[i % NSETS], non_blocking=True)          # H2D of this step's inputs
+        _, er, _ = step(stage_buf, dev_g[i % NSETS])
+        er_host.copy_(er, non_blocking=True)                            # D2H of the step's statistic
+        torch.cuda.current_stream().synchronize()
+
+    for i in range(max(args.warmup, 3)):
+        resident(i)
+    # ---- timed region (stage events on the launching stream are recorded inside it)
+    _lib.profile_enable(True)
+    _lib.profile_read(reset=True)
+    _lib.launch_count(reset=True)
+    clocks = ClockSampler(local) if rank == 0 else None
+    if clocks:
+        clocks.start()
+    ms = timed(resident, args.steps)
+    launches = _lib.launch_count(reset=True)
+    prof = _lib.profile_read(reset=True)
+    _lib.profile_enable(False)
+    clk = clocks.stop() if clocks else None
+    sweeps = step.sweeps.float().mean().item()
+    er_mean = step.er.mean().item()
+    # ---- end to end
+    for i in range(2):
+        end_to_end(i)
+    ms_e2e = timed(end_to_end, args.steps)
+
+    value = world * B * args.steps / (ms * 1e-3)
+    e2e = world * B * args.steps / (ms_e2e * 1e-3)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    stages, pk = stage_table(prof, args.steps, world)
+    dom = max(stages.items(), key=lambda kv: kv[1]["ms_per_step"])
+    dname, d = dom
+    roofline = {"kernel": dname, "bound": d.get("bound", "hbm"), "achieved": d.get("achieved"),
+                "peak": d.get("peak"), "unit": d.get("unit", "GB/s"), "frac": d.get("frac"),
+                "peak_source": pk["source"], "traffic": None,
+                "share_of_step": d["ms_per_step"] / (ms / args.steps)}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "DARai RGB+depth fuser fwd+bwd bf16 B=64 T=512 C=512 per GPU (BASELINE.json configs[1]): "
+                               "erank(rgb,depth) + score/bottom-k/exchange fwd + exchange/erank bwd",
+                   "B_per_gpu": B, "T": T, "C": C, "global_batch": B * world, "parallelism": f"dp{world}",
+                   "l2": f"{NSETS} rotating input+grad sets ({NSETS * 2 * 2 * B * T * C * 2 / 1e6:.0f} MB) > 126 MB L2",
+                   "jacobi_sweeps_mean": sweeps, "erank_mean": er_mean, "gram": args.gram},
+        "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+                "h2d_bytes_per_step": int(2 * B * T * C * 2), "d2h_bytes_per_step": int(2 * B * 4)},
+        "gpu_launches": int(launches),
+        "clocks": clk,
+        "roofline": roofline,
+        "stages": stages,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        val, cms = run_cpu(4, 1, args.cpu_sample)
+        line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                                "sample": f"{args.cpu_sample} clips/step x 4 steps (1 warm-up) of the same shape: "
+                                          "torch-CPU port of the reference token_fusion fwd+bwd + svdvals erank "
+                                          "restatement fwd+bwd, fp32 on the bf16-rounded inputs"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        main_reference(a)
+    else:
+        main_ours(a)

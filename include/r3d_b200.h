@@ -36,6 +36,13 @@ int r3d_abi_version(void);
 /* Number of kernels this library has launched from the calling thread since
  * the counter was last reset (bench.py's `gpu_launches`). */
 int64_t r3d_launch_count(int reset);
+/* Per-stage timing with CUDA events recorded on the launching stream (off by
+ * default).  r3d_profile_read synchronises the recorded events and returns, per
+ * stage, accumulated milliseconds, bracketed calls and kernel launches. */
+int r3d_profile_enable(int on);
+int r3d_profile_num_stages(void);
+const char* r3d_profile_stage_name(int stage);
+int r3d_profile_read(double* ms_out, int64_t* calls_out, int64_t* launches_out, int reset);
 
 /* ---- a1: channel score ---------------------------------------------------
  * Replaces  x.abs().mean(dim=(0,1))  for both modalities in one launch:

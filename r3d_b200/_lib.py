@@ -20,6 +20,10 @@ SIGNATURES = {
     "r3d_last_error": (c_char_p, []),
     "r3d_abi_version": (c_int, []),
     "r3d_launch_count": (c_int64, [c_int]),
+    "r3d_profile_enable": (c_int, [c_int]),
+    "r3d_profile_num_stages": (c_int, []),
+    "r3d_profile_stage_name": (c_char_p, [c_int]),
+    "r3d_profile_read": (c_int, [c_void_p, c_void_p, c_void_p, c_int]),
     "r3d_score_workspace_floats": (c_size_t, [c_int64, c_int64]),
     "r3d_channel_score_partial": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p]),
     "r3d_score_finalize": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
@@ -78,3 +82,22 @@ def check(rc: int):
 
 def launch_count(reset: bool = False) -> int:
     return int(lib().r3d_launch_count(1 if reset else 0))
+
+
+def profile_enable(on: bool = True) -> bool:
+    return bool(lib().r3d_profile_enable(1 if on else 0))
+
+
+def profile_read(reset: bool = True) -> dict:
+    """{stage: {"ms": total, "calls": n, "launches": k}} for stages that ran."""
+    L = lib()
+    n = L.r3d_profile_num_stages()
+    ms = (ctypes.c_double * n)()
+    calls = (ctypes.c_int64 * n)()
+    kl = (ctypes.c_int64 * n)()
+    check(L.r3d_profile_read(ms, calls, kl, 1 if reset else 0))
+    out = {}
+    for i in range(n):
+        if calls[i]:
+            out[L.r3d_profile_stage_name(i).decode()] = {"ms": ms[i], "calls": int(calls[i]), "launches": int(kl[i])}
+    return out

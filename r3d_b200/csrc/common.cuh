@@ -14,6 +14,22 @@ constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
 
+// ---- optional per-stage timing (CUDA events on the launching stream) -------------
+enum Stage {
+  ST_SCORE_PARTIAL = 0, ST_SCORE_FINALIZE, ST_BOTTOMK, ST_EXCHANGE_FWD, ST_EXCHANGE_BWD, ST_COLSUM_FINALIZE,
+  ST_BN_STATS, ST_BN_BWD, ST_GRAM, ST_JACOBI_INIT, ST_JACOBI_INNER, ST_JACOBI_UPDATE, ST_JACOBI_EXTRACT,
+  ST_REFINE_Y, ST_SIGMA, ST_ENTROPY, ST_COEF, ST_BWD_GEMM, ST_TOKEN_INFO, ST_BLOCK, ST_NUM
+};
+bool profiling_enabled();
+void stage_begin(int stage, cudaStream_t st);
+void stage_end(int stage, cudaStream_t st);
+struct StageScope {
+  int stage; cudaStream_t st; bool on;
+  StageScope(int s, cudaStream_t t) : stage(s), st(t), on(profiling_enabled()) { if (on) stage_begin(stage, st); }
+  ~StageScope() { if (on) stage_end(stage, st); }
+};
+#define R3D_STAGE(id, st) r3d::StageScope _stage_scope_##id(r3d::id, st)
+
 #define R3D_CHECK(cond, ...)            \
   do {                                  \
     if (!(cond)) {                      \

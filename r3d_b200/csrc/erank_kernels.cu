@@ -386,23 +386,35 @@ __global__ void __launch_bounds__(256) jacobi_update_kernel(float* __restrict__ 
   }
 }
 
-// lambda = diag(Gp), Ut (n x n compact) = Vt[:n, :n]; sweeps = first sweep with zero significant rotations
-__global__ void jacobi_extract_kernel(const float* __restrict__ Gp, const float* __restrict__ Vt, int n, int np,
-                                      const int* __restrict__ cnt, int max_sweeps, float* __restrict__ lambda,
-                                      float* __restrict__ Ut, int* __restrict__ sweeps) {
+// lambda = diag(Gp); Ut (n x n compact) = rows of Vt[:n, :n] renormalised to unit length (fp32 rotation
+// products drift from orthonormal by ~1e-4 over a few thousand rotations); one warp per row.
+// sweeps = number of sweeps executed (the last one found nothing significant to rotate).
+__global__ void __launch_bounds__(256) jacobi_extract_kernel(const float* __restrict__ Gp,
+                                                             const float* __restrict__ Vt, int n, int np,
+                                                             const int* __restrict__ cnt, int max_sweeps,
+                                                             float* __restrict__ lambda, float* __restrict__ Ut,
+                                                             int* __restrict__ sweeps) {
   const int b = blockIdx.y;
   const float* gp = Gp + int64_t(b) * np * np;
   const float* vt = Vt + int64_t(b) * np * np;
-  const int64_t total = int64_t(n) * n;
-  for (int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; e < total; e += int64_t(gridDim.x) * blockDim.x) {
-    const int i = int(e / n), j = int(e % n);
-    if (Ut) Ut[int64_t(b) * n * n + e] = vt[int64_t(i) * np + j];
-    if (i == j && lambda) lambda[int64_t(b) * n + i] = gp[int64_t(i) * np + i];
+  const int lane = threadIdx.x & 31;
+  for (int i = blockIdx.x * 8 + (threadIdx.x >> 5); i < n; i += gridDim.x * 8) {
+    const float* row = vt + int64_t(i) * np;
+    float ss = 0.f;
+    for (int j = lane; j < n; j += 32) { const float v = row[j]; ss = fmaf(v, v, ss); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float inv = ss > 0.f ? rsqrtf(ss) : 0.f;
+    if (Ut) {
+      float* out = Ut + int64_t(b) * n * n + int64_t(i) * n;
+      for (int j = lane; j < n; j += 32) out[j] = row[j] * inv;
+    }
+    if (lambda && lane == 0) lambda[int64_t(b) * n + i] = gp[int64_t(i) * np + i];
   }
   if (blockIdx.x == 0 && threadIdx.x == 0 && sweeps) {
     int s = 0;
     while (s < max_sweeps && cnt[b * JMAX_SWEEPS + s] != 0) ++s;
-    sweeps[b] = s + (s < max_sweeps ? 1 : 0);   // sweeps executed (the last one found nothing to do)
+    sweeps[b] = s + (s < max_sweeps ? 1 : 0);
   }
 }
 
@@ -550,6 +562,7 @@ static int gram_simt(const void* x, int64_t B, int64_t Tt, int64_t C, float* G, 
   int64_t n, m; bool ts; side(Tt, C, n, m, ts);
   const T* X = (const T*)x;
   // T-side: G = X X^T  (a(i,k)=X[i*C+k], b(k,j)=X[j*C+k]);  C-side: G = X^T X (a(i,k)=X[k*C+i], b(k,j)=X[k*C+j])
+  R3D_STAGE(ST_GRAM, st);
   return sgemm_launch<T, T, float>(!ts, ts, X, X, G, int(n), int(n), int(m), C, C, n, Tt * C, Tt * C, n * n, nullptr,
                                    0, 0, int(B), st);
 }
@@ -572,6 +585,7 @@ static int jacobi_run(const float* G, int64_t B, int64_t n, void* workspace, flo
   const float tol = 1e-5f;
   {
     dim3 grid(std::min<int64_t>((int64_t(w.np) * w.np + 255) / 256, 64), (unsigned)B);
+    R3D_STAGE(ST_JACOBI_INIT, st);
     jacobi_init_kernel<<<grid, 256, 0, st>>>(G, int(n), w.np, w.Gp, w.Vt, w.cnt, w.nu);
     R3D_LAUNCH_CHECK();
   }
@@ -581,16 +595,23 @@ static int jacobi_run(const float* G, int64_t B, int64_t n, void* workspace, flo
   const int upd_tiles = w.nt * w.nt + w.nt * (w.np / JM);
   for (int sweep = 0; sweep < max_sweeps; ++sweep) {
     for (int r = 0; r < rounds; ++r) {
-      jacobi_inner_kernel<<<dim3(w.nt, (unsigned)B), 256, 0, st>>>(w.Gp, w.np, w.nb, w.nt, r, sweep, w.cnt, w.qflag,
-                                                                  w.Qb, tol, w.nu, 8);
-      R3D_LAUNCH_CHECK();
-      jacobi_update_kernel<<<dim3(upd_tiles, (unsigned)B), 256, upd_smem, st>>>(w.Gp, w.Vt, w.np, w.nb, w.nt, r, sweep,
-                                                                               w.cnt, w.qflag, w.Qb);
-      R3D_LAUNCH_CHECK();
+      {
+        R3D_STAGE(ST_JACOBI_INNER, st);
+        jacobi_inner_kernel<<<dim3(w.nt, (unsigned)B), 256, 0, st>>>(w.Gp, w.np, w.nb, w.nt, r, sweep, w.cnt, w.qflag,
+                                                                    w.Qb, tol, w.nu, 8);
+        R3D_LAUNCH_CHECK();
+      }
+      {
+        R3D_STAGE(ST_JACOBI_UPDATE, st);
+        jacobi_update_kernel<<<dim3(upd_tiles, (unsigned)B), 256, upd_smem, st>>>(w.Gp, w.Vt, w.np, w.nb, w.nt, r,
+                                                                                 sweep, w.cnt, w.qflag, w.Qb);
+        R3D_LAUNCH_CHECK();
+      }
     }
   }
   {
-    dim3 grid(std::min<int64_t>((n * n + 255) / 256, 64), (unsigned)B);
+    dim3 grid((unsigned)std::min<int64_t>((n + 7) / 8, 64), (unsigned)B);
+    R3D_STAGE(ST_JACOBI_EXTRACT, st);
     jacobi_extract_kernel<<<grid, 256, 0, st>>>(w.Gp, w.Vt, int(n), w.np, w.cnt, max_sweeps, lambda_out, U_out,
                                                 sweeps_out);
     R3D_LAUNCH_CHECK();
@@ -611,6 +632,7 @@ static int refine_Y(const void* x, const float* Ut, int64_t B, int64_t Tt, int64
   const T* X = (const T*)x;
   // T-side: Y[j,c] = sum_r Ut[j,r] X[r,c]          (NN)
   // C-side: Y[j,t] = sum_c Ut[j,c] X[t,c]          (NT)
+  R3D_STAGE(ST_REFINE_Y, st);
   return sgemm_launch<float, T, float>(false, !ts, Ut, X, Y, int(n), int(m), int(n), n, C, m, n * n, Tt * C, n * m,
                                        nullptr, 0, 0, int(B), st);
 }
@@ -635,10 +657,16 @@ extern "C" int r3d_erank_fwd(const void* x, int64_t B, int64_t T, int64_t C, int
   if (int e = jacobi_run(G, B, n, jws, nullptr, U_out, sweeps_out, 0, st)) return e;
   if (int e = (dtype == R3D_F32 ? refine_Y<float>(x, U_out, B, T, C, Y_out, st)
                                 : refine_Y<__nv_bfloat16>(x, U_out, B, T, C, Y_out, st))) return e;
-  row_sigma_kernel<<<(unsigned)((B * n + 7) / 8), 256, 0, st>>>(Y_out, U_out, B * n, int(n), int(m), sigma_out);
-  R3D_LAUNCH_CHECK();
-  erank_entropy_kernel<<<(unsigned)B, 256, 0, st>>>(sigma_out, int(n), rtol, erank_out);
-  R3D_LAUNCH_CHECK();
+  {
+    R3D_STAGE(ST_SIGMA, st);
+    row_sigma_kernel<<<(unsigned)((B * n + 7) / 8), 256, 0, st>>>(Y_out, U_out, B * n, int(n), int(m), sigma_out);
+    R3D_LAUNCH_CHECK();
+  }
+  {
+    R3D_STAGE(ST_ENTROPY, st);
+    erank_entropy_kernel<<<(unsigned)B, 256, 0, st>>>(sigma_out, int(n), rtol, erank_out);
+    R3D_LAUNCH_CHECK();
+  }
   return 0;
 }
 
@@ -647,6 +675,7 @@ static int bwd_gemm(const float* Ut, const float* Y, const float* coef, int64_t 
                     int accumulate, cudaStream_t st) {
   int64_t n, m; bool ts; side(Tt, C, n, m, ts);
   T* D = (T*)dx;
+  R3D_STAGE(ST_BWD_GEMM, st);
   if (ts)   // dX[t,c] = sum_j Ut[j,t] coef_j Y[j,c]   : a(t,j)=Ut[j*n+t] (TRANS_A), b(j,c)=Y[j*m+c]
     return sgemm_launch<float, float, T>(true, false, Ut, Y, D, int(Tt), int(C), int(n), n, m, C, n * n, n * m, Tt * C,
                                          coef, n, accumulate, int(B), st);
@@ -666,8 +695,11 @@ extern "C" int r3d_erank_bwd(const float* g, const float* erank, const float* si
   p = (char*)((uintptr_t(p) + 255) & ~uintptr_t(255));
   p += size_t(B) * n * n * 4;
   float* coef = (float*)p;
-  erank_coef_kernel<<<(unsigned)B, 256, 0, st>>>(sigma, g, int(n), rtol, coef);
-  R3D_LAUNCH_CHECK();
+  {
+    R3D_STAGE(ST_COEF, st);
+    erank_coef_kernel<<<(unsigned)B, 256, 0, st>>>(sigma, g, int(n), rtol, coef);
+    R3D_LAUNCH_CHECK();
+  }
   return dtype == R3D_F32 ? bwd_gemm<float>(U, Y, coef, B, T, C, dx, accumulate, st)
                           : bwd_gemm<__nv_bfloat16>(U, Y, coef, B, T, C, dx, accumulate, st);
 }
@@ -676,6 +708,7 @@ extern "C" int r3d_token_informativeness(const float* sigma, const float* U, int
                                          float* score_out, void* stream) {
   R3D_CHECK(sigma && U && score_out, "null pointer");
   R3D_CHECK(n >= 1 && n <= 8192, "bad n");
+  R3D_STAGE(ST_TOKEN_INFO, (cudaStream_t)stream);
   token_info_kernel<<<(unsigned)B, 256, size_t(n) * 4, (cudaStream_t)stream>>>(sigma, U, int(n), rtol, score_out);
   R3D_LAUNCH_CHECK();
   return 0;

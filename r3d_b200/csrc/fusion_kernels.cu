@@ -10,6 +10,8 @@
 //             ..._batchnormalization.py:45-46,62-75
 #include <stdarg.h>
 
+#include <vector>
+
 #include "common.cuh"
 
 namespace r3d {
@@ -24,6 +26,51 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void count_launch(int n) { g_launches += n; }
+
+// ---- stage timing -----------------------------------------------------------------
+struct StageRec { int stage; cudaEvent_t a, b; };
+static thread_local bool g_prof = false;
+static thread_local std::vector<StageRec>* g_recs = nullptr;
+static thread_local std::vector<cudaEvent_t>* g_pool = nullptr;
+static thread_local cudaEvent_t g_open[ST_NUM];
+static thread_local int64_t g_stage_launch0[ST_NUM];
+static thread_local double g_ms[ST_NUM];
+static thread_local int64_t g_cnt[ST_NUM];
+static thread_local int64_t g_kl[ST_NUM];
+
+bool profiling_enabled() { return g_prof; }
+static cudaEvent_t get_event() {
+  if (!g_pool) g_pool = new std::vector<cudaEvent_t>();
+  if (!g_pool->empty()) { cudaEvent_t e = g_pool->back(); g_pool->pop_back(); return e; }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+void stage_begin(int stage, cudaStream_t st) {
+  cudaEvent_t e = get_event();
+  cudaEventRecord(e, st);
+  g_open[stage] = e;
+  g_stage_launch0[stage] = g_launches;
+}
+void stage_end(int stage, cudaStream_t st) {
+  cudaEvent_t e = get_event();
+  cudaEventRecord(e, st);
+  if (!g_recs) g_recs = new std::vector<StageRec>();
+  g_recs->push_back({stage, g_open[stage], e});
+  g_cnt[stage] += 1;
+  g_kl[stage] += g_launches - g_stage_launch0[stage];
+}
+static void drain_records() {
+  if (!g_recs) return;
+  for (auto& r : *g_recs) {
+    cudaEventSynchronize(r.b);
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) g_ms[r.stage] += ms;
+    g_pool->push_back(r.a);
+    g_pool->push_back(r.b);
+  }
+  g_recs->clear();
+}
 
 // half-width bf16 vectors (8-byte accesses) for the register-heavy BN backward
 template <>
@@ -534,6 +581,29 @@ using namespace r3d;
 
 extern "C" const char* r3d_last_error(void) { return g_err; }
 extern "C" int r3d_abi_version(void) { return 1; }
+extern "C" int r3d_profile_enable(int on) {
+  const int prev = g_prof ? 1 : 0;
+  g_prof = on != 0;
+  return prev;
+}
+extern "C" int r3d_profile_num_stages(void) { return ST_NUM; }
+extern "C" const char* r3d_profile_stage_name(int stage) {
+  static const char* names[ST_NUM] = {"score_partial", "score_finalize", "bottomk", "exchange_fwd", "exchange_bwd",
+                                      "colsum_finalize", "bn_stats", "bn_bwd", "gram", "jacobi_init", "jacobi_inner",
+                                      "jacobi_update", "jacobi_extract", "refine_y", "sigma", "entropy", "coef",
+                                      "bwd_gemm", "token_info", "block"};
+  return (stage >= 0 && stage < ST_NUM) ? names[stage] : "?";
+}
+extern "C" int r3d_profile_read(double* ms_out, int64_t* calls_out, int64_t* launches_out, int reset) {
+  drain_records();
+  for (int i = 0; i < ST_NUM; ++i) {
+    if (ms_out) ms_out[i] = g_ms[i];
+    if (calls_out) calls_out[i] = g_cnt[i];
+    if (launches_out) launches_out[i] = g_kl[i];
+    if (reset) { g_ms[i] = 0; g_cnt[i] = 0; g_kl[i] = 0; }
+  }
+  return 0;
+}
 extern "C" int64_t r3d_launch_count(int reset) {
   int64_t v = g_launches;
   if (reset) g_launches = 0;
@@ -558,6 +628,7 @@ static int score_partial_t(const void* rgb, const void* depth, int64_t rows, int
   constexpr int VN = VecOf<T>::N;
   Grid2 g = make_grid(rows, C, vec ? VN : 1);
   dim3 grid(g.row_chunks, g.col_chunks, 2);
+  R3D_STAGE(ST_SCORE_PARTIAL, st);
   if (vec)
     score_partial_kernel<T, VN><<<grid, 256, 0, st>>>((const T*)rgb, (const T*)depth, rows, C, g.tx_log2,
                                                       g.rows_per_cta, partial);
@@ -582,6 +653,7 @@ extern "C" int r3d_score_finalize(const float* partial, int64_t rows, int64_t C,
   R3D_CHECK(partial != nullptr, "null workspace");
   R3D_CHECK(rows >= 1 && C >= 1, "bad shape");
   dim3 grid((unsigned)((C + 255) / 256), 2);
+  R3D_STAGE(ST_SCORE_FINALIZE, (cudaStream_t)stream);
   score_finalize_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(partial, fixed_row_chunks(rows), rows, C, sums_out,
                                                                score_out);
   R3D_LAUNCH_CHECK();
@@ -600,6 +672,7 @@ extern "C" int r3d_bottomk(const float* score, int nvec, int64_t C, int64_t k, i
   const size_t smem = size_t(n2) * sizeof(unsigned long long);
   if (smem > 48 * 1024)
     R3D_CUDA(cudaFuncSetAttribute(bottomk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  R3D_STAGE(ST_BOTTOMK, (cudaStream_t)stream);
   bottomk_kernel<<<nvec, threads, smem, (cudaStream_t)stream>>>(score, C, k, n2, idx_out);
   R3D_LAUNCH_CHECK();
   return 0;
@@ -616,6 +689,7 @@ static int bn_stats_t(const void* rgb, const void* depth, int64_t rows, int64_t 
   constexpr int VN = VecOf<T>::N;
   Grid2 g = make_grid(rows, C, vec ? VN : 1);
   dim3 grid(g.row_chunks, g.col_chunks, 2);
+  R3D_STAGE(ST_BN_STATS, st);
   if (vec)
     bn_partial_kernel<T, VN><<<grid, 256, 0, st>>>((const T*)rgb, (const T*)depth, rows, C, g.tx_log2, g.rows_per_cta, ws);
   else
@@ -643,6 +717,7 @@ static int exchange_fwd_v(const void* rgb, const void* depth, const int64_t* idx
                           cudaStream_t st) {
   Grid2 g = make_grid(rows, C, V);
   dim3 grid(g.row_chunks, g.col_chunks, 1);
+  R3D_STAGE(ST_EXCHANGE_FWD, st);
 #define R3D_FWD(BL, AF)                                                                                           \
   exchange_fwd_kernel<T, V, BL, AF><<<grid, 256, 0, st>>>((const T*)rgb, (const T*)depth, idx_r, idx_d, k, alpha, \
                                                           affine, (T*)out, rows, C, g.tx_log2, g.rows_per_cta)
@@ -692,6 +767,7 @@ static int exchange_bwd_v(const void* g, const void* rgb, const void* depth, con
                           int64_t C, cudaStream_t st) {
   Grid2 gg = make_grid(rows, C, V);
   dim3 grid(gg.row_chunks, gg.col_chunks, 1);
+  R3D_STAGE(ST_EXCHANGE_BWD, st);
 #define R3D_BWD(BL, AF, BN)                                                                                        \
   exchange_bwd_kernel<T, V, BL, AF, BN><<<grid, 256, 0, st>>>((const T*)g, (const T*)rgb, (const T*)depth, idx_r,  \
                                                               idx_d, k, alpha, affine, bn_norm, (T*)d_rgb,         \
@@ -749,6 +825,7 @@ extern "C" int r3d_exchange_bwd_finalize(const float* colsum_partial, int64_t ro
                                          void* stream) {
   R3D_CHECK(colsum_partial && colsums_out, "null pointer");
   dim3 grid((unsigned)((C + 255) / 256), 5);
+  R3D_STAGE(ST_COLSUM_FINALIZE, (cudaStream_t)stream);
   colsum_finalize_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(colsum_partial, fixed_row_chunks(rows), C,
                                                                 colsums_out);
   R3D_LAUNCH_CHECK();
@@ -760,6 +837,7 @@ static int bn_bwd_apply_t(const void* rgb, const void* depth, const float* bn_no
                           const float* colsums, void* d_rgb, void* d_depth, int64_t rows, int64_t C,
                           cudaStream_t st) {
   const bool vec = vec_ok<T>(rgb, C) && vec_ok<T>(depth, C) && vec_ok<T>(d_rgb, C) && vec_ok<T>(d_depth, C);
+  R3D_STAGE(ST_BN_BWD, st);
   if (vec) {
     Grid2 g = make_grid(rows, C, 4);
     dim3 grid(g.row_chunks, g.col_chunks, 2);

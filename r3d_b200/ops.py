@@ -406,3 +406,70 @@ def _register():
 
 
 _register()
+
+
+# ---------------------------------------------------------------------------------
+# One whole pass of the hot path over a batch, preallocated (what bench.py times):
+#   forward : erank(rgb), erank(depth) ; score -> [all-reduce] -> bottom-k -> exchange
+#   backward: exchange backward of an upstream gradient + d(mean erank)/dX, accumulated
+# ---------------------------------------------------------------------------------
+class FuserStep:
+    """Preallocated buffers + the call sequence for one fused fwd/bwd step on (2, B, T, C)
+    inputs (rgb = buf[0], depth = buf[1]).  Tokenfusion variant, eval-branch score."""
+
+    def __init__(self, B, T, C, dtype, device, k=None, rtol=DEFAULT_RTOL, gram_impl=GRAM_TCGEN05, group=None,
+                 erank_weight=1.0):
+        self.B, self.T, self.C, self.dtype, self.device = B, T, C, dtype, device
+        self.k = C // 4 if k is None else k
+        self.rtol, self.gram_impl, self.group, self.w = float(rtol), int(gram_impl), group, float(erank_weight)
+        L = _lib.lib()
+        rows = B * T
+        n, m = (T, C) if T < C else (C, T)
+        f32 = dict(dtype=torch.float32, device=device)
+        dt = _DT[dtype]
+        self.ws_score = torch.empty(L.r3d_score_workspace_floats(rows, C), **f32)
+        self.packed = torch.zeros(2 * C + 2, **f32)          # [sum|rgb| (C) | sum|depth| (C) | sum erank | count]
+        self.score = torch.empty(2, C, **f32)
+        self.idx = torch.empty(2, max(self.k, 1), dtype=torch.int64, device=device)
+        self.out = torch.empty(B, T, 2, C, dtype=dtype, device=device)
+        self.dgrad = torch.empty(2, B, T, C, dtype=dtype, device=device)
+        self.ws_er = torch.empty(L.r3d_erank_workspace_bytes(2 * B, T, C, dt), dtype=torch.uint8, device=device)
+        self.er = torch.empty(2 * B, **f32)
+        self.sigma = torch.empty(2 * B, n, **f32)
+        self.U = torch.empty(2 * B, n, n, **f32)
+        self.Y = torch.empty(2 * B, n, m, **f32)
+        self.sweeps = torch.empty(2 * B, dtype=torch.int32, device=device)
+        self.gvec = torch.empty(2 * B, **f32)
+        self.world = 1
+        if group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            self.world = torch.distributed.get_world_size(group)
+        self.gvec.fill_(self.w / float(2 * B * self.world))   # d(mean erank over the global batch)/d erank_b
+
+    def __call__(self, buf: torch.Tensor, gst: torch.Tensor):
+        B, T, C = self.B, self.T, self.C
+        L = _lib.lib()
+        dt = _DT[self.dtype]
+        st = _stream()
+        rows = B * T
+        rgb_p, dep_p = buf.data_ptr(), buf.data_ptr() + buf.stride(0) * buf.element_size()
+        # ---- forward: effective rank of both modalities (2B samples in one batch)
+        check(L.r3d_erank_fwd(buf.data_ptr(), 2 * B, T, C, dt, self.rtol, self.gram_impl, _p(self.ws_er), _p(self.er),
+                              _p(self.sigma), _p(self.U), _p(self.Y), _p(self.sweeps), st))
+        # ---- forward: score sums -> (all-reduce with the erank statistic) -> bottom-k -> exchange
+        check(L.r3d_channel_score_partial(rgb_p, dep_p, rows, C, dt, _p(self.ws_score), st))
+        check(L.r3d_score_finalize(_p(self.ws_score), rows, C, _p(self.packed), None, st))
+        self.packed[2 * C] = self.er.sum()
+        self.packed[2 * C + 1] = float(rows)
+        if self.world > 1:
+            torch.distributed.all_reduce(self.packed, group=self.group)
+        torch.div(self.packed[:2 * C].view(2, C), self.packed[2 * C + 1], out=self.score)
+        check(L.r3d_bottomk(_p(self.score), 2, C, self.k, _p(self.idx), st))
+        ir, idd = self.idx[0].data_ptr(), self.idx[1].data_ptr()
+        check(L.r3d_exchange_fwd(rgb_p, dep_p, ir, idd, self.k, None, None, BLEND_SWAP, _p(self.out), rows, C, dt, st))
+        # ---- backward: exchange backward into dgrad, then accumulate d(mean erank)/dX
+        d0, d1 = self.dgrad.data_ptr(), self.dgrad.data_ptr() + self.dgrad.stride(0) * self.dgrad.element_size()
+        check(L.r3d_exchange_bwd(_p(gst), None, None, ir, idd, self.k, None, None, None, BLEND_SWAP, d0, d1, None,
+                                 rows, C, dt, st))
+        check(L.r3d_erank_bwd(_p(self.gvec), _p(self.er), _p(self.sigma), _p(self.U), _p(self.Y), 2 * B, T, C, dt,
+                              self.rtol, _p(self.ws_er), _p(self.dgrad), 1, st))
+        return self.out, self.er, self.dgrad
