@@ -200,10 +200,14 @@ __device__ __forceinline__ void rr_pair(int m, int r, int t, int& a, int& b) {
 __device__ __forceinline__ int blk_row(int I, int J, int i) { return (i < JB) ? I * JB + i : J * JB + (i - JB); }
 
 // ------------------------------------------------------------------------------
-// Inner solver: one CTA diagonalises the 64x64 sub-block G[IJ, IJ] of one block
-// pair with parallel-ordered two-sided Jacobi in shared memory and emits the
-// accumulated rotation product Q (64x64).  32 disjoint rotations per step; the
-// rotation parameters come from one warp, column/row rotations from all 8 warps.
+// Inner solver: one CTA runs parallel-ordered two-sided Jacobi on the 64x64 sub-block
+// G[IJ, IJ] of one block pair in shared memory and emits the accumulated rotation
+// product Q (64x64).  Per step: one warp derives the 32 disjoint rotations (packed
+// as {c, s, p, q}); then every thread owns 2x2 "pair blocks" {p_a,q_a} x {p_b,q_b} of S
+// and applies the row rotation a AND the column rotation b to them in registers
+// (S <- J^T S J needs no barrier between its two halves), and rotates rows of Q^T
+// with 128-bit accesses.  Two barriers per step.  One inner sweep per visit is
+// enough: the outer sweep count is set by the block round-robin (measured).
 // ------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) jacobi_inner_kernel(float* __restrict__ Gp, int np, int nb, int nt, int round,
                                                            int sweep, int* __restrict__ cnt,
@@ -212,9 +216,8 @@ __global__ void __launch_bounds__(256) jacobi_inner_kernel(float* __restrict__ G
   const int b = blockIdx.y, t = blockIdx.x;
   if (sweep > 0 && cnt[b * JMAX_SWEEPS + sweep - 1] == 0) return;   // this matrix converged
   __shared__ float S[JM][JM + 1];
-  __shared__ float Q[JM][JM + 1];
-  __shared__ float rc[JB], rs[JB];
-  __shared__ int rp[JB], rq[JB];
+  __shared__ __align__(16) float Qt[JM][JM + 4];     // Qt[i][k] = Q[k][i]
+  __shared__ float4 rot[JB];                         // {c, s, bits(p), bits(q)}
   __shared__ int s_any, s_sig, s_tot;
   const int tid = threadIdx.x;
   int I, J;
@@ -223,9 +226,9 @@ __global__ void __launch_bounds__(256) jacobi_inner_kernel(float* __restrict__ G
   for (int e = tid; e < JM * JM; e += 256) {
     const int i = e / JM, j = e % JM;
     S[i][j] = g[int64_t(blk_row(I, J, i)) * np + blk_row(I, J, j)];
-    Q[i][j] = (i == j) ? 1.f : 0.f;
+    Qt[i][j] = (i == j) ? 1.f : 0.f;
   }
-  if (tid == 0) { s_tot = 0; }
+  if (tid == 0) { s_tot = 0; s_sig = 0; }
   __syncthreads();
   // symmetrise (the tile updates leave eps-level asymmetry)
   for (int e = tid; e < JM * JM; e += 256) {
@@ -238,63 +241,70 @@ __global__ void __launch_bounds__(256) jacobi_inner_kernel(float* __restrict__ G
   const float nu_abs = nu[b];
   __syncthreads();
 
+  int sig_total = 0;
   for (int it = 0; it < max_inner; ++it) {
-    if (tid == 0) s_sig = 0;
-    __syncthreads();
     for (int s = 0; s < JM - 1; ++s) {
       if (tid < JB) {
         int p, q;
         rr_pair(JM, s, tid, p, q);
         const float app = S[p][p], aqq = S[q][q], apq = S[p][q];
-        const bool rot = (apq != 0.f) && (fabsf(apq) > tol * sqrtf(fabsf(app * aqq)));
-        const bool sig = rot && (fabsf(apq) > nu_abs);
+        const bool rt = (apq != 0.f) && (fabsf(apq) > tol * sqrtf(fabsf(app * aqq)));
+        const bool sg = rt && (fabsf(apq) > nu_abs);
         float c = 1.f, sn = 0.f;
-        if (rot) {
-          const float zeta = (aqq - app) / (2.f * apq);
-          const float tt = (zeta >= 0.f ? 1.f : -1.f) / (fabsf(zeta) + sqrtf(1.f + zeta * zeta));
-          c = rsqrtf(1.f + tt * tt);
+        if (rt) {
+          const float zeta = __fdividef(aqq - app, 2.f * apq);
+          const float tt = __fdividef(zeta >= 0.f ? 1.f : -1.f, fabsf(zeta) + sqrtf(fmaf(zeta, zeta, 1.f)));
+          c = rsqrtf(fmaf(tt, tt, 1.f));
           sn = tt * c;
         }
-        rp[tid] = p; rq[tid] = q; rc[tid] = c; rs[tid] = sn;
-        const unsigned any = __ballot_sync(0xffffffffu, rot), sg = __ballot_sync(0xffffffffu, sig);
-        if (tid == 0) { s_any = (any != 0); s_sig += __popc(sg); s_tot += __popc(any); }
+        rot[tid] = make_float4(c, sn, __int_as_float(p), __int_as_float(q));
+        const unsigned any = __ballot_sync(0xffffffffu, rt), sgm = __ballot_sync(0xffffffffu, sg);
+        if (tid == 0) { s_any = (any != 0); s_sig += __popc(sgm); s_tot += __popc(any); }
       }
       __syncthreads();
       if (s_any) {
-        // columns of S and Q:  [x_p, x_q] <- [c x_p - s x_q, s x_p + c x_q]
+        // S <- J^T S J on 2x2 pair blocks: 32 x 32 blocks, 4 per thread
 #pragma unroll
-        for (int u = 0; u < (JM * JB) / 256; ++u) {
-          const int item = tid + u * 256, r = item % JM, pr = item / JM;
-          const int p = rp[pr], q = rq[pr];
-          const float c = rc[pr], sn = rs[pr];
-          const float sp = S[r][p], sq = S[r][q];
-          S[r][p] = c * sp - sn * sq;
-          S[r][q] = sn * sp + c * sq;
-          const float qp = Q[r][p], qq = Q[r][q];
-          Q[r][p] = c * qp - sn * qq;
-          Q[r][q] = sn * qp + c * qq;
+        for (int u = 0; u < (JB * JB) / 256; ++u) {
+          const int item = tid + u * 256;
+          const float4 ra = rot[item / JB], rb = rot[item % JB];
+          const int pa = __float_as_int(ra.z), qa = __float_as_int(ra.w);
+          const int pb = __float_as_int(rb.z), qb = __float_as_int(rb.w);
+          const float x00 = S[pa][pb], x01 = S[pa][qb], x10 = S[qa][pb], x11 = S[qa][qb];
+          const float y00 = ra.x * x00 - ra.y * x10, y10 = ra.y * x00 + ra.x * x10;
+          const float y01 = ra.x * x01 - ra.y * x11, y11 = ra.y * x01 + ra.x * x11;
+          S[pa][pb] = rb.x * y00 - rb.y * y01;
+          S[pa][qb] = rb.y * y00 + rb.x * y01;
+          S[qa][pb] = rb.x * y10 - rb.y * y11;
+          S[qa][qb] = rb.y * y10 + rb.x * y11;
         }
-        __syncthreads();
-        // rows of S
+        // Qt <- J^T Qt : rows p, q of Qt, four columns at a time
 #pragma unroll
-        for (int u = 0; u < (JM * JB) / 256; ++u) {
-          const int item = tid + u * 256, cc = item % JM, pr = item / JM;
-          const int p = rp[pr], q = rq[pr];
-          const float c = rc[pr], sn = rs[pr];
-          const float sp = S[p][cc], sq = S[q][cc];
-          S[p][cc] = c * sp - sn * sq;
-          S[q][cc] = sn * sp + c * sq;
+        for (int u = 0; u < (JB * (JM / 4)) / 256; ++u) {
+          const int item = tid + u * 256;
+          const float4 ra = rot[item / (JM / 4)];
+          const int col = (item % (JM / 4)) * 4;
+          const int pa = __float_as_int(ra.z), qa = __float_as_int(ra.w);
+          const float4 vp = *reinterpret_cast<const float4*>(&Qt[pa][col]);
+          const float4 vq = *reinterpret_cast<const float4*>(&Qt[qa][col]);
+          *reinterpret_cast<float4*>(&Qt[pa][col]) =
+              make_float4(ra.x * vp.x - ra.y * vq.x, ra.x * vp.y - ra.y * vq.y, ra.x * vp.z - ra.y * vq.z,
+                          ra.x * vp.w - ra.y * vq.w);
+          *reinterpret_cast<float4*>(&Qt[qa][col]) =
+              make_float4(ra.y * vp.x + ra.x * vq.x, ra.y * vp.y + ra.x * vq.y, ra.y * vp.z + ra.x * vq.z,
+                          ra.y * vp.w + ra.x * vq.w);
         }
       }
       __syncthreads();
     }
-    const int sig_it = s_sig;   // stable: the step loop ended on a barrier
-    __syncthreads();
-    if (sig_it == 0) break;
-    if (tid == 0) atomicAdd(&cnt[b * JMAX_SWEEPS + sweep], sig_it);
+    const int sig_now = s_sig;        // stable: the step loop ended on a barrier
+    __syncthreads();                  // nobody may start the next sweep before all have read it
+    if (sig_now == sig_total) break;  // nothing significant in this inner sweep
+    sig_total = sig_now;
   }
+  if (tid == 0 && sig_total > 0) atomicAdd(&cnt[b * JMAX_SWEEPS + sweep], sig_total);
   float* qo = Qb + (int64_t(b) * nt + t) * JM * JM;
-  for (int e = tid; e < JM * JM; e += 256) qo[e] = Q[e / JM][e % JM];
+  for (int e = tid; e < JM * JM; e += 256) qo[e] = Qt[e % JM][e / JM];   // qo[k*64+i] = Q[k][i]
   if (tid == 0) qflag[b * nt + t] = (s_tot > 0);
 }
 
@@ -598,7 +608,7 @@ static int jacobi_run(const float* G, int64_t B, int64_t n, void* workspace, flo
       {
         R3D_STAGE(ST_JACOBI_INNER, st);
         jacobi_inner_kernel<<<dim3(w.nt, (unsigned)B), 256, 0, st>>>(w.Gp, w.np, w.nb, w.nt, r, sweep, w.cnt, w.qflag,
-                                                                    w.Qb, tol, w.nu, 8);
+                                                                    w.Qb, tol, w.nu, 1);
         R3D_LAUNCH_CHECK();
       }
       {

@@ -375,3 +375,20 @@ def test_host_buffer_entry(dev):
     np.testing.assert_array_equal(idx[0].numpy(), ir)
     np.testing.assert_array_equal(idx[1].numpy(), idd)
     np.testing.assert_array_equal(out.numpy(), ref)
+
+
+@pytest.mark.parametrize("B,T,C", [(2, 512, 512), (1, 600, 256), (3, 2048, 1024), (2, 1000, 768)])
+def test_gram_tcgen05_vs_oracle(B, T, C, dev):
+    """bf16 channel-side Gram on tcgen05/TMA against float64 numpy and against the SIMT kernel."""
+    from r3d_b200 import ops
+    x = torch.from_numpy(_spectra("relu", B, T, C, 9)).to(torch.bfloat16)
+    xd = x.to(dev)
+    G = ops.gram(xd, ops.GRAM_TCGEN05).cpu().numpy()
+    xf = x.float().numpy().astype(np.float64)
+    Gr = np.einsum("btc,btd->bcd", xf, xf)
+    assert G.shape == (B, C, C)
+    err = np.abs(G - Gr).max() / np.abs(Gr).max()
+    Gs = ops.gram(xd, ops.GRAM_SIMT).cpu().numpy()
+    err_s = np.abs(Gs - Gr).max() / np.abs(Gr).max()
+    print(f"tcgen05 gram rel err {err:.2e} (simt {err_s:.2e}) at T={T}")
+    assert err < 1e-5, (err, err_s)      # exact bf16 products; fp32 accumulation over T terms in TMEM
