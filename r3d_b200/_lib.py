@@ -20,6 +20,9 @@ SIGNATURES = {
     "r3d_last_error": (c_char_p, []),
     "r3d_abi_version": (c_int, []),
     "r3d_launch_count": (c_int64, [c_int]),
+    "r3d_set_option": (c_int, [c_char_p, ctypes.c_double]),
+    "r3d_debug_panel_round": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p,
+                                      c_void_p]),
     "r3d_profile_enable": (c_int, [c_int]),
     "r3d_profile_num_stages": (c_int, []),
     "r3d_profile_stage_name": (c_char_p, [c_int]),
@@ -101,3 +104,7 @@ def profile_read(reset: bool = True) -> dict:
         if calls[i]:
             out[L.r3d_profile_stage_name(i).decode()] = {"ms": ms[i], "calls": int(calls[i]), "launches": int(kl[i])}
     return out
+
+
+def set_option(key: str, value: float):
+    check(lib().r3d_set_option(key.encode(), float(value)))

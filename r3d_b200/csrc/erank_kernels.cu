@@ -11,10 +11,18 @@
 // X^T X a graded matrix, which two-sided Jacobi resolves to relative accuracy.
 // No transposes are materialised: the GEMMs read X through (row, col) strides.
 #include <algorithm>
+#include <string>
+#include <vector>
 
 #include "common.cuh"
+#include "jacobi_tc.cuh"
 
 namespace r3d {
+
+extern int g_panel_debug;
+extern int g_panel_grid_cap;
+static thread_local Options g_opts;
+Options& options() { return g_opts; }
 
 constexpr int JB = 32;        // Jacobi block width
 constexpr int JM = 2 * JB;    // inner problem size (one block pair)
@@ -127,12 +135,12 @@ static int sgemm_launch(bool ta, bool tb, const TA* A, const TB* Bm, TC* Cm, int
 // ------------------------------------------------------------------------------
 // Jacobi workspace layout (all per batch):
 //   Gp  (np, np)  padded symmetric working matrix        Vt (np, np) rows -> eigenvectors
-//   Qb  (nt, 64, 64) rotation products of the current round, nt = nb/2 tasks
+//   Qb  (nt, 64, 64) TRANSPOSED rotation products Q^T of the current round, nt = nb/2 tasks
 //   cnt (JMAX_SWEEPS) significant rotations per sweep     qflag (nt) task rotated anything
 //   nu  (1) absolute significance floor
 // ------------------------------------------------------------------------------
 struct JacobiWs {
-  float* Gp; float* Vt; float* Qb; int* cnt; int* qflag; float* nu;
+  float* Gp; float* Vt; float* H; float* Qb; int* cnt; int* qflag; float* nu;
   int np, nb, nt;
 };
 
@@ -140,7 +148,7 @@ static inline int jacobi_np(int64_t n) { return int(((n + JM - 1) / JM) * JM); }
 
 static size_t jacobi_ws_bytes(int64_t B, int64_t n) {
   const size_t np = jacobi_np(n), nt = np / JM;
-  size_t f = size_t(B) * (2 * np * np + nt * JM * JM + 1);
+  size_t f = size_t(B) * (3 * np * np + nt * JM * JM + 1);
   size_t i = size_t(B) * (JMAX_SWEEPS + nt);
   return f * 4 + i * 4 + 256;
 }
@@ -153,6 +161,7 @@ static JacobiWs jacobi_carve(void* ws, int64_t B, int64_t n) {
   const size_t np2 = size_t(w.np) * w.np;
   w.Gp = (float*)p; p += size_t(B) * np2 * 4;
   w.Vt = (float*)p; p += size_t(B) * np2 * 4;
+  w.H = (float*)p; p += size_t(B) * np2 * 4;
   w.Qb = (float*)p; p += size_t(B) * w.nt * JM * JM * 4;
   w.nu = (float*)p; p += size_t(B) * 4;
   w.cnt = (int*)p; p += size_t(B) * JMAX_SWEEPS * 4;
@@ -304,7 +313,7 @@ __global__ void __launch_bounds__(256) jacobi_inner_kernel(float* __restrict__ G
   }
   if (tid == 0 && sig_total > 0) atomicAdd(&cnt[b * JMAX_SWEEPS + sweep], sig_total);
   float* qo = Qb + (int64_t(b) * nt + t) * JM * JM;
-  for (int e = tid; e < JM * JM; e += 256) qo[e] = Qt[e % JM][e / JM];   // qo[k*64+i] = Q[k][i]
+  for (int e = tid; e < JM * JM; e += 256) qo[e] = Qt[e / JM][e % JM];   // qo[i*64+k] = Q[k][i]  (Q^T, row-major)
   if (tid == 0) qflag[b * nt + t] = (s_tot > 0);
 }
 
@@ -342,8 +351,8 @@ __global__ void __launch_bounds__(256) jacobi_update_kernel(float* __restrict__ 
     const int i = e / JM, j = e % JM;
     const int gj = two_sided ? blk_row(Ic, Jc, j) : slab * JM + j;
     Tm[i][j] = base[int64_t(blk_row(Ia, Ja, i)) * np + gj];
-    Qa[i][j] = qa[e];
-    if (two_sided) Qc[i][j] = qc[e];
+    Qa[j][i] = qa[e];                 // Qb holds Q^T: Qa[k][i] = Q[k][i] = qa[i*64+k]
+    if (two_sided) Qc[j][i] = qc[e];
   }
   __syncthreads();
   const int ti = tid / 16, tj = tid % 16;
@@ -403,21 +412,23 @@ __global__ void __launch_bounds__(256) jacobi_extract_kernel(const float* __rest
                                                              const float* __restrict__ Vt, int n, int np,
                                                              const int* __restrict__ cnt, int max_sweeps,
                                                              float* __restrict__ lambda, float* __restrict__ Ut,
-                                                             int* __restrict__ sweeps) {
+                                                             int* __restrict__ sweeps, int v_is_columns) {
   const int b = blockIdx.y;
   const float* gp = Gp + int64_t(b) * np * np;
   const float* vt = Vt + int64_t(b) * np * np;
   const int lane = threadIdx.x & 31;
   for (int i = blockIdx.x * 8 + (threadIdx.x >> 5); i < n; i += gridDim.x * 8) {
-    const float* row = vt + int64_t(i) * np;
+    // eigenvector i is row i of Vt (SIMT update) or column i of V (tensor-core update)
+    const float* row = v_is_columns ? vt + i : vt + int64_t(i) * np;
+    const int64_t stp = v_is_columns ? np : 1;
     float ss = 0.f;
-    for (int j = lane; j < n; j += 32) { const float v = row[j]; ss = fmaf(v, v, ss); }
+    for (int j = lane; j < n; j += 32) { const float v = row[j * stp]; ss = fmaf(v, v, ss); }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
     const float inv = ss > 0.f ? rsqrtf(ss) : 0.f;
     if (Ut) {
       float* out = Ut + int64_t(b) * n * n + int64_t(i) * n;
-      for (int j = lane; j < n; j += 32) out[j] = row[j] * inv;
+      for (int j = lane; j < n; j += 32) out[j] = row[j * stp] * inv;
     }
     if (lambda && lane == 0) lambda[int64_t(b) * n + i] = gp[int64_t(i) * np + i];
   }
@@ -557,6 +568,36 @@ static inline void side(int64_t T, int64_t C, int64_t& n, int64_t& m, bool& tsid
   m = tside ? C : T;
 }
 
+// Debug/test hook: one tensor-core panel-update round on caller-provided buffers (all (B, np, np) fp32,
+// Qb (B, np/64, 64, 64)); every task is applied (qflag = 1, nothing converged).
+extern "C" int r3d_debug_panel_round(float* G, float* H, float* V, const float* Qb, int64_t B, int np, int round,
+                                     int* scratch /* B*32 + B*np/64 ints */, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  R3D_CHECK(panel_tc_supported(np), "np must be a multiple of 128");
+  const int nt = np / JM;
+  int* cnt = scratch;
+  int* qflag = scratch + B * JMAX_SWEEPS;
+  R3D_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int) * B * JMAX_SWEEPS, st));
+  std::vector<int> ones(B * nt, 1);
+  R3D_CUDA(cudaMemcpyAsync(qflag, ones.data(), sizeof(int) * B * nt, cudaMemcpyHostToDevice, st));
+  R3D_CUDA(cudaStreamSynchronize(st));
+  PanelTc ptc;
+  if (int e = panel_tc_prepare(&ptc, G, H, V, Qb, B, np)) return e;
+  return panel_tc_round(&ptc, round, 0, cnt, qflag, st);
+}
+
+extern "C" int r3d_set_option(const char* key, double value) {
+  R3D_CHECK(key != nullptr, "null option key");
+  const std::string k(key);
+  if (k == "jacobi_update_tc") options().jacobi_update_tc = value != 0.0;
+  else if (k == "jacobi_tol") options().jacobi_tol = (float)value;
+  else if (k == "jacobi_max_sweeps") options().jacobi_max_sweeps = (int)value;
+  else if (k == "panel_debug") g_panel_debug = (int)value;
+  else if (k == "panel_grid_cap") g_panel_grid_cap = (int)value;
+  else R3D_CHECK(false, "unknown option '%s'", key);
+  return 0;
+}
+
 extern "C" size_t r3d_jacobi_workspace_bytes(int64_t B, int64_t n) { return jacobi_ws_bytes(B, n); }
 
 extern "C" size_t r3d_erank_workspace_bytes(int64_t B, int64_t T, int64_t C, int dtype) {
@@ -590,9 +631,15 @@ extern "C" int r3d_gram(const void* x, int64_t B, int64_t T, int64_t C, int dtyp
 
 static int jacobi_run(const float* G, int64_t B, int64_t n, void* workspace, float* lambda_out, float* U_out,
                       int32_t* sweeps_out, int max_sweeps, cudaStream_t st) {
+  if (max_sweeps <= 0 || max_sweeps > JMAX_SWEEPS) max_sweeps = options().jacobi_max_sweeps;
   if (max_sweeps <= 0 || max_sweeps > JMAX_SWEEPS) max_sweeps = 16;
   JacobiWs w = jacobi_carve(workspace, B, n);
-  const float tol = 1e-5f;
+  const float tol = options().jacobi_tol;
+  const bool tc = options().jacobi_update_tc != 0 && panel_tc_supported(w.np);
+  PanelTc ptc;
+  if (tc) {
+    if (int e = panel_tc_prepare(&ptc, w.Gp, w.H, w.Vt, w.Qb, B, w.np)) return e;
+  }
   {
     dim3 grid(std::min<int64_t>((int64_t(w.np) * w.np + 255) / 256, 64), (unsigned)B);
     R3D_STAGE(ST_JACOBI_INIT, st);
@@ -611,7 +658,9 @@ static int jacobi_run(const float* G, int64_t B, int64_t n, void* workspace, flo
                                                                     w.Qb, tol, w.nu, 1);
         R3D_LAUNCH_CHECK();
       }
-      {
+      if (tc) {
+        if (int e = panel_tc_round(&ptc, r, sweep, w.cnt, w.qflag, st)) return e;
+      } else {
         R3D_STAGE(ST_JACOBI_UPDATE, st);
         jacobi_update_kernel<<<dim3(upd_tiles, (unsigned)B), 256, upd_smem, st>>>(w.Gp, w.Vt, w.np, w.nb, w.nt, r,
                                                                                  sweep, w.cnt, w.qflag, w.Qb);
@@ -623,7 +672,7 @@ static int jacobi_run(const float* G, int64_t B, int64_t n, void* workspace, flo
     dim3 grid((unsigned)std::min<int64_t>((n + 7) / 8, 64), (unsigned)B);
     R3D_STAGE(ST_JACOBI_EXTRACT, st);
     jacobi_extract_kernel<<<grid, 256, 0, st>>>(w.Gp, w.Vt, int(n), w.np, w.cnt, max_sweeps, lambda_out, U_out,
-                                                sweeps_out);
+                                                sweeps_out, tc ? 1 : 0);
     R3D_LAUNCH_CHECK();
   }
   return 0;

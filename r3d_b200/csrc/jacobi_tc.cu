@@ -1,0 +1,459 @@
+// Block-Jacobi panel update on 5th-generation tensor cores (sm_100a), fp32-accurate.
+//
+// One round of the block two-sided Jacobi applies, for every block pair (task) c of the
+// round with rotation product Q_c (64x64):   G <- Q^T G Q   and   V <- V Q.
+// Both are expressed with ONE GEMM shape, the column-panel update
+//
+//        Z[:, IJ_c]  <-  Z[:, IJ_c] * Q_c          (M = 128 rows per tile, K = 64, N = 64)
+//
+// because G' = (G Q)^T Q for symmetric G: pass 1 writes H^T = (G Q)^T (transposed
+// store), pass 2 applies the same panel update to H^T.  V is updated in place.
+//
+// fp32 accuracy on TF32 tensor cores comes from the 3xTF32 split: x = hi + lo with
+// hi = round-to-nearest TF32 of x (exact in TF32), lo = x - hi, and D = A_hi B_hi + A_hi B_lo + A_lo B_hi
+// accumulated in fp32 in TMEM (error ~2^-22 per product).
+//
+// Pipeline per CTA (persistent over a strided tile list):
+//   warp 0      TMA producer: panel tile (two 32-column boxes of 128 rows, K-major
+//               SWIZZLE_128B) + Q^T (two 32-column boxes of 64 rows, K-major SWIZZLE_128B)
+//   warps 4-7   splitters: hi/lo split in shared memory (same swizzled addresses)
+//   warp 1      MMA issuer: 24 x tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=64, K=8)
+//   warps 8-11  epilogue: tcgen05.ld 32x32b.x64 -> (transposed) global stores
+//   warp 2      TMEM allocator (2 accumulator stages x 64 columns)
+// SASS evidence: UTCHMMA/UTCMMA (tcgen05.mma), UTMALDG (TMA), LDTM (tcgen05.ld).
+#include <cuda.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+#include "jacobi_tc.cuh"
+
+namespace r3d {
+
+namespace {
+
+constexpr int PB = 32;                 // Jacobi block width (must equal JB in erank_kernels.cu)
+constexpr int PM = 64;                 // panel width = 2 blocks
+constexpr int TM = 128;                // rows per tile
+constexpr int NSTAGE = 2;
+constexpr int A_RAW = TM * PM * 4;     // 32 KB: panel tile, hi part after the split (in place)
+constexpr int Q_RAW = PM * PM * 4;     // 16 KB
+constexpr int STAGE = 2 * A_RAW + 2 * Q_RAW;        // hi + lo of both operands: 96 KB
+constexpr int SMEM_TOTAL = NSTAGE * STAGE + 1024 + 256;
+constexpr int TMEM_COLS_P = 128;       // 2 accumulator stages x 64 fp32 columns
+constexpr int JMAXS = 32;              // must equal JMAX_SWEEPS
+
+__device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void bar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}" : "=r"(ok) : "r"(s_u32(bar)), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void tma_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(s_u32(dst)), "l"(map), "r"(s_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(s_u32(dst)), "l"(map), "r"(s_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ bool elect() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}" : "=r"(pred));
+  return pred != 0;
+}
+// cute::UMMA::SmemDescriptor, SWIZZLE_128B (layout type 2), version 1
+__device__ __forceinline__ uint64_t desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= uint64_t((saddr >> 4) & 0x3fff);
+  d |= uint64_t((lbo_bytes >> 4) & 0x3fff) << 16;
+  d |= uint64_t((sbo_bytes >> 4) & 0x3fff) << 32;
+  d |= uint64_t(1) << 46;
+  d |= uint64_t(2) << 61;
+  return d;
+}
+// InstrDescriptor: D fp32, A/B TF32, both K-major, N = 64, M = 128
+// (32-bit MN-major operands need the special SWIZZLE_128B_BASE32B layout; the inner solver emits Q^T
+//  instead, so B[n = j][k] = Qt[j][k] is K-major like the panel tile)
+constexpr uint32_t kIdescTf32 = (1u << 4) | (2u << 7) | (2u << 10) | (0u << 15) | (0u << 16) |
+                                (uint32_t(PM >> 3) << 17) | (uint32_t(TM >> 4) << 24);
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(kIdescTf32), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_to(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s_u32(bar))
+               : "memory");
+}
+
+// round-to-nearest TF32 (10 explicit mantissa bits): unbiased split x = hi + lo, |lo| <= 2^-11 |x|
+__device__ __forceinline__ float tf32_rn(float x) {
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+}
+
+// circle-method round robin (same function as erank_kernels.cu)
+__device__ __forceinline__ void rr_pair_tc(int m, int r, int t, int& a, int& b) {
+  if (m == 2) { a = 0; b = 1; return; }
+  int x, y;
+  if (t == 0) { x = r; y = m - 1; }
+  else { x = (r + t) % (m - 1); y = (r - t + (m - 1)) % (m - 1); }
+  a = min(x, y); b = max(x, y);
+}
+
+struct PanelJob {
+  // job 0 and job 1 may run in the same launch (e.g. G pass 1 and the V update)
+  float* out0; float* out1;
+  int transposed0, transposed1;
+  int skip_on_qflag0, skip_on_qflag1;   // in-place jobs may skip tasks whose Q is the identity
+};
+
+// tile index -> (job, matrix b, task c, row tile mt); returns false when the tile must be skipped
+struct TileInfo { int job, b, c, mt; bool run; };
+
+__device__ __forceinline__ TileInfo decode_tile(int tile, int njobs, int B, int nt, int mtiles, int sweep,
+                                                const int* __restrict__ cnt, const int* __restrict__ qflag,
+                                                const PanelJob& pj) {
+  TileInfo ti;
+  const int per_job = B * nt * mtiles;
+  ti.job = tile / per_job;
+  int r = tile % per_job;
+  ti.b = r / (nt * mtiles);
+  r %= nt * mtiles;
+  ti.c = r / mtiles;
+  ti.mt = r % mtiles;
+  ti.run = true;
+  if (sweep > 0 && cnt[ti.b * JMAXS + sweep - 1] == 0) ti.run = false;            // matrix converged
+  else if ((ti.job == 0 ? pj.skip_on_qflag0 : pj.skip_on_qflag1) && qflag[ti.b * nt + ti.c] == 0) ti.run = false;
+  (void)njobs;
+  return ti;
+}
+
+__global__ void __launch_bounds__(384, 1) panel_update_tc_kernel(const __grid_constant__ CUtensorMap map_in0,
+                                                                 const __grid_constant__ CUtensorMap map_in1,
+                                                                 const __grid_constant__ CUtensorMap map_q,
+                                                                 PanelJob pj, int njobs, int B, int np, int nb, int nt,
+                                                                 int round, int sweep, const int* __restrict__ cnt,
+                                                                 const int* __restrict__ qflag, int debug) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)((uintptr_t(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* raw_full = (uint64_t*)(smem + NSTAGE * STAGE);       // TMA -> splitters
+  uint64_t* split_done = raw_full + NSTAGE;                      // splitters -> MMA (count 128)
+  uint64_t* smem_empty = split_done + NSTAGE;                    // MMA commit -> producer
+  uint64_t* tmem_full = smem_empty + NSTAGE;                     // MMA commit -> epilogue
+  uint64_t* tmem_empty = tmem_full + 2;                          // epilogue -> MMA (count 128)
+  uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int mtiles = np / TM;
+  const int total_tiles = njobs * B * nt * mtiles;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_in0) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < NSTAGE; ++s) { bar_init(&raw_full[s], 1); bar_init(&split_done[s], 128); bar_init(&smem_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { bar_init(&tmem_full[s], 1); bar_init(&tmem_empty[s], 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_slot)),
+                 "n"(TMEM_COLS_P) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect()) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TileInfo ti = decode_tile(tile, njobs, B, nt, mtiles, sweep, cnt, qflag, pj);
+        if (!ti.run) continue;
+        const int s = it % NSTAGE;
+        const uint32_t ph = (it / NSTAGE) & 1;
+        bar_wait(&smem_empty[s], ph ^ 1);
+        uint8_t* st = smem + s * STAGE;
+        int I, J;
+        rr_pair_tc(nb, round, ti.c, I, J);
+        bar_expect_tx(&raw_full[s], A_RAW + Q_RAW);
+        const CUtensorMap* mp = ti.job == 0 ? &map_in0 : &map_in1;
+        // panel tile: rows [mt*128, +128), column blocks I and J (32 floats = 128 B each)
+        tma_3d(st, mp, &raw_full[s], I * PB, ti.mt * TM, ti.b);
+        tma_3d(st + TM * 128, mp, &raw_full[s], J * PB, ti.mt * TM, ti.b);
+        // Q_c^T: 64 rows (j) x two 32-column halves of k
+        const int qrow = (ti.b * nt + ti.c) * PM;
+        tma_2d(st + 2 * A_RAW, &map_q, &raw_full[s], 0, qrow);
+        tma_2d(st + 2 * A_RAW + PM * 128, &map_q, &raw_full[s], 32, qrow);
+        ++it;
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (elect()) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TileInfo ti = decode_tile(tile, njobs, B, nt, mtiles, sweep, cnt, qflag, pj);
+        if (!ti.run) continue;
+        const int s = it % NSTAGE;
+        const uint32_t ph = (it / NSTAGE) & 1;
+        const int acc = it & 1;
+        const uint32_t aph = (it >> 1) & 1;
+        bar_wait(&tmem_empty[acc], aph ^ 1);           // epilogue has drained this accumulator
+        bar_wait(&split_done[s], ph);                  // hi/lo operands are in shared memory
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a_hi = s_u32(smem + s * STAGE), a_lo = a_hi + A_RAW;
+        const uint32_t q_hi = a_hi + 2 * A_RAW, q_lo = q_hi + Q_RAW;
+        const uint32_t d = tmem_base + acc * PM;
+        uint32_t first = 0;
+#pragma unroll
+        for (int prod = 0; prod < 3; ++prod) {
+          if ((debug & 1) && prod > 0) break;
+          const uint32_t ab = (prod == 2) ? a_lo : a_hi;
+          const uint32_t qb = (prod == 1) ? q_lo : q_hi;
+#pragma unroll
+          for (int kk = 0; kk < PM / 8; ++kk) {
+            // A: K-major; 32-column half kk/4, 32 B (8 tf32) per step inside the 128 B swizzle row
+            const uint64_t ad = desc_sw128(ab + (kk / 4) * (TM * 128) + (kk % 4) * 32, 16, 1024);
+            // B (Q^T): K-major, rows = j (64), same half/step addressing as A
+            const uint64_t bd = desc_sw128(qb + (kk / 4) * (PM * 128) + (kk % 4) * 32, 16, 1024);
+            umma_tf32(d, ad, bd, first);
+            first = 1;
+          }
+        }
+        umma_commit_to(&smem_empty[s]);
+        umma_commit_to(&tmem_full[acc]);
+        ++it;
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ===================== splitters: x -> (hi, lo) in shared memory =====================
+    const int t = threadIdx.x - 128;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const TileInfo ti = decode_tile(tile, njobs, B, nt, mtiles, sweep, cnt, qflag, pj);
+      if (!ti.run) continue;
+      const int s = it % NSTAGE;
+      const uint32_t ph = (it / NSTAGE) & 1;
+      bar_wait(&raw_full[s], ph);
+      uint8_t* st = smem + s * STAGE;
+      float4* a_hi = reinterpret_cast<float4*>(st);
+      float4* a_lo = reinterpret_cast<float4*>(st + A_RAW);
+      float4* q_hi = reinterpret_cast<float4*>(st + 2 * A_RAW);
+      float4* q_lo = reinterpret_cast<float4*>(st + 2 * A_RAW + Q_RAW);
+      if (!(debug & 4)) {
+#pragma unroll 4
+      for (int e = t; e < A_RAW / 16; e += 128) {
+        const float4 x = a_hi[e];
+        float4 h, l;
+        h.x = tf32_rn(x.x); l.x = x.x - h.x;
+        h.y = tf32_rn(x.y); l.y = x.y - h.y;
+        h.z = tf32_rn(x.z); l.z = x.z - h.z;
+        h.w = tf32_rn(x.w); l.w = x.w - h.w;
+        a_hi[e] = h; a_lo[e] = l;
+      }
+#pragma unroll 4
+      for (int e = t; e < Q_RAW / 16; e += 128) {
+        const float4 x = q_hi[e];
+        float4 h, l;
+        h.x = tf32_rn(x.x); l.x = x.x - h.x;
+        h.y = tf32_rn(x.y); l.y = x.y - h.y;
+        h.z = tf32_rn(x.z); l.z = x.z - h.z;
+        h.w = tf32_rn(x.w); l.w = x.w - h.w;
+        q_hi[e] = h; q_lo[e] = l;
+      }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to UMMA
+      bar_arrive(&split_done[s]);
+      ++it;
+    }
+  } else if (warp >= 8) {
+    // ===================== epilogue: TMEM -> global =====================
+    const int q = warp & 3;                      // TMEM lanes [32q, 32q+32)
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const TileInfo ti = decode_tile(tile, njobs, B, nt, mtiles, sweep, cnt, qflag, pj);
+      if (!ti.run) continue;
+      const int acc = it & 1;
+      const uint32_t aph = (it >> 1) & 1;
+      bar_wait(&tmem_full[acc], aph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      int I, J;
+      rr_pair_tc(nb, round, ti.c, I, J);
+      float* out = (ti.job == 0 ? pj.out0 : pj.out1) + int64_t(ti.b) * np * np;
+      const bool tr = (ti.job == 0 ? pj.transposed0 : pj.transposed1) != 0;
+      const int row = ti.mt * TM + q * 32 + lane;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t v[32];
+        const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * PM + half * 32);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+              "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+              "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        const int col0 = (half == 0 ? I : J) * PB;
+        if (debug & 2) {
+          // dump the staged panel tile as the async proxy left it (after the split): element (row r, k = half*32 + j)
+          const int sidx = it % NSTAGE;
+          const uint8_t* abase = smem + sidx * STAGE + half * (TM * 128);
+          const int r = q * 32 + lane;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int chunk = (j >> 2) ^ (r & 7);
+            v[j] = *reinterpret_cast<const uint32_t*>(abase + r * 128 + chunk * 16 + (j & 3) * 4);
+          }
+        }
+        if (tr) {
+          // out[col0 + j][row]: for fixed j the 32 lanes write 32 consecutive floats
+          float* o = out + int64_t(col0) * np + row;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) o[int64_t(j) * np] = __uint_as_float(v[j]);
+        } else {
+          float4* o = reinterpret_cast<float4*>(out + int64_t(row) * np + col0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            o[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                               __uint_as_float(v[4 * j + 3]));
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      bar_arrive(&tmem_empty[acc]);
+      ++it;
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS_P) : "memory");
+  }
+}
+
+typedef CUresult (*EncodeTiledFn2)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn2 get_encode2() {
+  static EncodeTiledFn2 fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn2)p;
+  }
+  return fn;
+}
+
+int make_map_panel(CUtensorMap* m, const float* base, int64_t B, int np) {
+  EncodeTiledFn2 enc = get_encode2();
+  R3D_CHECK(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+  const cuuint64_t gdim[3] = {(cuuint64_t)np, (cuuint64_t)np, (cuuint64_t)B};
+  const cuuint64_t gstr[2] = {(cuuint64_t)np * 4, (cuuint64_t)np * np * 4};
+  const cuuint32_t box[3] = {PB, TM, 1};
+  const cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), gdim, gstr, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  R3D_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(panel) failed with %d", (int)r);
+  return 0;
+}
+int make_map_q(CUtensorMap* m, const float* base, int64_t rows) {
+  EncodeTiledFn2 enc = get_encode2();
+  R3D_CHECK(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+  const cuuint64_t gdim[2] = {(cuuint64_t)PM, (cuuint64_t)rows};
+  const cuuint64_t gstr[1] = {(cuuint64_t)PM * 4};
+  const cuuint32_t box[2] = {32, PM};
+  const cuuint32_t es[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  R3D_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(Q) failed with %d", (int)r);
+  return 0;
+}
+
+}  // namespace
+
+bool panel_tc_supported(int np) { return np % TM == 0; }
+
+int panel_tc_prepare(PanelTc* h, float* G, float* H, float* V, const float* Qb, int64_t B, int np) {
+  h->G = G; h->H = H; h->V = V; h->B = B; h->np = np; h->nb = np / PB; h->nt = np / PM;
+  if (int e = make_map_panel(&h->map_g, G, B, np)) return e;
+  if (int e = make_map_panel(&h->map_h, H, B, np)) return e;
+  if (int e = make_map_panel(&h->map_v, V, B, np)) return e;
+  if (int e = make_map_q(&h->map_q, Qb, B * h->nt * PM)) return e;
+  static bool attr_done = false;
+  if (!attr_done) {
+    R3D_CUDA(cudaFuncSetAttribute(panel_update_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    attr_done = true;
+  }
+  return 0;
+}
+
+// One round: launch 1 = { H^T <- (G Q)^T  (transposed store),  V <- V Q (in place) },
+//            launch 2 = { G <- H^T Q }.
+int g_panel_debug = 0;
+int g_panel_grid_cap = 0;
+int panel_tc_round(PanelTc* h, int round, int sweep, const int* cnt, const int* qflag, cudaStream_t st) {
+  const int mtiles = h->np / TM;
+  const int64_t tiles_per_job = h->B * h->nt * mtiles;
+  {
+    PanelJob pj;
+    pj.out0 = h->H; pj.transposed0 = 1; pj.skip_on_qflag0 = 0;
+    pj.out1 = h->V; pj.transposed1 = 0; pj.skip_on_qflag1 = 1;
+    int grid = (int)std::min<int64_t>(2 * tiles_per_job, kNumSMs);
+    if (g_panel_grid_cap > 0) grid = std::min(grid, g_panel_grid_cap);
+    R3D_STAGE(ST_JACOBI_UPDATE, st);
+    panel_update_tc_kernel<<<grid, 384, SMEM_TOTAL, st>>>(h->map_g, h->map_v, h->map_q, pj, 2, (int)h->B, h->np, h->nb,
+                                                          h->nt, round, sweep, cnt, qflag, g_panel_debug);
+    R3D_LAUNCH_CHECK();
+  }
+  {
+    PanelJob pj;
+    pj.out0 = h->G; pj.transposed0 = 0; pj.skip_on_qflag0 = 0;
+    pj.out1 = nullptr; pj.transposed1 = 0; pj.skip_on_qflag1 = 0;
+    int grid = (int)std::min<int64_t>(tiles_per_job, kNumSMs);
+    if (g_panel_grid_cap > 0) grid = std::min(grid, g_panel_grid_cap);
+    R3D_STAGE(ST_JACOBI_UPDATE, st);
+    panel_update_tc_kernel<<<grid, 384, SMEM_TOTAL, st>>>(h->map_h, h->map_h, h->map_q, pj, 1, (int)h->B, h->np, h->nb,
+                                                          h->nt, round, sweep, cnt, qflag, g_panel_debug);
+    R3D_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+}  // namespace r3d
