@@ -216,7 +216,8 @@ __device__ __forceinline__ int blk_row(int I, int J, int i) { return (i < JB) ? 
 // and applies the row rotation a AND the column rotation b to them in registers
 // (S <- J^T S J needs no barrier between its two halves), and rotates rows of Q^T
 // with 128-bit accesses.  Two barriers per step.  One inner sweep per visit is
-// enough: the outer sweep count is set by the block round-robin (measured).
+// enough: the outer sweep count is set by the block round-robin (measured); rounds
+// after the first rotate cross pairs only (see below).
 // ------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) jacobi_inner_kernel(float* __restrict__ Gp, int np, int nb, int nt, int round,
                                                            int sweep, int* __restrict__ cnt,
@@ -252,10 +253,15 @@ __global__ void __launch_bounds__(256) jacobi_inner_kernel(float* __restrict__ G
 
   int sig_total = 0;
   for (int it = 0; it < max_inner; ++it) {
-    for (int s = 0; s < JM - 1; ++s) {
+    // Round 0 of a sweep visits every pair of the 64 columns (63 steps), so the pairs inside each block are
+    // rotated once per sweep.  Later rounds rotate only the 32 x 32 cross pairs (t, 32 + (t+s) mod 32):
+    // half the steps, and the 32 p's / 32 q's of a step fall in 32 distinct shared-memory banks.
+    const int nsteps = (round == 0) ? JM - 1 : JB;
+    for (int s = 0; s < nsteps; ++s) {
       if (tid < JB) {
         int p, q;
-        rr_pair(JM, s, tid, p, q);
+        if (round == 0) rr_pair(JM, s, tid, p, q);
+        else { p = tid; q = JB + ((tid + s) & (JB - 1)); }
         const float app = S[p][p], aqq = S[q][q], apq = S[p][q];
         const bool rt = (apq != 0.f) && (fabsf(apq) > tol * sqrtf(fabsf(app * aqq)));
         const bool sg = rt && (fabsf(apq) > nu_abs);

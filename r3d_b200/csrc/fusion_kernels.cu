@@ -165,15 +165,30 @@ __global__ void __launch_bounds__(256) score_partial_kernel(const T* __restrict_
   }
 }
 
-__global__ void score_finalize_kernel(const float* __restrict__ partial, int row_chunks, int64_t rows, int64_t C,
-                                      float* __restrict__ sums_out, float* __restrict__ score_out) {
-  int64_t c = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  const float* p = partial + int64_t(blockIdx.y) * row_chunks * C + c;
+// Stage 2: 32 channels x 8 partial-sum lanes per CTA; every lane adds its slice of the row chunks in index
+// order, then lane 0 adds the 8 lane sums in order -- a fixed summation tree, so results are bit-reproducible.
+__global__ void __launch_bounds__(256) score_finalize_kernel(const float* __restrict__ partial, int row_chunks,
+                                                             int64_t rows, int64_t C, float* __restrict__ sums_out,
+                                                             float* __restrict__ score_out) {
+  __shared__ float red[8][33];
+  const int cl = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int64_t c = int64_t(blockIdx.x) * 32 + cl;
   float s = 0.f;
-  for (int i = 0; i < row_chunks; ++i) s += p[int64_t(i) * C];
-  if (sums_out) sums_out[blockIdx.y * C + c] = s;
-  if (score_out) score_out[blockIdx.y * C + c] = s / float(rows);
+  if (c < C) {
+    const float* p = partial + int64_t(blockIdx.y) * row_chunks * C + c;
+    const int per = (row_chunks + 7) / 8;
+    const int i0 = g * per, i1 = min(row_chunks, i0 + per);
+    for (int i = i0; i < i1; ++i) s += p[int64_t(i) * C];
+  }
+  red[g][cl] = s;
+  __syncthreads();
+  if (g == 0 && c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k][cl];
+    if (sums_out) sums_out[blockIdx.y * C + c] = t;
+    if (score_out) score_out[blockIdx.y * C + c] = t / float(rows);
+  }
 }
 
 // ------------------------------------------------------------------------------
@@ -652,7 +667,7 @@ extern "C" int r3d_score_finalize(const float* partial, int64_t rows, int64_t C,
                                   void* stream) {
   R3D_CHECK(partial != nullptr, "null workspace");
   R3D_CHECK(rows >= 1 && C >= 1, "bad shape");
-  dim3 grid((unsigned)((C + 255) / 256), 2);
+  dim3 grid((unsigned)((C + 31) / 32), 2);
   R3D_STAGE(ST_SCORE_FINALIZE, (cudaStream_t)stream);
   score_finalize_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(partial, fixed_row_chunks(rows), rows, C, sums_out,
                                                                score_out);
