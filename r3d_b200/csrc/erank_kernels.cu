@@ -146,6 +146,13 @@ struct JacobiWs {
 
 static inline int jacobi_np(int64_t n) { return int(((n + JM - 1) / JM) * JM); }
 
+// The Jacobi working matrices (Gp, H, V) are stored column-block-major: [np/32 column blocks][np rows][32],
+// so a column-panel tile (128 rows x one 32-column block) is one contiguous 16 KB run in HBM and a 32x32
+// sub-block is a contiguous 4 KB run.
+__host__ __device__ __forceinline__ int64_t boff(int np, int r, int c) {
+  return (int64_t(c >> 5) * np + r) * JB + (c & (JB - 1));
+}
+
 static size_t jacobi_ws_bytes(int64_t B, int64_t n) {
   const size_t np = jacobi_np(n), nt = np / JM;
   size_t f = size_t(B) * (3 * np * np + nt * JM * JM + 1);
@@ -178,7 +185,10 @@ __global__ void jacobi_init_kernel(const float* __restrict__ G, int n, int np, f
   float* vt = Vt + int64_t(b) * np * np;
   const int64_t total = int64_t(np) * np;
   for (int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; e < total; e += int64_t(gridDim.x) * blockDim.x) {
-    const int i = int(e / np), j = int(e % np);
+    // e enumerates the blocked layout directly: e = (cb * np + i) * 32 + cj
+    const int cj = int(e & (JB - 1));
+    const int64_t t = e >> 5;
+    const int i = int(t % np), j = int(t / np) * JB + cj;
     gp[e] = (i < n && j < n) ? g[int64_t(i) * n + j] : 0.f;
     vt[e] = (i == j) ? 1.f : 0.f;
   }
@@ -235,7 +245,7 @@ __global__ void __launch_bounds__(256) jacobi_inner_kernel(float* __restrict__ G
   float* g = Gp + int64_t(b) * np * np;
   for (int e = tid; e < JM * JM; e += 256) {
     const int i = e / JM, j = e % JM;
-    S[i][j] = g[int64_t(blk_row(I, J, i)) * np + blk_row(I, J, j)];
+    S[i][j] = g[boff(np, blk_row(I, J, i), blk_row(I, J, j))];
     Qt[i][j] = (i == j) ? 1.f : 0.f;
   }
   if (tid == 0) { s_tot = 0; s_sig = 0; }
@@ -356,7 +366,7 @@ __global__ void __launch_bounds__(256) jacobi_update_kernel(float* __restrict__ 
   for (int e = tid; e < JM * JM; e += 256) {
     const int i = e / JM, j = e % JM;
     const int gj = two_sided ? blk_row(Ic, Jc, j) : slab * JM + j;
-    Tm[i][j] = base[int64_t(blk_row(Ia, Ja, i)) * np + gj];
+    Tm[i][j] = base[boff(np, blk_row(Ia, Ja, i), gj)];
     Qa[j][i] = qa[e];                 // Qb holds Q^T: Qa[k][i] = Q[k][i] = qa[i*64+k]
     if (two_sided) Qc[j][i] = qc[e];
   }
@@ -404,10 +414,10 @@ __global__ void __launch_bounds__(256) jacobi_update_kernel(float* __restrict__ 
 #pragma unroll
   for (int u = 0; u < 4; ++u) {
     const int i = ti * 4 + u;
-    const int64_t gr = int64_t(blk_row(Ia, Ja, i)) * np;
     const int j0 = tj * 4;
     const int gj = two_sided ? blk_row(Ic, Jc, j0) : slab * JM + j0;   // 4 consecutive j stay inside one block
-    *reinterpret_cast<float4*>(&base[gr + gj]) = make_float4(acc[u][0], acc[u][1], acc[u][2], acc[u][3]);
+    *reinterpret_cast<float4*>(&base[boff(np, blk_row(Ia, Ja, i), gj)]) =
+        make_float4(acc[u][0], acc[u][1], acc[u][2], acc[u][3]);
   }
 }
 
@@ -424,19 +434,20 @@ __global__ void __launch_bounds__(256) jacobi_extract_kernel(const float* __rest
   const float* vt = Vt + int64_t(b) * np * np;
   const int lane = threadIdx.x & 31;
   for (int i = blockIdx.x * 8 + (threadIdx.x >> 5); i < n; i += gridDim.x * 8) {
-    // eigenvector i is row i of Vt (SIMT update) or column i of V (tensor-core update)
-    const float* row = v_is_columns ? vt + i : vt + int64_t(i) * np;
-    const int64_t stp = v_is_columns ? np : 1;
+    // eigenvector i is row i of Vt (SIMT update) or column i of V (tensor-core update); blocked layout
     float ss = 0.f;
-    for (int j = lane; j < n; j += 32) { const float v = row[j * stp]; ss = fmaf(v, v, ss); }
+    for (int j = lane; j < n; j += 32) {
+      const float v = v_is_columns ? vt[boff(np, j, i)] : vt[boff(np, i, j)];
+      ss = fmaf(v, v, ss);
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
     const float inv = ss > 0.f ? rsqrtf(ss) : 0.f;
     if (Ut) {
       float* out = Ut + int64_t(b) * n * n + int64_t(i) * n;
-      for (int j = lane; j < n; j += 32) out[j] = row[j * stp] * inv;
+      for (int j = lane; j < n; j += 32) out[j] = (v_is_columns ? vt[boff(np, j, i)] : vt[boff(np, i, j)]) * inv;
     }
-    if (lambda && lane == 0) lambda[int64_t(b) * n + i] = gp[int64_t(i) * np + i];
+    if (lambda && lane == 0) lambda[int64_t(b) * n + i] = gp[boff(np, i, i)];
   }
   if (blockIdx.x == 0 && threadIdx.x == 0 && sweeps) {
     int s = 0;

@@ -35,7 +35,7 @@ namespace {
 constexpr int PB = 32;                 // Jacobi block width (must equal JB in erank_kernels.cu)
 constexpr int PM = 64;                 // panel width = 2 blocks
 constexpr int TM = 128;                // rows per tile
-constexpr int NSTAGE = 2;
+constexpr int NSTAGE = 1;             // one stage per CTA, two CTAs per SM (24 warps) overlap each other
 constexpr int A_RAW = TM * PM * 4;     // 32 KB: panel tile, hi part after the split (in place)
 constexpr int Q_RAW = PM * PM * 4;     // 16 KB
 constexpr int STAGE = 2 * A_RAW + 2 * Q_RAW;        // hi + lo of both operands: 96 KB
@@ -155,7 +155,7 @@ __device__ __forceinline__ TileInfo decode_tile(int tile, int njobs, int B, int 
   return ti;
 }
 
-__global__ void __launch_bounds__(384, 1) panel_update_tc_kernel(const __grid_constant__ CUtensorMap map_in0,
+__global__ void __launch_bounds__(384, 2) panel_update_tc_kernel(const __grid_constant__ CUtensorMap map_in0,
                                                                  const __grid_constant__ CUtensorMap map_in1,
                                                                  const __grid_constant__ CUtensorMap map_q,
                                                                  PanelJob pj, int njobs, int B, int np, int nb, int nt,
@@ -209,8 +209,8 @@ __global__ void __launch_bounds__(384, 1) panel_update_tc_kernel(const __grid_co
         bar_expect_tx(&raw_full[s], A_RAW + Q_RAW);
         const CUtensorMap* mp = ti.job == 0 ? &map_in0 : &map_in1;
         // panel tile: rows [mt*128, +128), column blocks I and J (32 floats = 128 B each)
-        tma_3d(st, mp, &raw_full[s], I * PB, ti.mt * TM, ti.b);
-        tma_3d(st + TM * 128, mp, &raw_full[s], J * PB, ti.mt * TM, ti.b);
+        tma_3d(st, mp, &raw_full[s], 0, ti.mt * TM, ti.b * nb + I);      // 16 KB contiguous in HBM
+        tma_3d(st + TM * 128, mp, &raw_full[s], 0, ti.mt * TM, ti.b * nb + J);
         // Q_c^T: 64 rows (j) x two 32-column halves of k
         const int qrow = (ti.b * nt + ti.c) * PM;
         tma_2d(st + 2 * A_RAW, &map_q, &raw_full[s], 0, qrow);
@@ -327,7 +327,7 @@ __global__ void __launch_bounds__(384, 1) panel_update_tc_kernel(const __grid_co
               "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
             : "r"(taddr));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        const int col0 = (half == 0 ? I : J) * PB;
+        const int cblk = (half == 0 ? I : J);
         if (debug & 2) {
           // dump the staged panel tile as the async proxy left it (after the split): element (row r, k = half*32 + j)
           const int sidx = it % NSTAGE;
@@ -340,12 +340,14 @@ __global__ void __launch_bounds__(384, 1) panel_update_tc_kernel(const __grid_co
           }
         }
         if (tr) {
-          // out[col0 + j][row]: for fixed j the 32 lanes write 32 consecutive floats
-          float* o = out + int64_t(col0) * np + row;
+          // out[row' = cblk*32 + j][col' = row]: column block row/32 (warp uniform), lane = col' % 32, so the
+          // warp writes 32 consecutive 128-byte rows = one contiguous 4 KB run
+          float* o = out + (int64_t(row >> 5) * np + cblk * PB) * PB + (row & 31);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) o[int64_t(j) * np] = __uint_as_float(v[j]);
+          for (int j = 0; j < 32; ++j) o[j * PB] = __uint_as_float(v[j]);
         } else {
-          float4* o = reinterpret_cast<float4*>(out + int64_t(row) * np + col0);
+          // out[row][cblk*32 .. +32): 128 bytes per thread, 4 KB contiguous per warp
+          float4* o = reinterpret_cast<float4*>(out + (int64_t(cblk) * np + row) * PB);
 #pragma unroll
           for (int j = 0; j < 8; ++j)
             o[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
@@ -382,8 +384,9 @@ EncodeTiledFn2 get_encode2() {
 int make_map_panel(CUtensorMap* m, const float* base, int64_t B, int np) {
   EncodeTiledFn2 enc = get_encode2();
   R3D_CHECK(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
-  const cuuint64_t gdim[3] = {(cuuint64_t)np, (cuuint64_t)np, (cuuint64_t)B};
-  const cuuint64_t gstr[2] = {(cuuint64_t)np * 4, (cuuint64_t)np * np * 4};
+  // column-block-major storage: [B * np/32 column blocks][np rows][32 floats]
+  const cuuint64_t gdim[3] = {(cuuint64_t)PB, (cuuint64_t)np, (cuuint64_t)(B * (np / PB))};
+  const cuuint64_t gstr[2] = {(cuuint64_t)PB * 4, (cuuint64_t)np * PB * 4};
   const cuuint32_t box[3] = {PB, TM, 1};
   const cuuint32_t es[3] = {1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), gdim, gstr, box, es,
@@ -435,7 +438,7 @@ int panel_tc_round(PanelTc* h, int round, int sweep, const int* cnt, const int* 
     PanelJob pj;
     pj.out0 = h->H; pj.transposed0 = 1; pj.skip_on_qflag0 = 0;
     pj.out1 = h->V; pj.transposed1 = 0; pj.skip_on_qflag1 = 1;
-    int grid = (int)std::min<int64_t>(2 * tiles_per_job, kNumSMs);
+    int grid = (int)std::min<int64_t>(2 * tiles_per_job, 2 * kNumSMs);
     if (g_panel_grid_cap > 0) grid = std::min(grid, g_panel_grid_cap);
     R3D_STAGE(ST_JACOBI_UPDATE, st);
     panel_update_tc_kernel<<<grid, 384, SMEM_TOTAL, st>>>(h->map_g, h->map_v, h->map_q, pj, 2, (int)h->B, h->np, h->nb,
@@ -446,7 +449,7 @@ int panel_tc_round(PanelTc* h, int round, int sweep, const int* cnt, const int* 
     PanelJob pj;
     pj.out0 = h->G; pj.transposed0 = 0; pj.skip_on_qflag0 = 0;
     pj.out1 = nullptr; pj.transposed1 = 0; pj.skip_on_qflag1 = 0;
-    int grid = (int)std::min<int64_t>(tiles_per_job, kNumSMs);
+    int grid = (int)std::min<int64_t>(tiles_per_job, 2 * kNumSMs);
     if (g_panel_grid_cap > 0) grid = std::min(grid, g_panel_grid_cap);
     R3D_STAGE(ST_JACOBI_UPDATE, st);
     panel_update_tc_kernel<<<grid, 384, SMEM_TOTAL, st>>>(h->map_h, h->map_h, h->map_q, pj, 1, (int)h->B, h->np, h->nb,

@@ -21,8 +21,15 @@ def run(B, npad, rnd, seed=0, simpleQ=False, debug=0, pattern=False):
         V = rng.standard_normal((B, npad, npad)).astype(np.float32)
     Q = np.tile(np.eye(64, dtype=np.float32), (B, nt, 1, 1)) if simpleQ else rng.standard_normal((B, nt, 64, 64)).astype(np.float32) / 8
     dev = torch.device('cuda')
+    def to_blocked(M):   # (B, np, np) row-major -> [B][np/32][np][32]
+        return np.ascontiguousarray(M.reshape(B, npad, npad // 32, 32).transpose(0, 2, 1, 3))
+    def from_blocked(t):
+        return t.cpu().numpy().reshape(B, npad // 32, npad, 32).transpose(0, 2, 1, 3).reshape(B, npad, npad)
+    G_rm, V_rm = G, V
+    G, V = to_blocked(G), to_blocked(V)
     Gd, Vd, Qd = torch.from_numpy(G).to(dev), torch.from_numpy(V).to(dev), torch.from_numpy(np.ascontiguousarray(Q.transpose(0, 1, 3, 2))).to(dev)
     Hd = torch.full_like(Gd, -7.0)
+    G, V = G_rm, V_rm
     scratch = torch.zeros(B * 32 + B * nt, dtype=torch.int32, device=dev)
     _lib.check(L.r3d_debug_panel_round(_p(Gd), _p(Hd), _p(Vd), _p(Qd), B, npad, rnd, _p(scratch), _stream()))
     torch.cuda.synchronize()
@@ -38,7 +45,7 @@ def run(B, npad, rnd, seed=0, simpleQ=False, debug=0, pattern=False):
     Vref = V64 @ Qf
     print(f"--- B={B} np={npad} round={rnd} simpleQ={simpleQ} debug={debug} pattern={pattern}")
     for name, got, ref in (('H', Hd, Href), ('G', Gd, Gref), ('V', Vd, Vref)):
-        g = got.cpu().numpy()
+        g = from_blocked(got)
         err = np.abs(g - ref).max() / np.abs(ref).max()
         print(f"  {name}: rel err {err:.3e} got absmax {np.abs(g).max():.3f} ref absmax {np.abs(ref).max():.3f}")
     if pattern:
