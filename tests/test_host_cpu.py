@@ -1,0 +1,182 @@
+"""CPU-only tests (-m "not gpu"): the C-ABI library loads and exports every symbol the header declares,
+the host-side module mirrors the reference interface, CPU tensors are refused, and the N > 1 host logic
+agrees with the single-process oracle under a 2-rank gloo group."""
+import os
+import re
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, golden_files
+from oracle import fuser_oracle as O
+
+
+def _header_symbols():
+    txt = open(os.path.join(ROOT, "include", "r3d_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(r3d_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_header_symbol():
+    import ctypes
+    from r3d_b200 import _lib
+    assert os.path.exists(_lib.LIB_PATH), "build the library first: python -m r3d_b200.csrc.build"
+    h = ctypes.CDLL(_lib.LIB_PATH)
+    syms = _header_symbols()
+    assert len(syms) >= 25
+    for s in syms:
+        assert hasattr(h, s), f"{s} declared in include/r3d_b200.h but not exported"
+    # and the ctypes binding covers the same set (no drift between header and host side)
+    assert set(_lib.SIGNATURES) == set(syms), set(_lib.SIGNATURES) ^ set(syms)
+    L = _lib.lib()
+    assert L.r3d_abi_version() == 1
+    assert L.r3d_score_workspace_floats(2048, 512) > 0          # size queries need no GPU
+    assert L.r3d_erank_workspace_bytes(2, 64, 128, 0) > 0
+    assert L.r3d_profile_num_stages() > 10
+
+
+def test_abi_argument_errors_without_gpu():
+    from r3d_b200 import _lib
+    L = _lib.lib()
+    rc = L.r3d_bottomk(None, 1, 16, 4, None, None)
+    assert rc != 0 and b"null" in L.r3d_last_error()
+    rc = L.r3d_exchange_fwd(None, None, None, None, 0, None, None, 0, None, 4, 16, 0, None)
+    assert rc != 0
+    rc = L.r3d_set_option(b"no_such_option", 1.0)
+    assert rc != 0 and b"unknown option" in L.r3d_last_error()
+
+
+@pytest.mark.parametrize("variant", ["tokenfusion", "vary", "batchnorm", "safuser"])
+def test_state_dict_names_match_reference(variant):
+    import r3d_b200
+    path = [p for p in golden_files(variant) if "C16" in p][0]
+    z = np.load(path)
+    ref_names = sorted(k[3:] for k in z.files if k.startswith("sd/"))
+    f = r3d_b200.CMFuser(16, depth=1, num_heads=4, variant=variant)
+    assert sorted(f.state_dict().keys()) == ref_names
+    f.load_state_dict({k: torch.from_numpy(z["sd/" + k]) for k in ref_names}, strict=True)
+    for k in ref_names:
+        assert tuple(f.state_dict()[k].shape) == tuple(z["sd/" + k].shape)
+
+
+def test_reference_constructor_and_api_surface():
+    import inspect
+    import r3d_b200
+    sig = inspect.signature(r3d_b200.CMFuser.__init__)
+    assert list(sig.parameters)[:6] == ["self", "dim", "depth", "num_heads", "mlp_ratio", "qkv_bias"]
+    assert sig.parameters["depth"].default == 1 and sig.parameters["num_heads"].default == 4
+    f = r3d_b200.CMFuser(32)
+    assert f.k_for(512) == 128 and r3d_b200.CMFuser(32, variant="batchnorm").k_for(512) == 51
+    assert r3d_b200.CMFuser(8, variant="batchnorm").k_for(8) == 0          # int(C * 0.1) == 0 is legal
+    m = r3d_b200.CMFuser.generate_cross_attention_mask(2)
+    assert torch.isinf(m[0, 0]) and m[0, 1] == 0
+    with pytest.raises(ValueError):
+        r3d_b200.CMFuser(8, variant="nope")
+
+
+def test_cpu_tensors_are_refused():
+    import r3d_b200
+    f = r3d_b200.CMFuser(16)
+    x = torch.randn(2, 3, 16)
+    with pytest.raises(r3d_b200.R3DError):
+        f.token_fusion(x, x, "test")
+    with pytest.raises(r3d_b200.R3DError):
+        r3d_b200.ops.channel_score(x, x)
+    with pytest.raises(r3d_b200.R3DError):
+        r3d_b200.ops.erank(x)
+    with pytest.raises(r3d_b200.R3DError):
+        r3d_b200.ops.bottomk(torch.randn(4, 8), 2)
+
+
+def test_block_closed_form_equals_masked_attention():
+    """The CUDA path's Block evaluates the 2x2 masked attention in closed form; check it on CPU
+    against the oracle's unsimplified arithmetic."""
+    import r3d_b200
+    torch.manual_seed(0)
+    C, H = 32, 4
+    blk = r3d_b200.Block(C, H)
+    x = torch.randn(7, 2, C)
+    y, _ = blk(x)
+    p = {"b." + k: v.detach().numpy() for k, v in blk.state_dict().items()}
+    ref, attn = O.block_forward(x.numpy().astype(np.float64), p, "b.", H)
+    np.testing.assert_allclose(y.detach().numpy(), ref, rtol=1e-4, atol=1e-5)
+    assert set(np.unique(attn)) == {0.0, 1.0}
+
+
+def test_shard_bounds_cover_batch():
+    from r3d_b200.dist import shard_bounds
+    for total in (1, 7, 64, 513):
+        for world in (1, 2, 3, 8):
+            spans = [shard_bounds(total, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _gloo_worker(rank, world, port, B, T, C, k, q):
+    import torch.distributed as dist
+    from r3d_b200 import dist as D
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(1234)
+    c = torch.arange(C, dtype=torch.float32)
+    rgb = torch.relu(torch.randn(B, T, C, generator=g)) * (1 + c / C)
+    dep = torch.relu(torch.randn(B, T, C, generator=g)) * (2 - c / C)
+    lo, hi = D.shard_bounds(B, world, rank)
+    # local partial statistics (on a GPU these come from r3d_channel_score_partial / r3d_erank_fwd)
+    sums = torch.stack([rgb[lo:hi].abs().sum(dim=(0, 1)), dep[lo:hi].abs().sum(dim=(0, 1))])
+    er_local = torch.arange(lo, hi, dtype=torch.float32).sum()          # stand-in per-sample statistic
+    packed = D.allreduce_statistics(D.pack_statistics(sums, er_local, (hi - lo) * T))
+    score, er_mean = D.unpack_statistics(packed, B)
+    idx = D.global_bottomk_indices(score, k)
+    # gradient bucket: rank-dependent grads, one unused parameter
+    p1 = torch.nn.Parameter(torch.zeros(5))
+    p2 = torch.nn.Parameter(torch.zeros(3))
+    p3 = torch.nn.Parameter(torch.zeros(2))
+    p1.grad = torch.full((5,), float(rank + 1))
+    p2.grad = None
+    p3.grad = torch.full((2,), 10.0 * (rank + 1))
+    D.GradBucket([p1, p2, p3]).allreduce(average=True)
+    q.put((rank, score.numpy(), float(er_mean), idx.numpy(), p1.grad.numpy(), p2.grad.numpy(), p3.grad.numpy()))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_matches_single_process_oracle():
+    import torch.multiprocessing as mp
+    B, T, C = 6, 9, 64
+    k = C // 4
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, B, T, C, k, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    outs = sorted([q.get(timeout=120) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    g = torch.Generator().manual_seed(1234)
+    c = torch.arange(C, dtype=torch.float32)
+    rgb = (torch.relu(torch.randn(B, T, C, generator=g)) * (1 + c / C)).numpy()
+    dep = (torch.relu(torch.randn(B, T, C, generator=g)) * (2 - c / C)).numpy()
+    ref_score = np.stack([O.channel_score(rgb), O.channel_score(dep)])
+    ref_idx = np.stack([O.bottomk(ref_score[0], k), O.bottomk(ref_score[1], k)])
+    for rank, score, er_mean, idx, g1, g2, g3 in outs:
+        np.testing.assert_allclose(score, ref_score, rtol=1e-5)            # global scope == concatenated batch
+        np.testing.assert_array_equal(idx, ref_idx)                        # identical selection on every rank
+        assert abs(er_mean - np.arange(B).mean()) < 1e-6
+        np.testing.assert_allclose(g1, 1.5)
+        np.testing.assert_allclose(g2, 0.0)
+        np.testing.assert_allclose(g3, 15.0)
+    np.testing.assert_array_equal(outs[0][3], outs[1][3])
