@@ -223,6 +223,8 @@ def main_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the single JSON line
         dist.init_process_group("nccl", device_id=dev)
     import r3d_b200
     from r3d_b200 import _lib, ops
