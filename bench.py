@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=16, help="clips per CPU-baseline step")
     ap.add_argument("--gram", default="auto", choices=["auto", "tcgen05", "simt"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], help="library tuning knob key=value (r3d_set_option)")
     return ap.parse_args()
 
 
@@ -189,8 +190,9 @@ def stage_table(prof, steps, world):
         "gram": ("tensor", 2.0 * n * n * m * nb2),
         "refine_y": ("tensor", 2.0 * n * n * m * nb2),
         "bwd_gemm": ("tensor", 2.0 * n * n * m * nb2),
-        # one round: read+write every G and Vt tile once
-        "jacobi_update": ("hbm", nb2 * (2 * npad * npad * 4) * 2),
+        # one panel pass: read + write one np x np fp32 matrix per sample (G pass 1, G pass 2, V update)
+        "jacobi_update": ("hbm", nb2 * npad * npad * 4 * 2),
+        "jacobi_vupdate": ("hbm", nb2 * npad * npad * 4 * 2),
         "sigma": ("hbm", nb2 * (n * m + n * n) * 4),
     }
     out = {}
@@ -229,6 +231,9 @@ def main_ours(args):
     import r3d_b200
     from r3d_b200 import _lib, ops
 
+    for kv in args.opt:
+        k_, v_ = kv.split("=")
+        _lib.set_option(k_, float(v_))
     dtype = torch.bfloat16
     gram_impl = {"auto": ops.GRAM_TCGEN05, "tcgen05": ops.GRAM_TCGEN05, "simt": ops.GRAM_SIMT}[args.gram]
     step = ops.FuserStep(B, T, C, dtype, dev, gram_impl=gram_impl)

@@ -140,7 +140,7 @@ static int sgemm_launch(bool ta, bool tb, const TA* A, const TB* Bm, TC* Cm, int
 //   nu  (1) absolute significance floor
 // ------------------------------------------------------------------------------
 struct JacobiWs {
-  float* Gp; float* Vt; float* H; float* Qb; int* cnt; int* qflag; float* nu;
+  float* Gp; float* Vt; float* H; float* Qb[2]; int* cnt; int* qflag[2]; float* nu;
   int np, nb, nt;
 };
 
@@ -155,8 +155,8 @@ __host__ __device__ __forceinline__ int64_t boff(int np, int r, int c) {
 
 static size_t jacobi_ws_bytes(int64_t B, int64_t n) {
   const size_t np = jacobi_np(n), nt = np / JM;
-  size_t f = size_t(B) * (3 * np * np + nt * JM * JM + 1);
-  size_t i = size_t(B) * (JMAX_SWEEPS + nt);
+  size_t f = size_t(B) * (3 * np * np + 2 * nt * JM * JM + 1);
+  size_t i = size_t(B) * (JMAX_SWEEPS + 2 * nt);
   return f * 4 + i * 4 + 256;
 }
 
@@ -169,10 +169,12 @@ static JacobiWs jacobi_carve(void* ws, int64_t B, int64_t n) {
   w.Gp = (float*)p; p += size_t(B) * np2 * 4;
   w.Vt = (float*)p; p += size_t(B) * np2 * 4;
   w.H = (float*)p; p += size_t(B) * np2 * 4;
-  w.Qb = (float*)p; p += size_t(B) * w.nt * JM * JM * 4;
+  w.Qb[0] = (float*)p; p += size_t(B) * w.nt * JM * JM * 4;
+  w.Qb[1] = (float*)p; p += size_t(B) * w.nt * JM * JM * 4;
   w.nu = (float*)p; p += size_t(B) * 4;
   w.cnt = (int*)p; p += size_t(B) * JMAX_SWEEPS * 4;
-  w.qflag = (int*)p;
+  w.qflag[0] = (int*)p; p += size_t(B) * w.nt * 4;
+  w.qflag[1] = (int*)p;
   return w;
 }
 
@@ -599,8 +601,9 @@ extern "C" int r3d_debug_panel_round(float* G, float* H, float* V, const float* 
   R3D_CUDA(cudaMemcpyAsync(qflag, ones.data(), sizeof(int) * B * nt, cudaMemcpyHostToDevice, st));
   R3D_CUDA(cudaStreamSynchronize(st));
   PanelTc ptc;
-  if (int e = panel_tc_prepare(&ptc, G, H, V, Qb, B, np)) return e;
-  return panel_tc_round(&ptc, round, 0, cnt, qflag, st);
+  if (int e = panel_tc_prepare(&ptc, G, H, V, Qb, Qb, B, np)) return e;
+  if (int e = panel_tc_update_v(&ptc, 0, round, 0, cnt, qflag, st)) return e;
+  return panel_tc_update_g(&ptc, 0, round, 0, cnt, qflag, st);
 }
 
 extern "C" int r3d_set_option(const char* key, double value) {
@@ -609,6 +612,7 @@ extern "C" int r3d_set_option(const char* key, double value) {
   if (k == "jacobi_update_tc") options().jacobi_update_tc = value != 0.0;
   else if (k == "jacobi_tol") options().jacobi_tol = (float)value;
   else if (k == "jacobi_max_sweeps") options().jacobi_max_sweeps = (int)value;
+  else if (k == "jacobi_overlap_v") options().jacobi_overlap_v = value != 0.0;
   else if (k == "panel_debug") g_panel_debug = (int)value;
   else if (k == "panel_grid_cap") g_panel_grid_cap = (int)value;
   else R3D_CHECK(false, "unknown option '%s'", key);
@@ -646,6 +650,23 @@ extern "C" int r3d_gram(const void* x, int64_t B, int64_t T, int64_t C, int dtyp
   return dtype == R3D_F32 ? gram_simt<float>(x, B, T, C, G_out, st) : gram_simt<__nv_bfloat16>(x, B, T, C, G_out, st);
 }
 
+// Library-owned side stream: the V <- V Q update of round r overlaps the inner solve of round r+1 (which needs
+// only G and leaves HBM idle).  Fork/join with events, so the pattern is also legal under stream capture.
+struct SideStream {
+  cudaStream_t st = nullptr;
+  cudaEvent_t ev_inner[2] = {nullptr, nullptr}, ev_v[2] = {nullptr, nullptr};
+  int ensure() {
+    if (st) return 0;
+    R3D_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      R3D_CUDA(cudaEventCreateWithFlags(&ev_inner[i], cudaEventDisableTiming));
+      R3D_CUDA(cudaEventCreateWithFlags(&ev_v[i], cudaEventDisableTiming));
+    }
+    return 0;
+  }
+};
+static thread_local SideStream g_side;
+
 static int jacobi_run(const float* G, int64_t B, int64_t n, void* workspace, float* lambda_out, float* U_out,
                       int32_t* sweeps_out, int max_sweeps, cudaStream_t st) {
   if (max_sweeps <= 0 || max_sweeps > JMAX_SWEEPS) max_sweeps = options().jacobi_max_sweeps;
@@ -654,8 +675,10 @@ static int jacobi_run(const float* G, int64_t B, int64_t n, void* workspace, flo
   const float tol = options().jacobi_tol;
   const bool tc = options().jacobi_update_tc != 0 && panel_tc_supported(w.np);
   PanelTc ptc;
+  const bool overlap = tc && options().jacobi_overlap_v != 0;
   if (tc) {
-    if (int e = panel_tc_prepare(&ptc, w.Gp, w.H, w.Vt, w.Qb, B, w.np)) return e;
+    if (int e = panel_tc_prepare(&ptc, w.Gp, w.H, w.Vt, w.Qb[0], w.Qb[1], B, w.np)) return e;
+    if (overlap) { if (int e = g_side.ensure()) return e; }
   }
   {
     dim3 grid(std::min<int64_t>((int64_t(w.np) * w.np + 255) / 256, 64), (unsigned)B);
@@ -667,24 +690,42 @@ static int jacobi_run(const float* G, int64_t B, int64_t n, void* workspace, flo
   R3D_CUDA(cudaFuncSetAttribute(jacobi_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)upd_smem));
   const int rounds = w.nb - 1;
   const int upd_tiles = w.nt * w.nt + w.nt * (w.np / JM);
+  int iter = 0;
+  bool v_pending[2] = {false, false};
   for (int sweep = 0; sweep < max_sweeps; ++sweep) {
-    for (int r = 0; r < rounds; ++r) {
+    for (int r = 0; r < rounds; ++r, ++iter) {
+      const int qb = tc ? (iter & 1) : 0;
+      if (overlap && v_pending[qb]) {        // the V update that last read this Q buffer must be done
+        R3D_CUDA(cudaStreamWaitEvent(st, g_side.ev_v[qb], 0));
+        v_pending[qb] = false;
+      }
       {
         R3D_STAGE(ST_JACOBI_INNER, st);
-        jacobi_inner_kernel<<<dim3(w.nt, (unsigned)B), 256, 0, st>>>(w.Gp, w.np, w.nb, w.nt, r, sweep, w.cnt, w.qflag,
-                                                                    w.Qb, tol, w.nu, 1);
+        jacobi_inner_kernel<<<dim3(w.nt, (unsigned)B), 256, 0, st>>>(w.Gp, w.np, w.nb, w.nt, r, sweep, w.cnt,
+                                                                    w.qflag[qb], w.Qb[qb], tol, w.nu, 1);
         R3D_LAUNCH_CHECK();
       }
       if (tc) {
-        if (int e = panel_tc_round(&ptc, r, sweep, w.cnt, w.qflag, st)) return e;
+        if (overlap) {
+          R3D_CUDA(cudaEventRecord(g_side.ev_inner[qb], st));
+          R3D_CUDA(cudaStreamWaitEvent(g_side.st, g_side.ev_inner[qb], 0));
+          if (int e = panel_tc_update_v(&ptc, qb, r, sweep, w.cnt, w.qflag[qb], g_side.st)) return e;
+          R3D_CUDA(cudaEventRecord(g_side.ev_v[qb], g_side.st));
+          v_pending[qb] = true;
+        } else {
+          if (int e = panel_tc_update_v(&ptc, qb, r, sweep, w.cnt, w.qflag[qb], st)) return e;
+        }
+        if (int e = panel_tc_update_g(&ptc, qb, r, sweep, w.cnt, w.qflag[qb], st)) return e;
       } else {
         R3D_STAGE(ST_JACOBI_UPDATE, st);
         jacobi_update_kernel<<<dim3(upd_tiles, (unsigned)B), 256, upd_smem, st>>>(w.Gp, w.Vt, w.np, w.nb, w.nt, r,
-                                                                                 sweep, w.cnt, w.qflag, w.Qb);
+                                                                                 sweep, w.cnt, w.qflag[qb], w.Qb[qb]);
         R3D_LAUNCH_CHECK();
       }
     }
   }
+  for (int i = 0; i < 2; ++i)
+    if (overlap && v_pending[i]) R3D_CUDA(cudaStreamWaitEvent(st, g_side.ev_v[i], 0));
   {
     dim3 grid((unsigned)std::min<int64_t>((n + 7) / 8, 64), (unsigned)B);
     R3D_STAGE(ST_JACOBI_EXTRACT, st);

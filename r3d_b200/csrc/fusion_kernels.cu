@@ -606,7 +606,7 @@ extern "C" const char* r3d_profile_stage_name(int stage) {
   static const char* names[ST_NUM] = {"score_partial", "score_finalize", "bottomk", "exchange_fwd", "exchange_bwd",
                                       "colsum_finalize", "bn_stats", "bn_bwd", "gram", "jacobi_init", "jacobi_inner",
                                       "jacobi_update", "jacobi_extract", "refine_y", "sigma", "entropy", "coef",
-                                      "bwd_gemm", "token_info", "block"};
+                                      "bwd_gemm", "token_info", "block", "jacobi_vupdate"};
   return (stage >= 0 && stage < ST_NUM) ? names[stage] : "?";
 }
 extern "C" int r3d_profile_read(double* ms_out, int64_t* calls_out, int64_t* launches_out, int reset) {

@@ -239,6 +239,7 @@ __global__ void __launch_bounds__(384, 2) panel_update_tc_kernel(const __grid_co
 #pragma unroll
         for (int prod = 0; prod < 3; ++prod) {
           if ((debug & 1) && prod > 0) break;
+          if (debug & 16) break;                      // timing experiment: no MMAs at all
           const uint32_t ab = (prod == 2) ? a_lo : a_hi;
           const uint32_t qb = (prod == 1) ? q_lo : q_hi;
 #pragma unroll
@@ -339,6 +340,7 @@ __global__ void __launch_bounds__(384, 2) panel_update_tc_kernel(const __grid_co
             v[j] = *reinterpret_cast<const uint32_t*>(abase + r * 128 + chunk * 16 + (j & 3) * 4);
           }
         }
+        if (debug & 8) continue;                      // timing experiment: no global stores
         if (tr) {
           // out[row' = cblk*32 + j][col' = row]: column block row/32 (warp uniform), lane = col' % 32, so the
           // warp writes 32 consecutive 128-byte rows = one contiguous 4 KB run
@@ -413,12 +415,14 @@ int make_map_q(CUtensorMap* m, const float* base, int64_t rows) {
 
 bool panel_tc_supported(int np) { return np % TM == 0; }
 
-int panel_tc_prepare(PanelTc* h, float* G, float* H, float* V, const float* Qb, int64_t B, int np) {
+int panel_tc_prepare(PanelTc* h, float* G, float* H, float* V, const float* Qb0, const float* Qb1, int64_t B,
+                     int np) {
   h->G = G; h->H = H; h->V = V; h->B = B; h->np = np; h->nb = np / PB; h->nt = np / PM;
   if (int e = make_map_panel(&h->map_g, G, B, np)) return e;
   if (int e = make_map_panel(&h->map_h, H, B, np)) return e;
   if (int e = make_map_panel(&h->map_v, V, B, np)) return e;
-  if (int e = make_map_q(&h->map_q, Qb, B * h->nt * PM)) return e;
+  if (int e = make_map_q(&h->map_q[0], Qb0, B * h->nt * PM)) return e;
+  if (int e = make_map_q(&h->map_q[1], Qb1, B * h->nt * PM)) return e;
   static bool attr_done = false;
   if (!attr_done) {
     R3D_CUDA(cudaFuncSetAttribute(panel_update_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
@@ -427,36 +431,35 @@ int panel_tc_prepare(PanelTc* h, float* G, float* H, float* V, const float* Qb, 
   return 0;
 }
 
-// One round: launch 1 = { H^T <- (G Q)^T  (transposed store),  V <- V Q (in place) },
-//            launch 2 = { G <- H^T Q }.
 int g_panel_debug = 0;
 int g_panel_grid_cap = 0;
-int panel_tc_round(PanelTc* h, int round, int sweep, const int* cnt, const int* qflag, cudaStream_t st) {
+
+static int panel_launch(PanelTc* h, const CUtensorMap& in, const CUtensorMap& q, float* out, int transposed,
+                        int skip_on_qflag, int round, int sweep, const int* cnt, const int* qflag, int stage_id,
+                        cudaStream_t st) {
   const int mtiles = h->np / TM;
-  const int64_t tiles_per_job = h->B * h->nt * mtiles;
-  {
-    PanelJob pj;
-    pj.out0 = h->H; pj.transposed0 = 1; pj.skip_on_qflag0 = 0;
-    pj.out1 = h->V; pj.transposed1 = 0; pj.skip_on_qflag1 = 1;
-    int grid = (int)std::min<int64_t>(2 * tiles_per_job, 2 * kNumSMs);
-    if (g_panel_grid_cap > 0) grid = std::min(grid, g_panel_grid_cap);
-    R3D_STAGE(ST_JACOBI_UPDATE, st);
-    panel_update_tc_kernel<<<grid, 384, SMEM_TOTAL, st>>>(h->map_g, h->map_v, h->map_q, pj, 2, (int)h->B, h->np, h->nb,
-                                                          h->nt, round, sweep, cnt, qflag, g_panel_debug);
-    R3D_LAUNCH_CHECK();
-  }
-  {
-    PanelJob pj;
-    pj.out0 = h->G; pj.transposed0 = 0; pj.skip_on_qflag0 = 0;
-    pj.out1 = nullptr; pj.transposed1 = 0; pj.skip_on_qflag1 = 0;
-    int grid = (int)std::min<int64_t>(tiles_per_job, 2 * kNumSMs);
-    if (g_panel_grid_cap > 0) grid = std::min(grid, g_panel_grid_cap);
-    R3D_STAGE(ST_JACOBI_UPDATE, st);
-    panel_update_tc_kernel<<<grid, 384, SMEM_TOTAL, st>>>(h->map_h, h->map_h, h->map_q, pj, 1, (int)h->B, h->np, h->nb,
-                                                          h->nt, round, sweep, cnt, qflag, g_panel_debug);
-    R3D_LAUNCH_CHECK();
-  }
+  const int64_t tiles = h->B * h->nt * mtiles;
+  PanelJob pj;
+  pj.out0 = out; pj.transposed0 = transposed; pj.skip_on_qflag0 = skip_on_qflag;
+  pj.out1 = nullptr; pj.transposed1 = 0; pj.skip_on_qflag1 = 0;
+  int grid = (int)std::min<int64_t>(tiles, 2 * kNumSMs);
+  if (g_panel_grid_cap > 0) grid = std::min(grid, g_panel_grid_cap);
+  StageScope scope(stage_id, st);
+  panel_update_tc_kernel<<<grid, 384, SMEM_TOTAL, st>>>(in, in, q, pj, 1, (int)h->B, h->np, h->nb, h->nt, round, sweep,
+                                                        cnt, qflag, g_panel_debug);
+  R3D_LAUNCH_CHECK();
   return 0;
+}
+
+int panel_tc_update_g(PanelTc* h, int qbuf, int round, int sweep, const int* cnt, const int* qflag, cudaStream_t st) {
+  // pass 1: H^T = (G Q)^T (transposed store);  pass 2: G = H^T Q.  Identity tasks cannot be skipped (ping-pong).
+  if (int e = panel_launch(h, h->map_g, h->map_q[qbuf], h->H, 1, 0, round, sweep, cnt, qflag, ST_JACOBI_UPDATE, st))
+    return e;
+  return panel_launch(h, h->map_h, h->map_q[qbuf], h->G, 0, 0, round, sweep, cnt, qflag, ST_JACOBI_UPDATE, st);
+}
+
+int panel_tc_update_v(PanelTc* h, int qbuf, int round, int sweep, const int* cnt, const int* qflag, cudaStream_t st) {
+  return panel_launch(h, h->map_v, h->map_q[qbuf], h->V, 0, 1, round, sweep, cnt, qflag, ST_JACOBI_VUPDATE, st);
 }
 
 }  // namespace r3d

@@ -6,19 +6,23 @@
 
 namespace r3d {
 struct PanelTc {
-  CUtensorMap map_g, map_h, map_v, map_q;
+  CUtensorMap map_g, map_h, map_v, map_q[2];   // Q^T is double-buffered (round parity)
   float *G, *H, *V;
   int64_t B;
   int np, nb, nt;
 };
 bool panel_tc_supported(int np);
-int panel_tc_prepare(PanelTc* h, float* G, float* H, float* V, const float* Qb, int64_t B, int np);
-int panel_tc_round(PanelTc* h, int round, int sweep, const int* cnt, const int* qflag, cudaStream_t st);
+int panel_tc_prepare(PanelTc* h, float* G, float* H, float* V, const float* Qb0, const float* Qb1, int64_t B, int np);
+// G <- Q^T G Q for one round (two launches on `st`): pass 1 writes (G Q)^T into H, pass 2 H Q back into G.
+int panel_tc_update_g(PanelTc* h, int qbuf, int round, int sweep, const int* cnt, const int* qflag, cudaStream_t st);
+// V <- V Q for one round (one launch on `st`); independent of the G update and of the next inner solve.
+int panel_tc_update_v(PanelTc* h, int qbuf, int round, int sweep, const int* cnt, const int* qflag, cudaStream_t st);
 
 struct Options {
   int jacobi_update_tc = 1;     // 1: tcgen05 3xTF32 panel update, 0: SIMT fp32 tile update
   float jacobi_tol = 1e-5f;     // relative off-diagonal threshold
   int jacobi_max_sweeps = 16;
+  int jacobi_overlap_v = 1;     // run V <- V Q on a side stream, overlapped with the next inner solve
 };
 Options& options();
 }  // namespace r3d
