@@ -213,6 +213,47 @@ def stage_table(prof, steps, world):
     return out, pk
 
 
+def full_fuser_numbers(dev, dtype, steps=5):
+    """Whole CMFuser forward+backward (token fusion + Block + LN + mean) at the headline shape: this repo's module
+    vs the reference's own op sequence (oracle/torch_port.py: full qkv GEMM, 2x2 masked softmax, clone + index_put
+    + stack) run eagerly on the same GPU.  Reported as an extra; the Block still uses library GEMMs."""
+    import torch
+    import r3d_b200
+    from oracle.torch_port import PortCMFuser
+    out = {}
+    buf = synth_host(99, B, dtype).to(dev)
+    gy = torch.randn(B, T, C, device=dev, dtype=dtype)
+    torch.manual_seed(0)
+    ref = PortCMFuser(C, depth=1, num_heads=8, variant="tokenfusion").to(dev).to(dtype).train()
+    ours = r3d_b200.CMFuser(C, depth=1, num_heads=8).to(dev).to(dtype).train()
+    ours.load_state_dict(ref.state_dict())
+    ref.embd_drop.p = ours.embd_drop.p = 0.0
+
+    def run(mod):
+        r = buf[0].clone().requires_grad_(True)
+        d = buf[1].clone().requires_grad_(True)
+        y = mod({"rgb": r, "depth": d}, "test")
+        y.backward(gy)
+        return y
+
+    for name, mod in (("ours", ours), ("reference_ops_eager_gpu", ref)):
+        try:
+            for _ in range(3):
+                y = run(mod)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                y = run(mod)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            out[name] = {"ms_per_step": ms, "clips_per_s": B / ms * 1e3}
+        except Exception as ex:   # pragma: no cover
+            out[name] = {"error": repr(ex)[:200]}
+    return out
+
+
 def main_ours(args):
     import torch
     import torch.distributed as dist
@@ -302,9 +343,14 @@ def main_ours(args):
     stages, pk = stage_table(prof, args.steps, world)
     dom = max(stages.items(), key=lambda kv: kv[1]["ms_per_step"])
     dname, d = dom
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tp):
+        with open(tp) as f:
+            traffic = json.load(f).get(dname)
     roofline = {"kernel": dname, "bound": d.get("bound", "hbm"), "achieved": d.get("achieved"),
                 "peak": d.get("peak"), "unit": d.get("unit", "GB/s"), "frac": d.get("frac"),
-                "peak_source": pk["source"], "traffic": None,
+                "peak_source": pk["source"], "traffic": traffic,
                 "share_of_step": d["ms_per_step"] / (ms / args.steps)}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -322,6 +368,8 @@ def main_ours(args):
         "roofline": roofline,
         "stages": stages,
     }
+    if world == 1:
+        line["full_fuser_fwd_bwd"] = full_fuser_numbers(dev, dtype)
     if world == 1 and not args.no_cpu_baseline:
         val, cms = run_cpu(4, 1, args.cpu_sample)
         line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",

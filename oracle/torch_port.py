@@ -111,7 +111,7 @@ class PortCMFuser(nn.Module):
                     s_r = g[0].abs().mean(dim=(0, 1))
                     s_d = g[1].abs().mean(dim=(0, 1))
                 else:
-                    s_r = s_d = torch.full((C,), 1.0 / (B * T * C))
+                    s_r = s_d = torch.full((C,), 1.0 / (B * T * C), device=rgb.device)
             else:
                 s_r, s_d = rgb.abs().mean(dim=(0, 1)), depth.abs().mean(dim=(0, 1))
             k = C // 4
@@ -141,7 +141,8 @@ class PortCMFuser(nn.Module):
     def forward(self, modal_feats, mode="test"):
         rgb, depth = modal_feats["rgb"], modal_feats["depth"]
         B, T, C = rgb.shape
-        mask = torch.zeros(2, 2).masked_fill(torch.eye(2) == 1, float("-inf"))
+        mask = torch.zeros(2, 2, device=rgb.device, dtype=rgb.dtype).masked_fill(
+            torch.eye(2, device=rgb.device) == 1, float("-inf"))
         if self.variant == "safuser":
             st = torch.stack([rgb, depth], dim=2) + self.modality_token
         else:
