@@ -1,5 +1,7 @@
-// Batched Gram matrix on 5th-generation tensor cores (sm_100a):  G[b] = X[b]^T X[b]
-// (channel side, n = C) for bf16 X of shape (B, T, C), fp32 accumulation in TMEM.
+// Batched Gram matrix on 5th-generation tensor cores (sm_100a) for bf16 X of shape (B, T, C), fp32
+// accumulation in TMEM:  channel side  G[b] = X[b]^T X[b]  (n = C, T >= C; operands MN-major) and token side
+// G[b] = X[b] X[b]^T  (n = T, T < C; operands K-major).  The two variants differ only in the TMA box, the
+// shared-memory descriptor and the major bits of the instruction descriptor.
 //
 //   * operands are staged by TMA (cp.async.bulk.tensor.3d, 128-byte swizzle) straight
 //     from the row-major (T, C) sample: a box of 64 channels x BK tokens is exactly one
@@ -84,9 +86,11 @@ __device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t saddr, uint32_t 
 }
 
 // cute::UMMA::InstrDescriptor: c_format F32 (bit 4), a/b format BF16 (bits 7, 10),
-// a/b major MN (bits 15, 16), N >> 3 at [17,23), M >> 4 at [24,29).
-constexpr uint32_t kInstrDesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
-                                (uint32_t(TILE_N >> 3) << 17) | (uint32_t(TILE_M >> 4) << 24);
+// a/b major (bits 15, 16: 1 = MN-major, 0 = K-major), N >> 3 at [17,23), M >> 4 at [24,29).
+constexpr uint32_t kInstrDescMN = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                                  (uint32_t(TILE_N >> 3) << 17) | (uint32_t(TILE_M >> 4) << 24);
+constexpr uint32_t kInstrDescK = (1u << 4) | (1u << 7) | (1u << 10) |
+                                 (uint32_t(TILE_N >> 3) << 17) | (uint32_t(TILE_M >> 4) << 24);
 
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                           uint32_t accumulate) {
@@ -102,8 +106,11 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                : "memory");
 }
 
-__global__ void __launch_bounds__(256, 2) gram_cside_bf16_kernel(const __grid_constant__ CUtensorMap tmap,
-                                                                 float* __restrict__ G, int T, int C) {
+// TSIDE = false: n = C, K runs over tokens (BK = 64 tokens per stage).
+// TSIDE = true : n = T, K runs over channels (64 channels = one 128-byte swizzle row per stage).
+template <bool TSIDE>
+__global__ void __launch_bounds__(256, 2) gram_bf16_kernel(const __grid_constant__ CUtensorMap tmap,
+                                                           float* __restrict__ G, int T, int C) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)((uintptr_t(smem_raw) + 1023) & ~uintptr_t(1023));   // SWIZZLE_128B needs 1024 B
   uint64_t* full_bar = (uint64_t*)(smem + STAGES * STAGE_BYTES);
@@ -112,11 +119,12 @@ __global__ void __launch_bounds__(256, 2) gram_cside_bf16_kernel(const __grid_co
   uint32_t* tmem_slot = (uint32_t*)(tmem_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_tiles = C / TILE_N, m_tiles = C / TILE_M;
+  const int n = TSIDE ? T : C, kdim = TSIDE ? C : T;
+  const int n_tiles = (n + TILE_N - 1) / TILE_N, m_tiles = (n + TILE_M - 1) / TILE_M;
   const int b = blockIdx.x / (n_tiles * m_tiles);
   const int rem = blockIdx.x % (n_tiles * m_tiles);
   const int m0 = (rem / n_tiles) * TILE_M, n0 = (rem % n_tiles) * TILE_N;
-  const int num_kb = (T + BK - 1) / BK;
+  const int num_kb = (kdim + BK - 1) / BK;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
@@ -145,12 +153,21 @@ __global__ void __launch_bounds__(256, 2) gram_cside_bf16_kernel(const __grid_co
         mbar_wait(&empty_bar[s], ph ^ 1);
         uint8_t* stage = smem + s * STAGE_BYTES;
         mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+        if (!TSIDE) {
+          // boxes of 64 channels x 64 tokens: one MN-major slab each (8 KB)
 #pragma unroll
-        for (int h = 0; h < TILE_M / BOX_C; ++h)
-          tma_load_3d(stage + h * SLAB_BYTES, &tmap, &full_bar[s], m0 + h * BOX_C, kb * BK, b);
+          for (int h = 0; h < TILE_M / BOX_C; ++h)
+            tma_load_3d(stage + h * SLAB_BYTES, &tmap, &full_bar[s], m0 + h * BOX_C, kb * BK, b);
 #pragma unroll
-        for (int q = 0; q < TILE_N / BOX_C; ++q)
-          tma_load_3d(stage + A_BYTES + q * SLAB_BYTES, &tmap, &full_bar[s], n0 + q * BOX_C, kb * BK, b);
+          for (int q = 0; q < TILE_N / BOX_C; ++q)
+            tma_load_3d(stage + A_BYTES + q * SLAB_BYTES, &tmap, &full_bar[s], n0 + q * BOX_C, kb * BK, b);
+        } else {
+          // boxes of 64 channels x 128 tokens: K-major rows of 128 bytes (16 KB each)
+          tma_load_3d(stage, &tmap, &full_bar[s], kb * BK, m0, b);
+#pragma unroll
+          for (int q = 0; q < TILE_N / 128; ++q)
+            tma_load_3d(stage + A_BYTES + q * 16384, &tmap, &full_bar[s], kb * BK, n0 + q * 128, b);
+        }
       }
     }
   } else if (warp == 1) {
@@ -165,10 +182,17 @@ __global__ void __launch_bounds__(256, 2) gram_cside_bf16_kernel(const __grid_co
         const uint32_t b_addr = a_addr + A_BYTES;
 #pragma unroll
         for (int k = 0; k < BK / 16; ++k) {
-          // 16 tokens = two 8-row swizzle groups of 1024 B; slabs (64 channels) are SLAB_BYTES apart
-          const uint64_t ad = make_desc_mn_sw128(a_addr + k * 2048, SLAB_BYTES, 1024);
-          const uint64_t bd = make_desc_mn_sw128(b_addr + k * 2048, SLAB_BYTES, 1024);
-          umma_bf16(tmem_base, ad, bd, kInstrDesc, (kb | k) != 0);
+          if (!TSIDE) {
+            // 16 tokens = two 8-row swizzle groups of 1024 B; slabs (64 channels) are SLAB_BYTES apart
+            const uint64_t ad = make_desc_mn_sw128(a_addr + k * 2048, SLAB_BYTES, 1024);
+            const uint64_t bd = make_desc_mn_sw128(b_addr + k * 2048, SLAB_BYTES, 1024);
+            umma_bf16(tmem_base, ad, bd, kInstrDescMN, (kb | k) != 0);
+          } else {
+            // K-major: 16 channels = 32 bytes inside the 128-byte swizzle row; 8-row groups are 1024 B apart
+            const uint64_t ad = make_desc_mn_sw128(a_addr + k * 32, 16, 1024);
+            const uint64_t bd = make_desc_mn_sw128(b_addr + k * 32, 16, 1024);
+            umma_bf16(tmem_base, ad, bd, kInstrDescK, (kb | k) != 0);
+          }
         }
         umma_commit(&empty_bar[s]);          // frees the smem stage once these MMAs have read it
       }
@@ -180,7 +204,7 @@ __global__ void __launch_bounds__(256, 2) gram_cside_bf16_kernel(const __grid_co
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int q = warp & 3;                          // this warp may touch TMEM lanes [32q, 32q+32)
     const int row = m0 + q * 32 + lane;
-    float* grow = G + (int64_t(b) * C + row) * C + n0;
+    float* grow = G + (int64_t(b) * n + row) * n + n0;
 #pragma unroll 1
     for (int c0 = 0; c0 < TILE_N; c0 += 32) {
       uint32_t v[32];
@@ -195,11 +219,19 @@ __global__ void __launch_bounds__(256, 2) gram_cside_bf16_kernel(const __grid_co
             "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
           : "r"(taddr));
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (row < n) {
+        if (n0 + c0 + 32 <= n && (n & 3) == 0) {
 #pragma unroll
-      for (int j = 0; j < 32; j += 4)
-        __stcs(reinterpret_cast<float4*>(grow + c0 + j),
-               make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                           __uint_as_float(v[j + 3])));
+          for (int j = 0; j < 32; j += 4)
+            __stcs(reinterpret_cast<float4*>(grow + c0 + j),
+                   make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                               __uint_as_float(v[j + 3])));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (n0 + c0 + j < n) grow[c0 + j] = __uint_as_float(v[j]);
+        }
+      }
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -228,8 +260,11 @@ EncodeTiledFn get_encode() {
 }  // namespace
 
 bool gram_tcgen05_supported(int64_t B, int64_t T, int64_t C, int dtype) {
-  // channel-side (T >= C) bf16 with whole tiles; everything else takes the SIMT Gram for now
-  return dtype == R3D_BF16 && T >= C && C % TILE_N == 0 && T >= 1 && B >= 1 && B * (C / TILE_M) * (C / TILE_N) < (1ll << 31);
+  // bf16 with a 16-byte-aligned row pitch; fp32 inputs take the SIMT Gram (32-bit MN-major operands need the
+  // SWIZZLE_128B_BASE32B layout -- not implemented yet)
+  const int64_t n = T < C ? T : C;
+  const int64_t tiles = B * ((n + TILE_M - 1) / TILE_M) * ((n + TILE_N - 1) / TILE_N);
+  return dtype == R3D_BF16 && C % 8 == 0 && T >= 1 && B >= 1 && tiles < (1ll << 31);
 }
 
 int gram_tcgen05_launch(const void* x, int64_t B, int64_t T, int64_t C, int dtype, void* workspace, float* G,
@@ -239,10 +274,12 @@ int gram_tcgen05_launch(const void* x, int64_t B, int64_t T, int64_t C, int dtyp
   R3D_CHECK((reinterpret_cast<uintptr_t>(x) & 15) == 0, "x must be 16-byte aligned for TMA");
   EncodeTiledFn enc = get_encode();
   R3D_CHECK(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+  const bool tside = T < C;
+  const int64_t n = tside ? T : C;
   CUtensorMap tmap;
   const cuuint64_t gdim[3] = {(cuuint64_t)C, (cuuint64_t)T, (cuuint64_t)B};
   const cuuint64_t gstride[2] = {(cuuint64_t)C * 2, (cuuint64_t)T * C * 2};   // bytes, dims 1 and 2
-  const cuuint32_t box[3] = {BOX_C, BK, 1};
+  const cuuint32_t box[3] = {BOX_C, (cuuint32_t)(tside ? 128 : BK), 1};
   const cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(x), gdim, gstride, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -250,12 +287,14 @@ int gram_tcgen05_launch(const void* x, int64_t B, int64_t T, int64_t C, int dtyp
   R3D_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with %d", (int)r);
   static bool attr_done = false;
   if (!attr_done) {
-    R3D_CUDA(cudaFuncSetAttribute(gram_cside_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    R3D_CUDA(cudaFuncSetAttribute(gram_bf16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    R3D_CUDA(cudaFuncSetAttribute(gram_bf16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr_done = true;
   }
-  const int grid = int(B * (C / TILE_M) * (C / TILE_N));
+  const int grid = int(B * ((n + TILE_M - 1) / TILE_M) * ((n + TILE_N - 1) / TILE_N));
   R3D_STAGE(ST_GRAM, st);
-  gram_cside_bf16_kernel<<<grid, 256, SMEM_BYTES, st>>>(tmap, G, int(T), int(C));
+  if (tside) gram_bf16_kernel<true><<<grid, 256, SMEM_BYTES, st>>>(tmap, G, int(T), int(C));
+  else gram_bf16_kernel<false><<<grid, 256, SMEM_BYTES, st>>>(tmap, G, int(T), int(C));
   R3D_LAUNCH_CHECK();
   return 0;
 }

@@ -382,16 +382,19 @@ def test_host_buffer_entry(dev):
     np.testing.assert_array_equal(out.numpy(), ref)
 
 
-@pytest.mark.parametrize("B,T,C", [(2, 512, 512), (1, 600, 256), (3, 2048, 1024), (2, 1000, 768)])
+@pytest.mark.parametrize("B,T,C", [(2, 512, 512), (1, 600, 256), (3, 2048, 1024), (2, 1000, 768),   # channel side
+                                   (2, 256, 512), (3, 128, 1024), (2, 200, 264), (2, 64, 2048),      # token side
+                                   (2, 100, 72), (1, 300, 328), (3, 40, 72)])                         # ragged tiles
 def test_gram_tcgen05_vs_oracle(B, T, C, dev):
-    """bf16 channel-side Gram on tcgen05/TMA against float64 numpy and against the SIMT kernel."""
+    """bf16 Gram on tcgen05/TMA (both sides, ragged edges) against float64 numpy and against the SIMT kernel."""
     from r3d_b200 import ops
     x = torch.from_numpy(_spectra("relu", B, T, C, 9)).to(torch.bfloat16)
     xd = x.to(dev)
     G = ops.gram(xd, ops.GRAM_TCGEN05).cpu().numpy()
     xf = x.float().numpy().astype(np.float64)
-    Gr = np.einsum("btc,btd->bcd", xf, xf)
-    assert G.shape == (B, C, C)
+    Gr = xf.transpose(0, 2, 1) @ xf if T >= C else xf @ xf.transpose(0, 2, 1)
+    n = min(T, C)
+    assert G.shape == (B, n, n)
     err = np.abs(G - Gr).max() / np.abs(Gr).max()
     Gs = ops.gram(xd, ops.GRAM_SIMT).cpu().numpy()
     err_s = np.abs(Gs - Gr).max() / np.abs(Gr).max()
