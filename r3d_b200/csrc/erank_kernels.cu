@@ -153,11 +153,11 @@ __host__ __device__ __forceinline__ int64_t boff(int np, int r, int c) {
   return (int64_t(c >> 5) * np + r) * JB + (c & (JB - 1));
 }
 
-static size_t jacobi_ws_bytes(int64_t B, int64_t n) {
+static size_t jacobi_ws_bytes(int64_t B, int64_t n) {   // includes slack so that two half-batch carvings fit
   const size_t np = jacobi_np(n), nt = np / JM;
   size_t f = size_t(B) * (3 * np * np + 2 * nt * JM * JM + 1);
   size_t i = size_t(B) * (JMAX_SWEEPS + 2 * nt);
-  return f * 4 + i * 4 + 256;
+  return f * 4 + i * 4 + 2048;
 }
 
 static JacobiWs jacobi_carve(void* ws, int64_t B, int64_t n) {
@@ -613,6 +613,7 @@ extern "C" int r3d_set_option(const char* key, double value) {
   else if (k == "jacobi_tol") options().jacobi_tol = (float)value;
   else if (k == "jacobi_max_sweeps") options().jacobi_max_sweeps = (int)value;
   else if (k == "jacobi_overlap_v") options().jacobi_overlap_v = value != 0.0;
+  else if (k == "jacobi_chunks") options().jacobi_chunks = (int)value;
   else if (k == "panel_debug") g_panel_debug = (int)value;
   else if (k == "panel_grid_cap") g_panel_grid_cap = (int)value;
   else R3D_CHECK(false, "unknown option '%s'", key);
@@ -650,25 +651,36 @@ extern "C" int r3d_gram(const void* x, int64_t B, int64_t T, int64_t C, int dtyp
   return dtype == R3D_F32 ? gram_simt<float>(x, B, T, C, G_out, st) : gram_simt<__nv_bfloat16>(x, B, T, C, G_out, st);
 }
 
-// Library-owned side stream: the V <- V Q update of round r overlaps the inner solve of round r+1 (which needs
-// only G and leaves HBM idle).  Fork/join with events, so the pattern is also legal under stream capture.
-struct SideStream {
-  cudaStream_t st = nullptr;
-  cudaEvent_t ev_inner[2] = {nullptr, nullptr}, ev_v[2] = {nullptr, nullptr};
+// Library-owned streams.  (1) Per chunk, the V <- V Q update of round r runs on a side stream and overlaps the
+// inner solve of round r+1 (which needs only G and leaves HBM idle).  (2) The batch is split into two chunks
+// whose Jacobi iterations run on two streams, so one chunk's issue-bound inner solve overlaps the other's
+// HBM-bound panel passes.  Fork/join with events only, so the pattern is also legal under stream capture.
+constexpr int kMaxChunks = 2;
+struct StreamSet {
+  bool ready = false;
+  cudaStream_t chunk[kMaxChunks] = {nullptr, nullptr};     // chunk 0 uses the caller's stream
+  cudaStream_t vst[kMaxChunks] = {nullptr, nullptr};
+  cudaEvent_t ev_inner[kMaxChunks][2], ev_v[kMaxChunks][2], ev_fork, ev_join[kMaxChunks];
   int ensure() {
-    if (st) return 0;
-    R3D_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; ++i) {
-      R3D_CUDA(cudaEventCreateWithFlags(&ev_inner[i], cudaEventDisableTiming));
-      R3D_CUDA(cudaEventCreateWithFlags(&ev_v[i], cudaEventDisableTiming));
+    if (ready) return 0;
+    for (int c = 0; c < kMaxChunks; ++c) {
+      R3D_CUDA(cudaStreamCreateWithFlags(&chunk[c], cudaStreamNonBlocking));
+      R3D_CUDA(cudaStreamCreateWithFlags(&vst[c], cudaStreamNonBlocking));
+      R3D_CUDA(cudaEventCreateWithFlags(&ev_join[c], cudaEventDisableTiming));
+      for (int i = 0; i < 2; ++i) {
+        R3D_CUDA(cudaEventCreateWithFlags(&ev_inner[c][i], cudaEventDisableTiming));
+        R3D_CUDA(cudaEventCreateWithFlags(&ev_v[c][i], cudaEventDisableTiming));
+      }
     }
+    R3D_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+    ready = true;
     return 0;
   }
 };
-static thread_local SideStream g_side;
+static thread_local StreamSet g_streams;
 
 static int jacobi_run(const float* G, int64_t B, int64_t n, void* workspace, float* lambda_out, float* U_out,
-                      int32_t* sweeps_out, int max_sweeps, cudaStream_t st) {
+                      int32_t* sweeps_out, int max_sweeps, cudaStream_t st, int chunk = 0) {
   if (max_sweeps <= 0 || max_sweeps > JMAX_SWEEPS) max_sweeps = options().jacobi_max_sweeps;
   if (max_sweeps <= 0 || max_sweeps > JMAX_SWEEPS) max_sweeps = 16;
   JacobiWs w = jacobi_carve(workspace, B, n);
@@ -678,7 +690,7 @@ static int jacobi_run(const float* G, int64_t B, int64_t n, void* workspace, flo
   const bool overlap = tc && options().jacobi_overlap_v != 0;
   if (tc) {
     if (int e = panel_tc_prepare(&ptc, w.Gp, w.H, w.Vt, w.Qb[0], w.Qb[1], B, w.np)) return e;
-    if (overlap) { if (int e = g_side.ensure()) return e; }
+    if (overlap) { if (int e = g_streams.ensure()) return e; }
   }
   {
     dim3 grid(std::min<int64_t>((int64_t(w.np) * w.np + 255) / 256, 64), (unsigned)B);
@@ -696,7 +708,7 @@ static int jacobi_run(const float* G, int64_t B, int64_t n, void* workspace, flo
     for (int r = 0; r < rounds; ++r, ++iter) {
       const int qb = tc ? (iter & 1) : 0;
       if (overlap && v_pending[qb]) {        // the V update that last read this Q buffer must be done
-        R3D_CUDA(cudaStreamWaitEvent(st, g_side.ev_v[qb], 0));
+        R3D_CUDA(cudaStreamWaitEvent(st, g_streams.ev_v[chunk][qb], 0));
         v_pending[qb] = false;
       }
       {
@@ -707,10 +719,11 @@ static int jacobi_run(const float* G, int64_t B, int64_t n, void* workspace, flo
       }
       if (tc) {
         if (overlap) {
-          R3D_CUDA(cudaEventRecord(g_side.ev_inner[qb], st));
-          R3D_CUDA(cudaStreamWaitEvent(g_side.st, g_side.ev_inner[qb], 0));
-          if (int e = panel_tc_update_v(&ptc, qb, r, sweep, w.cnt, w.qflag[qb], g_side.st)) return e;
-          R3D_CUDA(cudaEventRecord(g_side.ev_v[qb], g_side.st));
+          cudaStream_t vs = g_streams.vst[chunk];
+          R3D_CUDA(cudaEventRecord(g_streams.ev_inner[chunk][qb], st));
+          R3D_CUDA(cudaStreamWaitEvent(vs, g_streams.ev_inner[chunk][qb], 0));
+          if (int e = panel_tc_update_v(&ptc, qb, r, sweep, w.cnt, w.qflag[qb], vs)) return e;
+          R3D_CUDA(cudaEventRecord(g_streams.ev_v[chunk][qb], vs));
           v_pending[qb] = true;
         } else {
           if (int e = panel_tc_update_v(&ptc, qb, r, sweep, w.cnt, w.qflag[qb], st)) return e;
@@ -725,7 +738,7 @@ static int jacobi_run(const float* G, int64_t B, int64_t n, void* workspace, flo
     }
   }
   for (int i = 0; i < 2; ++i)
-    if (overlap && v_pending[i]) R3D_CUDA(cudaStreamWaitEvent(st, g_side.ev_v[i], 0));
+    if (overlap && v_pending[i]) R3D_CUDA(cudaStreamWaitEvent(st, g_streams.ev_v[chunk][i], 0));
   {
     dim3 grid((unsigned)std::min<int64_t>((n + 7) / 8, 64), (unsigned)B);
     R3D_STAGE(ST_JACOBI_EXTRACT, st);
@@ -736,11 +749,33 @@ static int jacobi_run(const float* G, int64_t B, int64_t n, void* workspace, flo
   return 0;
 }
 
+// Split the batch into two chunks on two streams when it is large enough to fill the GPU twice over.
+static int jacobi_run_chunked(const float* G, int64_t B, int64_t n, void* workspace, float* lambda_out, float* U_out,
+                              int32_t* sweeps_out, int max_sweeps, cudaStream_t st) {
+  const int np = jacobi_np(n);
+  const bool split = options().jacobi_chunks >= 2 && B >= 2 && panel_tc_supported(np) &&
+                     options().jacobi_update_tc != 0 && (B / 2) * (np / JM) >= 2 * kNumSMs;
+  if (!split) return jacobi_run(G, B, n, workspace, lambda_out, U_out, sweeps_out, max_sweeps, st, 0);
+  if (int e = g_streams.ensure()) return e;
+  const int64_t B0 = (B + 1) / 2, B1 = B - B0;
+  char* ws1 = (char*)workspace + ((jacobi_ws_bytes(B0, n) + 255) & ~size_t(255));
+  cudaStream_t s1 = g_streams.chunk[1];
+  R3D_CUDA(cudaEventRecord(g_streams.ev_fork, st));
+  R3D_CUDA(cudaStreamWaitEvent(s1, g_streams.ev_fork, 0));
+  if (int e = jacobi_run(G, B0, n, workspace, lambda_out, U_out, sweeps_out, max_sweeps, st, 0)) return e;
+  if (int e = jacobi_run(G + B0 * n * n, B1, n, ws1, lambda_out ? lambda_out + B0 * n : nullptr,
+                         U_out ? U_out + B0 * n * n : nullptr, sweeps_out ? sweeps_out + B0 : nullptr, max_sweeps,
+                         s1, 1)) return e;
+  R3D_CUDA(cudaEventRecord(g_streams.ev_join[1], s1));
+  R3D_CUDA(cudaStreamWaitEvent(st, g_streams.ev_join[1], 0));
+  return 0;
+}
+
 extern "C" int r3d_jacobi_eigh(const float* G, int64_t B, int64_t n, void* workspace, float* lambda_out, float* U_out,
                                int32_t* sweeps_out, int max_sweeps, void* stream) {
   R3D_CHECK(G && workspace, "null pointer");
   R3D_CHECK(B >= 1 && n >= 1 && n <= 8192, "bad shape B=%lld n=%lld", (long long)B, (long long)n);
-  return jacobi_run(G, B, n, workspace, lambda_out, U_out, sweeps_out, max_sweeps, (cudaStream_t)stream);
+  return jacobi_run_chunked(G, B, n, workspace, lambda_out, U_out, sweeps_out, max_sweeps, (cudaStream_t)stream);
 }
 
 template <typename T>
@@ -771,7 +806,7 @@ extern "C" int r3d_erank_fwd(const void* x, int64_t B, int64_t T, int64_t C, int
   void* jws = p; p += jacobi_ws_bytes(B, n);
   void* gws = p;            // tcgen05 staging
   if (int e = r3d_gram(x, B, T, C, dtype, gram_impl, gws, G, st)) return e;
-  if (int e = jacobi_run(G, B, n, jws, nullptr, U_out, sweeps_out, 0, st)) return e;
+  if (int e = jacobi_run_chunked(G, B, n, jws, nullptr, U_out, sweeps_out, 0, st)) return e;
   if (int e = (dtype == R3D_F32 ? refine_Y<float>(x, U_out, B, T, C, Y_out, st)
                                 : refine_Y<__nv_bfloat16>(x, U_out, B, T, C, Y_out, st))) return e;
   {
