@@ -42,7 +42,8 @@ int64_t r3d_launch_count(int reset);
 /* Thread-local tuning knobs: "jacobi_update_tc" (1 = tcgen05 3xTF32 panel update, default;
  * 0 = SIMT fp32), "jacobi_tol" (relative off-diagonal threshold, default 1e-5),
  * "jacobi_max_sweeps" (default 16, at most 32), "jacobi_overlap_v" (1 = run the eigenvector update on a
- * library-owned side stream overlapped with the next inner solve, default), "jacobi_chunks" (default 1; 2 = split a large
+ * library-owned side stream overlapped with the next inner solve, default), "gemm_tc" (1 = refinement/backward/fp32-Gram GEMMs on tcgen05 through bf16 planes, default; 0 = SIMT),
+ * "jacobi_chunks" (default 1; 2 = split a large
  * batch into two halves on two streams so that one half's inner solve overlaps the other's panel passes). */
 int r3d_set_option(const char* key, double value);
 /* Test hook: one tensor-core panel-update round (G <- Q^T G Q via H, V <- V Q) on caller buffers. */

@@ -16,6 +16,7 @@
 
 #include "common.cuh"
 #include "jacobi_tc.cuh"
+#include "pgemm.cuh"
 
 namespace r3d {
 
@@ -614,6 +615,7 @@ extern "C" int r3d_set_option(const char* key, double value) {
   else if (k == "jacobi_max_sweeps") options().jacobi_max_sweeps = (int)value;
   else if (k == "jacobi_overlap_v") options().jacobi_overlap_v = value != 0.0;
   else if (k == "jacobi_chunks") options().jacobi_chunks = (int)value;
+  else if (k == "gemm_tc") options().gemm_tc = value != 0.0;
   else if (k == "panel_debug") g_panel_debug = (int)value;
   else if (k == "panel_grid_cap") g_panel_grid_cap = (int)value;
   else R3D_CHECK(false, "unknown option '%s'", key);
@@ -622,12 +624,91 @@ extern "C" int r3d_set_option(const char* key, double value) {
 
 extern "C" size_t r3d_jacobi_workspace_bytes(int64_t B, int64_t n) { return jacobi_ws_bytes(B, n); }
 
+// Workspace layout: [G (B,n,n) f32][coef (B,n) f32][Jacobi workspace][bf16 planes: U (3,B,n,n) | Y (3,B,n,m) |
+// X (3,B,T,C), the last only for fp32 inputs]
+struct ErankWs {
+  float* G; float* coef; void* jws; __nv_bfloat16* Upl; __nv_bfloat16* Ypl; __nv_bfloat16* Xpl;
+};
+static size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
+static ErankWs erank_carve(void* workspace, int64_t B, int64_t T, int64_t C, int dtype) {
+  int64_t n, m; bool ts; side(T, C, n, m, ts);
+  ErankWs w;
+  char* p = (char*)((uintptr_t(workspace) + 255) & ~uintptr_t(255));
+  w.G = (float*)p; p += align256(size_t(B) * n * n * 4);
+  w.coef = (float*)p; p += align256(size_t(B) * n * 4);
+  w.jws = p; p += align256(jacobi_ws_bytes(B, n));
+  w.Upl = (__nv_bfloat16*)p; p += align256(size_t(3) * B * n * n * 2);
+  w.Ypl = (__nv_bfloat16*)p; p += align256(size_t(3) * B * n * m * 2);
+  w.Xpl = (dtype == R3D_F32) ? (__nv_bfloat16*)p : nullptr;
+  return w;
+}
+
 extern "C" size_t r3d_erank_workspace_bytes(int64_t B, int64_t T, int64_t C, int dtype) {
   int64_t n, m; bool ts; side(T, C, n, m, ts);
-  // G (B,n,n) + coef (B,n) + Jacobi workspace + tcgen05 Gram staging (hi/lo split of an fp32 input)
-  size_t bytes = size_t(B) * n * n * 4 + size_t(B) * n * 4 + jacobi_ws_bytes(B, n) + 1024;
-  if (dtype == R3D_F32) bytes += size_t(2) * B * T * C * 4;
+  size_t bytes = align256(size_t(B) * n * n * 4) + align256(size_t(B) * n * 4) + align256(jacobi_ws_bytes(B, n)) +
+                 align256(size_t(3) * B * n * n * 2) + align256(size_t(3) * B * n * m * 2) + 1024;
+  if (dtype == R3D_F32) bytes += align256(size_t(3) * B * T * C * 2);
   return bytes;
+}
+
+// ---- tensor-core (bf16-plane) versions of the three GEMMs; return -1 when the shape needs the SIMT fallback ----
+static bool tc_gemm_ok(int64_t T, int64_t C) {
+  return options().gemm_tc != 0 && T % 8 == 0 && C % 8 == 0;
+}
+
+// Y (B,n,m) f32 = Ut * A   (A = the (n, m) short-side-major view of x)
+static int refine_Y_tc(const void* x, int dtype, const float* Ut, const ErankWs& w, int64_t B, int64_t T, int64_t C,
+                       float* Y, cudaStream_t st) {
+  int64_t n, m; bool ts; side(T, C, n, m, ts);
+  R3D_STAGE(ST_REFINE_Y, st);
+  if (int e = split_planes(Ut, R3D_F32, w.Upl, B * n * n, 3, n, nullptr, st)) return e;
+  const void* xb = x;
+  int pb = 1;
+  if (dtype == R3D_F32) {
+    if (int e = split_planes(x, R3D_F32, w.Xpl, B * T * C, 3, C, nullptr, st)) return e;
+    xb = w.Xpl; pb = 3;
+  }
+  PGemm g{};
+  g.A = w.Upl; g.B = xb; g.batch = (int)B; g.pa = 3; g.pb = pb;
+  g.a_kmajor = 1;                   // Ut[j][k]
+  g.b_kmajor = ts ? 0 : 1;          // token side: X[r (K)][c (N)] is MN-major; channel side: X[t (N)][c (K)] is K-major
+  g.M = (int)n; g.N = (int)m; g.K = (int)n;
+  pgemm_products(g, 3, pb, true);
+  g.out_mode = 0; g.C = Y; g.ldc = m; g.strideC = n * m;
+  return pgemm_launch(g, st);
+}
+
+// dX (B,T,C) (+)= U diag(coef) Y
+static int bwd_gemm_tc(const float* Ut, const float* Y, const float* coef, const ErankWs& w, int64_t B, int64_t T,
+                       int64_t C, int dtype, void* dx, int accumulate, cudaStream_t st) {
+  int64_t n, m; bool ts; side(T, C, n, m, ts);
+  R3D_STAGE(ST_BWD_GEMM, st);
+  const int P = dtype == R3D_F32 ? 3 : 2;
+  if (int e = split_planes(Ut, R3D_F32, w.Upl, B * n * n, P, n, nullptr, st)) return e;
+  if (int e = split_planes(Y, R3D_F32, w.Ypl, B * n * m, P, m, coef, st)) return e;     // rows scaled by coef_j
+  PGemm g{};
+  g.batch = (int)B; g.pa = P; g.pb = P; g.a_kmajor = 0; g.b_kmajor = 0;   // both operands are [rows j = K][cols]
+  if (ts) { g.A = w.Upl; g.B = w.Ypl; }      // dX[t][c] = sum_j Ut[j][t] * (coef Y)[j][c]
+  else    { g.A = w.Ypl; g.B = w.Upl; }      // dX[t][c] = sum_j (coef Y)[j][t] * Ut[j][c]
+  g.M = (int)T; g.N = (int)C; g.K = (int)n;
+  pgemm_products(g, P, P, dtype == R3D_F32);
+  g.out_mode = (dtype == R3D_F32 ? 0 : 2) + (accumulate ? 1 : 0);
+  g.C = dx; g.ldc = C; g.strideC = T * C;
+  return pgemm_launch(g, st);
+}
+
+// Gram of an fp32 input on tensor cores: 6 products of the 3 bf16 planes
+static int gram_f32_tc(const void* x, const ErankWs& w, int64_t B, int64_t T, int64_t C, float* G, cudaStream_t st) {
+  int64_t n, m; bool ts; side(T, C, n, m, ts);
+  R3D_STAGE(ST_GRAM, st);
+  if (int e = split_planes(x, R3D_F32, w.Xpl, B * T * C, 3, C, nullptr, st)) return e;
+  PGemm g{};
+  g.A = w.Xpl; g.B = w.Xpl; g.batch = (int)B; g.pa = 3; g.pb = 3;
+  g.a_kmajor = ts ? 1 : 0; g.b_kmajor = ts ? 1 : 0;      // token side: X[t][c = K]; channel side: X[t = K][c]
+  g.M = (int)n; g.N = (int)n; g.K = (int)m;
+  pgemm_products(g, 3, 3, true);
+  g.out_mode = 0; g.C = G; g.ldc = n; g.strideC = n * n;
+  return pgemm_launch(g, st);
 }
 
 template <typename T>
@@ -648,6 +729,11 @@ extern "C" int r3d_gram(const void* x, int64_t B, int64_t T, int64_t C, int dtyp
   cudaStream_t st = (cudaStream_t)stream;
   if (gram_impl == 0 && gram_tcgen05_supported(B, T, C, dtype))
     return gram_tcgen05_launch(x, B, T, C, dtype, workspace, G_out, st);
+  if (gram_impl == 0 && dtype == R3D_F32 && workspace && tc_gemm_ok(T, C) &&
+      (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    const ErankWs w = erank_carve(workspace, B, T, C, dtype);
+    return gram_f32_tc(x, w, B, T, C, G_out, st);
+  }
   return dtype == R3D_F32 ? gram_simt<float>(x, B, T, C, G_out, st) : gram_simt<__nv_bfloat16>(x, B, T, C, G_out, st);
 }
 
@@ -799,16 +885,15 @@ extern "C" int r3d_erank_fwd(const void* x, int64_t B, int64_t T, int64_t C, int
   cudaStream_t st = (cudaStream_t)stream;
   int64_t n, m; bool ts; side(T, C, n, m, ts);
   R3D_CHECK(n <= 8192, "min(T, C) = %lld exceeds 8192", (long long)n);
-  char* p = (char*)workspace;
-  p = (char*)((uintptr_t(p) + 255) & ~uintptr_t(255));
-  float* G = (float*)p; p += size_t(B) * n * n * 4;
-  p += size_t(B) * n * 4;   // coef slot (backward)
-  void* jws = p; p += jacobi_ws_bytes(B, n);
-  void* gws = p;            // tcgen05 staging
-  if (int e = r3d_gram(x, B, T, C, dtype, gram_impl, gws, G, st)) return e;
-  if (int e = jacobi_run_chunked(G, B, n, jws, nullptr, U_out, sweeps_out, 0, st)) return e;
-  if (int e = (dtype == R3D_F32 ? refine_Y<float>(x, U_out, B, T, C, Y_out, st)
-                                : refine_Y<__nv_bfloat16>(x, U_out, B, T, C, Y_out, st))) return e;
+  const ErankWs w = erank_carve(workspace, B, T, C, dtype);
+  if (int e = r3d_gram(x, B, T, C, dtype, gram_impl, workspace, w.G, st)) return e;
+  if (int e = jacobi_run_chunked(w.G, B, n, w.jws, nullptr, U_out, sweeps_out, 0, st)) return e;
+  if (tc_gemm_ok(T, C) && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    if (int e = refine_Y_tc(x, dtype, U_out, w, B, T, C, Y_out, st)) return e;
+  } else {
+    if (int e = (dtype == R3D_F32 ? refine_Y<float>(x, U_out, B, T, C, Y_out, st)
+                                  : refine_Y<__nv_bfloat16>(x, U_out, B, T, C, Y_out, st))) return e;
+  }
   {
     R3D_STAGE(ST_SIGMA, st);
     row_sigma_kernel<<<(unsigned)((B * n + 7) / 8), 256, 0, st>>>(Y_out, U_out, B * n, int(n), int(m), sigma_out);
@@ -843,15 +928,15 @@ extern "C" int r3d_erank_bwd(const float* g, const float* erank, const float* si
   R3D_CHECK(dtype == R3D_F32 || dtype == R3D_BF16, "bad dtype %d", dtype);
   cudaStream_t st = (cudaStream_t)stream;
   int64_t n, m; bool ts; side(T, C, n, m, ts);
-  char* p = (char*)workspace;
-  p = (char*)((uintptr_t(p) + 255) & ~uintptr_t(255));
-  p += size_t(B) * n * n * 4;
-  float* coef = (float*)p;
+  const ErankWs w = erank_carve(workspace, B, T, C, dtype);
+  float* coef = w.coef;
   {
     R3D_STAGE(ST_COEF, st);
     erank_coef_kernel<<<(unsigned)B, 256, 0, st>>>(sigma, g, int(n), rtol, coef);
     R3D_LAUNCH_CHECK();
   }
+  if (tc_gemm_ok(T, C) && (reinterpret_cast<uintptr_t>(dx) & 15) == 0)
+    return bwd_gemm_tc(U, Y, coef, w, B, T, C, dtype, dx, accumulate, st);
   return dtype == R3D_F32 ? bwd_gemm<float>(U, Y, coef, B, T, C, dx, accumulate, st)
                           : bwd_gemm<__nv_bfloat16>(U, Y, coef, B, T, C, dx, accumulate, st);
 }
