@@ -224,23 +224,49 @@ __device__ __forceinline__ int blk_row(int I, int J, int i) { return (i < JB) ? 
 // ------------------------------------------------------------------------------
 // Inner solver: one CTA runs parallel-ordered two-sided Jacobi on the 64x64 sub-block
 // G[IJ, IJ] of one block pair in shared memory and emits the accumulated rotation
-// product Q (64x64).  Per step: one warp derives the 32 disjoint rotations (packed
-// as {c, s, p, q}); then every thread owns 2x2 "pair blocks" {p_a,q_a} x {p_b,q_b} of S
-// and applies the row rotation a AND the column rotation b to them in registers
-// (S <- J^T S J needs no barrier between its two halves), and rotates rows of Q^T
-// with 128-bit accesses.  Two barriers per step.  One inner sweep per visit is
-// enough: the outer sweep count is set by the block round-robin (measured); rounds
-// after the first rotate cross pairs only (see below).
+// product Q^T (64x64).  Per step one warp derives the 32 disjoint rotations; then every
+// thread applies the row rotation a AND the column rotation b to 2x2 "pair blocks"
+// {p_a,q_a} x {p_b,q_b} of S in registers (S <- J^T S J needs no barrier between its two
+// halves) and rotates rows of Q^T.  Two barriers per step.  One inner sweep per visit is
+// enough: the outer sweep count is set by the block round-robin (measured).
+//
+// Round 0 of a sweep visits every pair of the 64 columns (63 steps, circle method), so the
+// pairs inside each block are rotated once per sweep.  Later rounds rotate only the 32x32
+// cross pairs with the XOR schedule (t, 32 + (t ^ s)), s = 0..31: half the steps, and an
+// aligned group of four columns maps to an aligned group of four, so every shared-memory
+// access of the step is a conflict-free 128-bit access.
 // ------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) jacobi_inner_kernel(float* __restrict__ Gp, int np, int nb, int nt, int round,
+constexpr int SP = JM + 4;   // row pitch of S and Qt: 16-byte aligned rows
+
+__device__ __forceinline__ bool jacobi_rotation(float app, float aqq, float apq, float tol, float nu_abs, float& c,
+                                                float& sn, bool& sig) {
+  const bool rt = (apq != 0.f) && (fabsf(apq) > tol * sqrtf(fabsf(app * aqq)));
+  sig = rt && (fabsf(apq) > nu_abs);
+  c = 1.f; sn = 0.f;
+  if (rt) {
+    const float zeta = __fdividef(aqq - app, 2.f * apq);
+    const float tt = __fdividef(zeta >= 0.f ? 1.f : -1.f, fabsf(zeta) + sqrtf(fmaf(zeta, zeta, 1.f)));
+    c = rsqrtf(fmaf(tt, tt, 1.f));
+    sn = tt * c;
+  }
+  return rt;
+}
+
+__device__ __forceinline__ void permute4(float4& v, int sel) {   // v[i] <- v[i ^ sel], sel warp-uniform
+  if (sel & 1) { float t = v.x; v.x = v.y; v.y = t; t = v.z; v.z = v.w; v.w = t; }
+  if (sel & 2) { float t = v.x; v.x = v.z; v.z = t; t = v.y; v.y = v.w; v.w = t; }
+}
+
+__global__ void __launch_bounds__(256, 5) jacobi_inner_kernel(float* __restrict__ Gp, int np, int nb, int nt, int round,
                                                            int sweep, int* __restrict__ cnt,
                                                            int* __restrict__ qflag, float* __restrict__ Qb, float tol,
                                                            const float* __restrict__ nu, int max_inner) {
   const int b = blockIdx.y, t = blockIdx.x;
   if (sweep > 0 && cnt[b * JMAX_SWEEPS + sweep - 1] == 0) return;   // this matrix converged
-  __shared__ float S[JM][JM + 1];
-  __shared__ __align__(16) float Qt[JM][JM + 4];     // Qt[i][k] = Q[k][i]
-  __shared__ float4 rot[JB];                         // {c, s, bits(p), bits(q)}
+  __shared__ __align__(16) float S[JM][SP];
+  __shared__ __align__(16) float Qt[JM][SP];         // Qt[i][k] = Q[k][i]
+  __shared__ __align__(16) float4 rot[JB];           // generic rounds: {c, s, bits(p), bits(q)}
+  __shared__ __align__(16) float rc[JB], rs[JB];     // cross rounds: c and s of pair t
   __shared__ int s_any, s_sig, s_tot;
   const int tid = threadIdx.x;
   int I, J;
@@ -266,64 +292,109 @@ __global__ void __launch_bounds__(256) jacobi_inner_kernel(float* __restrict__ G
 
   int sig_total = 0;
   for (int it = 0; it < max_inner; ++it) {
-    // Round 0 of a sweep visits every pair of the 64 columns (63 steps), so the pairs inside each block are
-    // rotated once per sweep.  Later rounds rotate only the 32 x 32 cross pairs (t, 32 + (t+s) mod 32):
-    // half the steps, and the 32 p's / 32 q's of a step fall in 32 distinct shared-memory banks.
-    const int nsteps = (round == 0) ? JM - 1 : JB;
-    for (int s = 0; s < nsteps; ++s) {
-      if (tid < JB) {
-        int p, q;
-        if (round == 0) rr_pair(JM, s, tid, p, q);
-        else { p = tid; q = JB + ((tid + s) & (JB - 1)); }
-        const float app = S[p][p], aqq = S[q][q], apq = S[p][q];
-        const bool rt = (apq != 0.f) && (fabsf(apq) > tol * sqrtf(fabsf(app * aqq)));
-        const bool sg = rt && (fabsf(apq) > nu_abs);
-        float c = 1.f, sn = 0.f;
-        if (rt) {
-          const float zeta = __fdividef(aqq - app, 2.f * apq);
-          const float tt = __fdividef(zeta >= 0.f ? 1.f : -1.f, fabsf(zeta) + sqrtf(fmaf(zeta, zeta, 1.f)));
-          c = rsqrtf(fmaf(tt, tt, 1.f));
-          sn = tt * c;
+    if (round == 0) {
+      // ---------------- generic schedule: all pairs of the 64 columns ----------------
+      for (int s = 0; s < JM - 1; ++s) {
+        if (tid < JB) {
+          int p, q;
+          rr_pair(JM, s, tid, p, q);
+          float c, sn; bool sg;
+          const bool rt = jacobi_rotation(S[p][p], S[q][q], S[p][q], tol, nu_abs, c, sn, sg);
+          rot[tid] = make_float4(c, sn, __int_as_float(p), __int_as_float(q));
+          const unsigned any = __ballot_sync(0xffffffffu, rt), sgm = __ballot_sync(0xffffffffu, sg);
+          if (tid == 0) { s_any = (any != 0); s_sig += __popc(sgm); s_tot += __popc(any); }
         }
-        rot[tid] = make_float4(c, sn, __int_as_float(p), __int_as_float(q));
-        const unsigned any = __ballot_sync(0xffffffffu, rt), sgm = __ballot_sync(0xffffffffu, sg);
-        if (tid == 0) { s_any = (any != 0); s_sig += __popc(sgm); s_tot += __popc(any); }
-      }
-      __syncthreads();
-      if (s_any) {
-        // S <- J^T S J on 2x2 pair blocks: 32 x 32 blocks, 4 per thread
+        __syncthreads();
+        if (s_any) {
 #pragma unroll
-        for (int u = 0; u < (JB * JB) / 256; ++u) {
-          const int item = tid + u * 256;
-          const float4 ra = rot[item / JB], rb = rot[item % JB];
-          const int pa = __float_as_int(ra.z), qa = __float_as_int(ra.w);
-          const int pb = __float_as_int(rb.z), qb = __float_as_int(rb.w);
-          const float x00 = S[pa][pb], x01 = S[pa][qb], x10 = S[qa][pb], x11 = S[qa][qb];
-          const float y00 = ra.x * x00 - ra.y * x10, y10 = ra.y * x00 + ra.x * x10;
-          const float y01 = ra.x * x01 - ra.y * x11, y11 = ra.y * x01 + ra.x * x11;
-          S[pa][pb] = rb.x * y00 - rb.y * y01;
-          S[pa][qb] = rb.y * y00 + rb.x * y01;
-          S[qa][pb] = rb.x * y10 - rb.y * y11;
-          S[qa][qb] = rb.y * y10 + rb.x * y11;
-        }
-        // Qt <- J^T Qt : rows p, q of Qt, four columns at a time
+          for (int u = 0; u < (JB * JB) / 256; ++u) {
+            const int item = tid + u * 256;
+            const float4 ra = rot[item / JB], rb = rot[item % JB];
+            const int pa = __float_as_int(ra.z), qa = __float_as_int(ra.w);
+            const int pb = __float_as_int(rb.z), qb = __float_as_int(rb.w);
+            const float x00 = S[pa][pb], x01 = S[pa][qb], x10 = S[qa][pb], x11 = S[qa][qb];
+            const float y00 = ra.x * x00 - ra.y * x10, y10 = ra.y * x00 + ra.x * x10;
+            const float y01 = ra.x * x01 - ra.y * x11, y11 = ra.y * x01 + ra.x * x11;
+            S[pa][pb] = rb.x * y00 - rb.y * y01;
+            S[pa][qb] = rb.y * y00 + rb.x * y01;
+            S[qa][pb] = rb.x * y10 - rb.y * y11;
+            S[qa][qb] = rb.y * y10 + rb.x * y11;
+          }
 #pragma unroll
-        for (int u = 0; u < (JB * (JM / 4)) / 256; ++u) {
-          const int item = tid + u * 256;
-          const float4 ra = rot[item / (JM / 4)];
-          const int col = (item % (JM / 4)) * 4;
-          const int pa = __float_as_int(ra.z), qa = __float_as_int(ra.w);
-          const float4 vp = *reinterpret_cast<const float4*>(&Qt[pa][col]);
-          const float4 vq = *reinterpret_cast<const float4*>(&Qt[qa][col]);
-          *reinterpret_cast<float4*>(&Qt[pa][col]) =
-              make_float4(ra.x * vp.x - ra.y * vq.x, ra.x * vp.y - ra.y * vq.y, ra.x * vp.z - ra.y * vq.z,
-                          ra.x * vp.w - ra.y * vq.w);
-          *reinterpret_cast<float4*>(&Qt[qa][col]) =
-              make_float4(ra.y * vp.x + ra.x * vq.x, ra.y * vp.y + ra.x * vq.y, ra.y * vp.z + ra.x * vq.z,
-                          ra.y * vp.w + ra.x * vq.w);
+          for (int u = 0; u < (JB * (JM / 4)) / 256; ++u) {
+            const int item = tid + u * 256;
+            const float4 ra = rot[item / (JM / 4)];
+            const int col = (item % (JM / 4)) * 4;
+            const int pa = __float_as_int(ra.z), qa = __float_as_int(ra.w);
+            const float4 vp = *reinterpret_cast<const float4*>(&Qt[pa][col]);
+            const float4 vq = *reinterpret_cast<const float4*>(&Qt[qa][col]);
+            *reinterpret_cast<float4*>(&Qt[pa][col]) =
+                make_float4(ra.x * vp.x - ra.y * vq.x, ra.x * vp.y - ra.y * vq.y, ra.x * vp.z - ra.y * vq.z,
+                            ra.x * vp.w - ra.y * vq.w);
+            *reinterpret_cast<float4*>(&Qt[qa][col]) =
+                make_float4(ra.y * vp.x + ra.x * vq.x, ra.y * vp.y + ra.x * vq.y, ra.y * vp.z + ra.x * vq.z,
+                            ra.y * vp.w + ra.x * vq.w);
+          }
         }
+        __syncthreads();
       }
-      __syncthreads();
+    } else {
+      // ---------------- cross schedule: pairs (t, 32 + (t ^ s)) ----------------
+      const int a = tid >> 3;            // row pair owned by this thread
+      const int g4 = (tid & 7) * 4;      // four column pairs b = g4 .. g4+3
+      for (int s = 0; s < JB; ++s) {
+        if (tid < JB) {
+          const int p = tid, q = JB + (tid ^ s);
+          float c, sn; bool sg;
+          const bool rt = jacobi_rotation(S[p][p], S[q][q], S[p][q], tol, nu_abs, c, sn, sg);
+          rc[tid] = c; rs[tid] = sn;
+          const unsigned any = __ballot_sync(0xffffffffu, rt), sgm = __ballot_sync(0xffffffffu, sg);
+          if (tid == 0) { s_any = (any != 0); s_sig += __popc(sgm); s_tot += __popc(any); }
+        }
+        __syncthreads();
+        if (s_any) {
+          const int qa = JB + (a ^ s);
+          const int gq = JB + (g4 ^ (s & ~3));      // aligned group holding the partners of columns g4..g4+3
+          const int sel = s & 3;
+          const float ca = rc[a], sa = rs[a];
+          const float4 cb = *reinterpret_cast<const float4*>(&rc[g4]);
+          const float4 sb = *reinterpret_cast<const float4*>(&rs[g4]);
+          float4 x00 = *reinterpret_cast<const float4*>(&S[a][g4]);
+          float4 x10 = *reinterpret_cast<const float4*>(&S[qa][g4]);
+          float4 x01 = *reinterpret_cast<const float4*>(&S[a][gq]);
+          float4 x11 = *reinterpret_cast<const float4*>(&S[qa][gq]);
+          permute4(x01, sel);                       // now component i is the partner column of g4 + i
+          permute4(x11, sel);
+          float4 o00, o01, o10, o11;
+#define R3D_BLOCK(F)                                                                   \
+          {                                                                              \
+            const float y00 = ca * x00.F - sa * x10.F, y10 = sa * x00.F + ca * x10.F;    \
+            const float y01 = ca * x01.F - sa * x11.F, y11 = sa * x01.F + ca * x11.F;    \
+            o00.F = cb.F * y00 - sb.F * y01; o01.F = sb.F * y00 + cb.F * y01;            \
+            o10.F = cb.F * y10 - sb.F * y11; o11.F = sb.F * y10 + cb.F * y11;            \
+          }
+          R3D_BLOCK(x) R3D_BLOCK(y) R3D_BLOCK(z) R3D_BLOCK(w)
+#undef R3D_BLOCK
+          permute4(o01, sel);                       // the permutation is an involution
+          permute4(o11, sel);
+          *reinterpret_cast<float4*>(&S[a][g4]) = o00;
+          *reinterpret_cast<float4*>(&S[qa][g4]) = o10;
+          *reinterpret_cast<float4*>(&S[a][gq]) = o01;
+          *reinterpret_cast<float4*>(&S[qa][gq]) = o11;
+          // Qt <- J^T Qt: rows a and qa; each quarter-warp touches 128 contiguous bytes per access
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int col = g4 + 32 * h;
+            const float4 vp = *reinterpret_cast<const float4*>(&Qt[a][col]);
+            const float4 vq = *reinterpret_cast<const float4*>(&Qt[qa][col]);
+            *reinterpret_cast<float4*>(&Qt[a][col]) =
+                make_float4(ca * vp.x - sa * vq.x, ca * vp.y - sa * vq.y, ca * vp.z - sa * vq.z, ca * vp.w - sa * vq.w);
+            *reinterpret_cast<float4*>(&Qt[qa][col]) =
+                make_float4(sa * vp.x + ca * vq.x, sa * vp.y + ca * vq.y, sa * vp.z + ca * vq.z, sa * vp.w + ca * vq.w);
+          }
+        }
+        __syncthreads();
+      }
     }
     const int sig_now = s_sig;        // stable: the step loop ended on a barrier
     __syncthreads();                  // nobody may start the next sweep before all have read it
