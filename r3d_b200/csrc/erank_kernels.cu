@@ -687,6 +687,7 @@ extern "C" int r3d_set_option(const char* key, double value) {
   else if (k == "jacobi_overlap_v") options().jacobi_overlap_v = value != 0.0;
   else if (k == "jacobi_chunks") options().jacobi_chunks = (int)value;
   else if (k == "gemm_tc") options().gemm_tc = value != 0.0;
+  else if (k == "jacobi_v_after_g") options().jacobi_v_after_g = value != 0.0;
   else if (k == "panel_debug") g_panel_debug = (int)value;
   else if (k == "panel_grid_cap") g_panel_grid_cap = (int)value;
   else R3D_CHECK(false, "unknown option '%s'", key);
@@ -875,17 +876,27 @@ static int jacobi_run(const float* G, int64_t B, int64_t n, void* workspace, flo
         R3D_LAUNCH_CHECK();
       }
       if (tc) {
-        if (overlap) {
+        if (overlap && options().jacobi_v_after_g == 0) {
           cudaStream_t vs = g_streams.vst[chunk];
           R3D_CUDA(cudaEventRecord(g_streams.ev_inner[chunk][qb], st));
           R3D_CUDA(cudaStreamWaitEvent(vs, g_streams.ev_inner[chunk][qb], 0));
           if (int e = panel_tc_update_v(&ptc, qb, r, sweep, w.cnt, w.qflag[qb], vs)) return e;
           R3D_CUDA(cudaEventRecord(g_streams.ev_v[chunk][qb], vs));
           v_pending[qb] = true;
-        } else {
+        } else if (!overlap) {
           if (int e = panel_tc_update_v(&ptc, qb, r, sweep, w.cnt, w.qflag[qb], st)) return e;
         }
         if (int e = panel_tc_update_g(&ptc, qb, r, sweep, w.cnt, w.qflag[qb], st)) return e;
+        if (overlap && options().jacobi_v_after_g != 0) {
+          // start V(r) only when the G passes of round r are done, so that it overlaps inner(r+1) instead of
+          // competing with the G passes for HBM bandwidth
+          cudaStream_t vs = g_streams.vst[chunk];
+          R3D_CUDA(cudaEventRecord(g_streams.ev_inner[chunk][qb], st));
+          R3D_CUDA(cudaStreamWaitEvent(vs, g_streams.ev_inner[chunk][qb], 0));
+          if (int e = panel_tc_update_v(&ptc, qb, r, sweep, w.cnt, w.qflag[qb], vs)) return e;
+          R3D_CUDA(cudaEventRecord(g_streams.ev_v[chunk][qb], vs));
+          v_pending[qb] = true;
+        }
       } else {
         R3D_STAGE(ST_JACOBI_UPDATE, st);
         jacobi_update_kernel<<<dim3(upd_tiles, (unsigned)B), 256, upd_smem, st>>>(w.Gp, w.Vt, w.np, w.nb, w.nt, r,

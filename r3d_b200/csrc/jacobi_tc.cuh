@@ -24,6 +24,7 @@ struct Options {
   int jacobi_max_sweeps = 16;
   int jacobi_chunks = 1;        // 2: run two half-batches on two streams (measured slower at the headline shape: 69.8 vs 65.9 ms)
   int gemm_tc = 1;              // 1: refinement / backward / fp32 Gram GEMMs on tcgen05 via bf16 planes, 0: SIMT
+  int jacobi_v_after_g = 1;     // 1: start V(r) after the G passes of round r, so it overlaps inner(r+1) instead of competing for HBM
   int jacobi_overlap_v = 1;     // run V <- V Q on a side stream, overlapped with the next inner solve
 };
 Options& options();

@@ -400,3 +400,46 @@ def test_gram_tcgen05_vs_oracle(B, T, C, dev):
     err_s = np.abs(Gs - Gr).max() / np.abs(Gr).max()
     print(f"tcgen05 gram rel err {err:.2e} (simt {err_s:.2e}) at T={T}")
     assert err < 1e-5, (err, err_s)      # exact bf16 products; fp32 accumulation over T terms in TMEM
+
+
+@pytest.mark.parametrize("B,T,C", [(2, 256, 512), (2, 512, 256), (1, 200, 264), (2, 264, 200), (1, 512, 512)])
+def test_fp32_gram_on_tensor_cores(B, T, C, dev):
+    """fp32 inputs: Gram through the bf16-plane tcgen05 GEMM (6 plane products) vs float64 and vs SIMT."""
+    from r3d_b200 import ops
+    x = _spectra("relu", B, T, C, 21)
+    xd = torch.from_numpy(x).to(dev)
+    G = ops.gram(xd, ops.GRAM_TCGEN05).cpu().numpy()
+    Gs = ops.gram(xd, ops.GRAM_SIMT).cpu().numpy()
+    xf = x.astype(np.float64)
+    Gr = xf.transpose(0, 2, 1) @ xf if T >= C else xf @ xf.transpose(0, 2, 1)
+    scale = np.abs(Gr).max()
+    # tensor-core fp32 accumulation in TMEM truncates (round-toward-zero) once per MMA: a systematic
+    # -(number of accumulations) * 2^-25 relative offset (~3-5e-6 here), nearly uniform over G and therefore
+    # harmless for sigma / sum(sigma); the SIMT kernel rounds to nearest (1e-7).
+    assert np.abs(G - Gr).max() / scale < 1e-5, np.abs(G - Gr).max() / scale
+    assert np.abs(Gs - Gr).max() / scale < 2e-6
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("B,T,C", [(2, 128, 256), (2, 256, 128), (1, 256, 256)])
+def test_tensor_core_gemms_match_simt(B, T, C, dtype, dev):
+    """A/B: refinement + backward GEMMs on tcgen05 (bf16 planes) vs the SIMT kernels, same inputs."""
+    from r3d_b200 import ops, _lib
+    x = torch.from_numpy(_spectra("relu", B, T, C, 31)).to(dtype).to(dev)
+    outs = {}
+    for tc in (1, 0):
+        _lib.set_option("gemm_tc", tc)
+        try:
+            xt = x.clone().requires_grad_(True)
+            er, sigma, _ = ops.erank(xt, return_aux=True)
+            er.sum().backward()
+            outs[tc] = (er.detach().float().cpu().numpy(), np.sort(sigma.cpu().numpy(), -1), xt.grad.float().cpu().numpy())
+        finally:
+            _lib.set_option("gemm_tc", 1)
+    np.testing.assert_allclose(outs[1][0], outs[0][0], rtol=2e-6)
+    assert np.abs(outs[1][1] - outs[0][1]).max() / outs[0][1].max() < 2e-6
+    gmax = np.abs(outs[0][2]).max()
+    tol = 1e-4 if dtype == torch.float32 else 1.6e-2          # bf16 output rounding dominates
+    if T == C:
+        tol = max(tol, 1e-2)     # square hard-edge spectrum: gradient is ill-conditioned (see test_erank_backward_vs_oracle)
+    assert np.abs(outs[1][2] - outs[0][2]).max() / gmax < tol
