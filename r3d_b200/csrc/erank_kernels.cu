@@ -238,16 +238,24 @@ __device__ __forceinline__ int blk_row(int I, int J, int i) { return (i < JB) ? 
 // ------------------------------------------------------------------------------
 constexpr int SP = JM + 4;   // row pitch of S and Qt: 16-byte aligned rows
 
-__device__ __forceinline__ bool jacobi_rotation(float app, float aqq, float apq, float tol, float nu_abs, float& c,
-                                                float& sn, bool& sig) {
-  const bool rt = (apq != 0.f) && (fabsf(apq) > tol * sqrtf(fabsf(app * aqq)));
-  sig = rt && (fabsf(apq) > nu_abs);
-  c = 1.f; sn = 0.f;
+// Scaled ("fast Givens") rotations.  The kernel stores S~ and Q~^T with S = D S~ D and Q^T = D Q~^T (D = diag(d),
+// d starts at 1).  The Jacobi rotation J = c [[1, t], [-t, 1]] on the true matrices becomes, on the stored ones,
+//     x~_p <- x~_p - tau_pq x~_q ,   x~_q <- x~_q + tau_qp x~_p      (two FFMAs per element pair instead of four ops)
+// with tau_pq = t d_q / d_p, tau_qp = t d_p / d_q, followed by d_p <- c d_p, d_q <- c d_q.  c in [1/sqrt(2), 1], so
+// over one visit d stays above 2^-32 and nothing over- or underflows; D is applied once when Q^T is written out.
+// The relative convergence test |S_pq| > tol sqrt(|S_pp S_qq|) is scale invariant, so it reads S~ directly.
+__device__ __forceinline__ bool jacobi_rotation(float spp, float sqq, float spq, float dp, float dq, float tol,
+                                                float nu_abs, float& tau_pq, float& tau_qp, float& c, bool& sig) {
+  const bool rt = (spq != 0.f) && (fabsf(spq) > tol * sqrtf(fabsf(spp * sqq)));
+  sig = rt && (fabsf(spq) * dp * dq > nu_abs);
+  tau_pq = 0.f; tau_qp = 0.f; c = 1.f;
   if (rt) {
-    const float zeta = __fdividef(aqq - app, 2.f * apq);
+    const float r = __fdividef(dq, dp);                                  // d_q / d_p
+    const float zeta = __fdividef(r * sqq - __fdividef(spp, r), 2.f * spq);   // (S_qq - S_pp) / (2 S_pq) on true values
     const float tt = __fdividef(zeta >= 0.f ? 1.f : -1.f, fabsf(zeta) + sqrtf(fmaf(zeta, zeta, 1.f)));
     c = rsqrtf(fmaf(tt, tt, 1.f));
-    sn = tt * c;
+    tau_pq = tt * r;
+    tau_qp = __fdividef(tt, r);
   }
   return rt;
 }
@@ -258,15 +266,17 @@ __device__ __forceinline__ void permute4(float4& v, int sel) {   // v[i] <- v[i 
 }
 
 __global__ void __launch_bounds__(256, 5) jacobi_inner_kernel(float* __restrict__ Gp, int np, int nb, int nt, int round,
-                                                           int sweep, int* __restrict__ cnt,
-                                                           int* __restrict__ qflag, float* __restrict__ Qb, float tol,
-                                                           const float* __restrict__ nu, int max_inner) {
+                                                              int sweep, int* __restrict__ cnt,
+                                                              int* __restrict__ qflag, float* __restrict__ Qb,
+                                                              float tol, const float* __restrict__ nu,
+                                                              int max_inner) {
   const int b = blockIdx.y, t = blockIdx.x;
   if (sweep > 0 && cnt[b * JMAX_SWEEPS + sweep - 1] == 0) return;   // this matrix converged
-  __shared__ __align__(16) float S[JM][SP];
-  __shared__ __align__(16) float Qt[JM][SP];         // Qt[i][k] = Q[k][i]
-  __shared__ __align__(16) float4 rot[JB];           // generic rounds: {c, s, bits(p), bits(q)}
-  __shared__ __align__(16) float rc[JB], rs[JB];     // cross rounds: c and s of pair t
+  __shared__ __align__(16) float S[JM][SP];          // S~
+  __shared__ __align__(16) float Qt[JM][SP];         // Q~^T: Qt[i][k] = Q[k][i] / d_i
+  __shared__ __align__(16) float4 rot[JB];           // generic rounds: {tau_pq, tau_qp, bits(p), bits(q)}
+  __shared__ __align__(16) float ra_[JB], rb_[JB];   // cross rounds: tau_pq and tau_qp of pair t
+  __shared__ float dsc[JM];                          // d
   __shared__ int s_any, s_sig, s_tot;
   const int tid = threadIdx.x;
   int I, J;
@@ -277,6 +287,7 @@ __global__ void __launch_bounds__(256, 5) jacobi_inner_kernel(float* __restrict_
     S[i][j] = g[boff(np, blk_row(I, J, i), blk_row(I, J, j))];
     Qt[i][j] = (i == j) ? 1.f : 0.f;
   }
+  if (tid < JM) dsc[tid] = 1.f;
   if (tid == 0) { s_tot = 0; s_sig = 0; }
   __syncthreads();
   // symmetrise (the tile updates leave eps-level asymmetry)
@@ -298,9 +309,11 @@ __global__ void __launch_bounds__(256, 5) jacobi_inner_kernel(float* __restrict_
         if (tid < JB) {
           int p, q;
           rr_pair(JM, s, tid, p, q);
-          float c, sn; bool sg;
-          const bool rt = jacobi_rotation(S[p][p], S[q][q], S[p][q], tol, nu_abs, c, sn, sg);
-          rot[tid] = make_float4(c, sn, __int_as_float(p), __int_as_float(q));
+          float tpq, tqp, c; bool sg;
+          const float dp = dsc[p], dq = dsc[q];
+          const bool rt = jacobi_rotation(S[p][p], S[q][q], S[p][q], dp, dq, tol, nu_abs, tpq, tqp, c, sg);
+          rot[tid] = make_float4(tpq, tqp, __int_as_float(p), __int_as_float(q));
+          if (rt) { dsc[p] = dp * c; dsc[q] = dq * c; }
           const unsigned any = __ballot_sync(0xffffffffu, rt), sgm = __ballot_sync(0xffffffffu, sg);
           if (tid == 0) { s_any = (any != 0); s_sig += __popc(sgm); s_tot += __popc(any); }
         }
@@ -313,12 +326,12 @@ __global__ void __launch_bounds__(256, 5) jacobi_inner_kernel(float* __restrict_
             const int pa = __float_as_int(ra.z), qa = __float_as_int(ra.w);
             const int pb = __float_as_int(rb.z), qb = __float_as_int(rb.w);
             const float x00 = S[pa][pb], x01 = S[pa][qb], x10 = S[qa][pb], x11 = S[qa][qb];
-            const float y00 = ra.x * x00 - ra.y * x10, y10 = ra.y * x00 + ra.x * x10;
-            const float y01 = ra.x * x01 - ra.y * x11, y11 = ra.y * x01 + ra.x * x11;
-            S[pa][pb] = rb.x * y00 - rb.y * y01;
-            S[pa][qb] = rb.y * y00 + rb.x * y01;
-            S[qa][pb] = rb.x * y10 - rb.y * y11;
-            S[qa][qb] = rb.y * y10 + rb.x * y11;
+            const float y00 = fmaf(-ra.x, x10, x00), y10 = fmaf(ra.y, x00, x10);
+            const float y01 = fmaf(-ra.x, x11, x01), y11 = fmaf(ra.y, x01, x11);
+            S[pa][pb] = fmaf(-rb.x, y01, y00);
+            S[pa][qb] = fmaf(rb.y, y00, y01);
+            S[qa][pb] = fmaf(-rb.x, y11, y10);
+            S[qa][qb] = fmaf(rb.y, y10, y11);
           }
 #pragma unroll
           for (int u = 0; u < (JB * (JM / 4)) / 256; ++u) {
@@ -329,11 +342,11 @@ __global__ void __launch_bounds__(256, 5) jacobi_inner_kernel(float* __restrict_
             const float4 vp = *reinterpret_cast<const float4*>(&Qt[pa][col]);
             const float4 vq = *reinterpret_cast<const float4*>(&Qt[qa][col]);
             *reinterpret_cast<float4*>(&Qt[pa][col]) =
-                make_float4(ra.x * vp.x - ra.y * vq.x, ra.x * vp.y - ra.y * vq.y, ra.x * vp.z - ra.y * vq.z,
-                            ra.x * vp.w - ra.y * vq.w);
+                make_float4(fmaf(-ra.x, vq.x, vp.x), fmaf(-ra.x, vq.y, vp.y), fmaf(-ra.x, vq.z, vp.z),
+                            fmaf(-ra.x, vq.w, vp.w));
             *reinterpret_cast<float4*>(&Qt[qa][col]) =
-                make_float4(ra.y * vp.x + ra.x * vq.x, ra.y * vp.y + ra.x * vq.y, ra.y * vp.z + ra.x * vq.z,
-                            ra.y * vp.w + ra.x * vq.w);
+                make_float4(fmaf(ra.y, vp.x, vq.x), fmaf(ra.y, vp.y, vq.y), fmaf(ra.y, vp.z, vq.z),
+                            fmaf(ra.y, vp.w, vq.w));
           }
         }
         __syncthreads();
@@ -345,9 +358,11 @@ __global__ void __launch_bounds__(256, 5) jacobi_inner_kernel(float* __restrict_
       for (int s = 0; s < JB; ++s) {
         if (tid < JB) {
           const int p = tid, q = JB + (tid ^ s);
-          float c, sn; bool sg;
-          const bool rt = jacobi_rotation(S[p][p], S[q][q], S[p][q], tol, nu_abs, c, sn, sg);
-          rc[tid] = c; rs[tid] = sn;
+          float tpq, tqp, c; bool sg;
+          const float dp = dsc[p], dq = dsc[q];
+          const bool rt = jacobi_rotation(S[p][p], S[q][q], S[p][q], dp, dq, tol, nu_abs, tpq, tqp, c, sg);
+          ra_[tid] = tpq; rb_[tid] = tqp;
+          if (rt) { dsc[p] = dp * c; dsc[q] = dq * c; }
           const unsigned any = __ballot_sync(0xffffffffu, rt), sgm = __ballot_sync(0xffffffffu, sg);
           if (tid == 0) { s_any = (any != 0); s_sig += __popc(sgm); s_tot += __popc(any); }
         }
@@ -356,9 +371,9 @@ __global__ void __launch_bounds__(256, 5) jacobi_inner_kernel(float* __restrict_
           const int qa = JB + (a ^ s);
           const int gq = JB + (g4 ^ (s & ~3));      // aligned group holding the partners of columns g4..g4+3
           const int sel = s & 3;
-          const float ca = rc[a], sa = rs[a];
-          const float4 cb = *reinterpret_cast<const float4*>(&rc[g4]);
-          const float4 sb = *reinterpret_cast<const float4*>(&rs[g4]);
+          const float ta = ra_[a], ua = rb_[a];     // tau_pq, tau_qp of the row pair
+          const float4 tb = *reinterpret_cast<const float4*>(&ra_[g4]);
+          const float4 ub = *reinterpret_cast<const float4*>(&rb_[g4]);
           float4 x00 = *reinterpret_cast<const float4*>(&S[a][g4]);
           float4 x10 = *reinterpret_cast<const float4*>(&S[qa][g4]);
           float4 x01 = *reinterpret_cast<const float4*>(&S[a][gq]);
@@ -368,10 +383,10 @@ __global__ void __launch_bounds__(256, 5) jacobi_inner_kernel(float* __restrict_
           float4 o00, o01, o10, o11;
 #define R3D_BLOCK(F)                                                                   \
           {                                                                              \
-            const float y00 = ca * x00.F - sa * x10.F, y10 = sa * x00.F + ca * x10.F;    \
-            const float y01 = ca * x01.F - sa * x11.F, y11 = sa * x01.F + ca * x11.F;    \
-            o00.F = cb.F * y00 - sb.F * y01; o01.F = sb.F * y00 + cb.F * y01;            \
-            o10.F = cb.F * y10 - sb.F * y11; o11.F = sb.F * y10 + cb.F * y11;            \
+            const float y00 = fmaf(-ta, x10.F, x00.F), y10 = fmaf(ua, x00.F, x10.F);     \
+            const float y01 = fmaf(-ta, x11.F, x01.F), y11 = fmaf(ua, x01.F, x11.F);     \
+            o00.F = fmaf(-tb.F, y01, y00); o01.F = fmaf(ub.F, y00, y01);                 \
+            o10.F = fmaf(-tb.F, y11, y10); o11.F = fmaf(ub.F, y10, y11);                 \
           }
           R3D_BLOCK(x) R3D_BLOCK(y) R3D_BLOCK(z) R3D_BLOCK(w)
 #undef R3D_BLOCK
@@ -381,16 +396,16 @@ __global__ void __launch_bounds__(256, 5) jacobi_inner_kernel(float* __restrict_
           *reinterpret_cast<float4*>(&S[qa][g4]) = o10;
           *reinterpret_cast<float4*>(&S[a][gq]) = o01;
           *reinterpret_cast<float4*>(&S[qa][gq]) = o11;
-          // Qt <- J^T Qt: rows a and qa; each quarter-warp touches 128 contiguous bytes per access
+          // Q~t <- T^T Q~t: rows a and qa; each quarter-warp touches 128 contiguous bytes per access
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             const int col = g4 + 32 * h;
             const float4 vp = *reinterpret_cast<const float4*>(&Qt[a][col]);
             const float4 vq = *reinterpret_cast<const float4*>(&Qt[qa][col]);
             *reinterpret_cast<float4*>(&Qt[a][col]) =
-                make_float4(ca * vp.x - sa * vq.x, ca * vp.y - sa * vq.y, ca * vp.z - sa * vq.z, ca * vp.w - sa * vq.w);
+                make_float4(fmaf(-ta, vq.x, vp.x), fmaf(-ta, vq.y, vp.y), fmaf(-ta, vq.z, vp.z), fmaf(-ta, vq.w, vp.w));
             *reinterpret_cast<float4*>(&Qt[qa][col]) =
-                make_float4(sa * vp.x + ca * vq.x, sa * vp.y + ca * vq.y, sa * vp.z + ca * vq.z, sa * vp.w + ca * vq.w);
+                make_float4(fmaf(ua, vp.x, vq.x), fmaf(ua, vp.y, vq.y), fmaf(ua, vp.z, vq.z), fmaf(ua, vp.w, vq.w));
           }
         }
         __syncthreads();
@@ -403,7 +418,7 @@ __global__ void __launch_bounds__(256, 5) jacobi_inner_kernel(float* __restrict_
   }
   if (tid == 0 && sig_total > 0) atomicAdd(&cnt[b * JMAX_SWEEPS + sweep], sig_total);
   float* qo = Qb + (int64_t(b) * nt + t) * JM * JM;
-  for (int e = tid; e < JM * JM; e += 256) qo[e] = Qt[e / JM][e % JM];   // qo[i*64+k] = Q[k][i]  (Q^T, row-major)
+  for (int e = tid; e < JM * JM; e += 256) qo[e] = dsc[e / JM] * Qt[e / JM][e % JM];   // Q^T = D Q~^T, row-major
   if (tid == 0) qflag[b * nt + t] = (s_tot > 0);
 }
 
