@@ -39,7 +39,9 @@ constexpr int NSTAGE = 1;             // one stage per CTA, two CTAs per SM (24 
 constexpr int A_RAW = TM * PM * 4;     // 32 KB: panel tile, hi part after the split (in place)
 constexpr int Q_RAW = PM * PM * 4;     // 16 KB
 constexpr int STAGE = 2 * A_RAW + 2 * Q_RAW;        // hi + lo of both operands: 96 KB
-constexpr int SMEM_TOTAL = NSTAGE * STAGE + 1024 + 256;
+constexpr int STG_PITCH = 80;                       // bytes per staged row (16 floats + pad): conflict-free 128-bit access
+constexpr int STG_WARP = 32 * STG_PITCH;            // 2560 B per epilogue warp
+constexpr int SMEM_TOTAL = NSTAGE * STAGE + 4 * STG_WARP + 1024 + 256;
 constexpr int TMEM_COLS_P = 128;       // 2 accumulator stages x 64 fp32 columns
 constexpr int JMAXS = 32;              // must equal JMAX_SWEEPS
 
@@ -163,7 +165,8 @@ __global__ void __launch_bounds__(384, 2) panel_update_tc_kernel(const __grid_co
                                                                  const int* __restrict__ qflag, int debug) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)((uintptr_t(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* raw_full = (uint64_t*)(smem + NSTAGE * STAGE);       // TMA -> splitters
+  uint8_t* stg_base = smem + NSTAGE * STAGE;                       // epilogue staging (normal-store path)
+  uint64_t* raw_full = (uint64_t*)(smem + NSTAGE * STAGE + 4 * STG_WARP);       // TMA -> splitters
   uint64_t* split_done = raw_full + NSTAGE;                      // splitters -> MMA (count 128)
   uint64_t* smem_empty = split_done + NSTAGE;                    // MMA commit -> producer
   uint64_t* tmem_full = smem_empty + NSTAGE;                     // MMA commit -> epilogue
@@ -348,12 +351,27 @@ __global__ void __launch_bounds__(384, 2) panel_update_tc_kernel(const __grid_co
 #pragma unroll
           for (int j = 0; j < 32; ++j) o[j * PB] = __uint_as_float(v[j]);
         } else {
-          // out[row][cblk*32 .. +32): 128 bytes per thread, 4 KB contiguous per warp
-          float4* o = reinterpret_cast<float4*>(out + (int64_t(cblk) * np + row) * PB);
+          // out[row][cblk*32 .. +32) for the warp's 32 rows = one contiguous 4 KB run.  A lane owns a row, so a
+          // direct store would touch 32 different lines per instruction; stage 16 columns at a time through
+          // shared memory and write 64-byte row segments with 4 lanes each (full sectors, 8 rows per instruction).
+          uint8_t* stg = stg_base + q * STG_WARP;
+          float* oblk = out + (int64_t(cblk) * np + (row - lane)) * PB;       // first row of this warp's block
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            o[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
-                               __uint_as_float(v[4 * j + 3]));
+          for (int qt = 0; qt < 2; ++qt) {
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<float4*>(stg + lane * STG_PITCH + j * 16) =
+                  make_float4(__uint_as_float(v[16 * qt + 4 * j]), __uint_as_float(v[16 * qt + 4 * j + 1]),
+                              __uint_as_float(v[16 * qt + 4 * j + 2]), __uint_as_float(v[16 * qt + 4 * j + 3]));
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int id = j * 32 + lane, r = id >> 2, c = id & 3;
+              const float4 val = *reinterpret_cast<const float4*>(stg + r * STG_PITCH + c * 16);
+              *reinterpret_cast<float4*>(oblk + r * PB + qt * 16 + c * 4) = val;
+            }
+          }
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -455,7 +473,8 @@ int panel_tc_update_g(PanelTc* h, int qbuf, int round, int sweep, const int* cnt
   // pass 1: H^T = (G Q)^T (transposed store);  pass 2: G = H^T Q.  Identity tasks cannot be skipped (ping-pong).
   if (int e = panel_launch(h, h->map_g, h->map_q[qbuf], h->H, 1, 0, round, sweep, cnt, qflag, ST_JACOBI_UPDATE, st))
     return e;
-  return panel_launch(h, h->map_h, h->map_q[qbuf], h->G, 0, 0, round, sweep, cnt, qflag, ST_JACOBI_UPDATE, st);
+  // G' is symmetric, so pass 2 may also use the transposed store (one full 128-byte line per store instruction)
+  return panel_launch(h, h->map_h, h->map_q[qbuf], h->G, 1, 0, round, sweep, cnt, qflag, ST_JACOBI_UPDATE, st);
 }
 
 int panel_tc_update_v(PanelTc* h, int qbuf, int round, int sweep, const int* cnt, const int* qflag, cudaStream_t st) {
