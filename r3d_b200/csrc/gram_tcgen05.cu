@@ -20,6 +20,7 @@
 #include <cuda.h>
 
 #include "common.cuh"
+#include "tc_store.cuh"
 
 namespace r3d {
 
@@ -34,7 +35,7 @@ constexpr int SLAB_BYTES = BK * 128;                       // one 64-channel sla
 constexpr int A_BYTES = (TILE_M / BOX_C) * SLAB_BYTES;     // 16 KB
 constexpr int B_BYTES = (TILE_N / BOX_C) * SLAB_BYTES;     // 32 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;             // 48 KB
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 4 * kStgWarpBytes + 1024 /*align*/ + 256 /*barriers*/;
 constexpr int TMEM_COLS = 256;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -113,7 +114,8 @@ __global__ void __launch_bounds__(256, 2) gram_bf16_kernel(const __grid_constant
                                                            float* __restrict__ G, int T, int C) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)((uintptr_t(smem_raw) + 1023) & ~uintptr_t(1023));   // SWIZZLE_128B needs 1024 B
-  uint64_t* full_bar = (uint64_t*)(smem + STAGES * STAGE_BYTES);
+  uint8_t* stg_base = smem + STAGES * STAGE_BYTES;                 // epilogue staging, 2560 B per warp
+  uint64_t* full_bar = (uint64_t*)(smem + STAGES * STAGE_BYTES + 4 * kStgWarpBytes);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
   uint32_t* tmem_slot = (uint32_t*)(tmem_full + 1);
@@ -219,7 +221,11 @@ __global__ void __launch_bounds__(256, 2) gram_bf16_kernel(const __grid_constant
             "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
           : "r"(taddr));
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (row < n) {
+      const int row_w = m0 + q * 32;                                     // first row of this warp's block
+      if (row_w + 32 <= n && n0 + c0 + 32 <= n && (n & 3) == 0) {
+        // whole 32 x 32 block in range: coalesced store through shared memory (warp-uniform branch)
+        staged_store_32x32(stg_base + q * kStgWarpBytes, lane, v, G + (int64_t(b) * n + row_w) * n + n0 + c0, n, 0);
+      } else if (row < n) {
         if (n0 + c0 + 32 <= n && (n & 3) == 0) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4)

@@ -27,6 +27,7 @@
 
 #include "common.cuh"
 #include "jacobi_tc.cuh"
+#include "tc_store.cuh"
 
 namespace r3d {
 
@@ -39,8 +40,7 @@ constexpr int NSTAGE = 1;             // one stage per CTA, two CTAs per SM (24 
 constexpr int A_RAW = TM * PM * 4;     // 32 KB: panel tile, hi part after the split (in place)
 constexpr int Q_RAW = PM * PM * 4;     // 16 KB
 constexpr int STAGE = 2 * A_RAW + 2 * Q_RAW;        // hi + lo of both operands: 96 KB
-constexpr int STG_PITCH = 80;                       // bytes per staged row (16 floats + pad): conflict-free 128-bit access
-constexpr int STG_WARP = 32 * STG_PITCH;            // 2560 B per epilogue warp
+constexpr int STG_WARP = kStgWarpBytes;              // 2560 B of store staging per epilogue warp (tc_store.cuh)
 constexpr int SMEM_TOTAL = NSTAGE * STAGE + 4 * STG_WARP + 1024 + 256;
 constexpr int TMEM_COLS_P = 128;       // 2 accumulator stages x 64 fp32 columns
 constexpr int JMAXS = 32;              // must equal JMAX_SWEEPS
@@ -354,24 +354,7 @@ __global__ void __launch_bounds__(384, 2) panel_update_tc_kernel(const __grid_co
           // out[row][cblk*32 .. +32) for the warp's 32 rows = one contiguous 4 KB run.  A lane owns a row, so a
           // direct store would touch 32 different lines per instruction; stage 16 columns at a time through
           // shared memory and write 64-byte row segments with 4 lanes each (full sectors, 8 rows per instruction).
-          uint8_t* stg = stg_base + q * STG_WARP;
-          float* oblk = out + (int64_t(cblk) * np + (row - lane)) * PB;       // first row of this warp's block
-#pragma unroll
-          for (int qt = 0; qt < 2; ++qt) {
-            __syncwarp();
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              *reinterpret_cast<float4*>(stg + lane * STG_PITCH + j * 16) =
-                  make_float4(__uint_as_float(v[16 * qt + 4 * j]), __uint_as_float(v[16 * qt + 4 * j + 1]),
-                              __uint_as_float(v[16 * qt + 4 * j + 2]), __uint_as_float(v[16 * qt + 4 * j + 3]));
-            __syncwarp();
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int id = j * 32 + lane, r = id >> 2, c = id & 3;
-              const float4 val = *reinterpret_cast<const float4*>(stg + r * STG_PITCH + c * 16);
-              *reinterpret_cast<float4*>(oblk + r * PB + qt * 16 + c * 4) = val;
-            }
-          }
+          staged_store_32x32(stg_base + q * STG_WARP, lane, v, out + (int64_t(cblk) * np + (row - lane)) * PB, PB, 0);
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

@@ -19,6 +19,7 @@
 
 #include "common.cuh"
 #include "pgemm.cuh"
+#include "tc_store.cuh"
 
 namespace r3d {
 
@@ -104,7 +105,8 @@ __global__ void __launch_bounds__(256, 1) pgemm_kernel(const __grid_constant__ C
   const int a_plane_bytes = PG_M * 128;            // 16 KB: 128 (m) x 64 (k) bf16
   const int b_plane_bytes = TN * 128;
   const int stage_bytes = g.pa * a_plane_bytes + g.pb * b_plane_bytes;
-  uint64_t* full_bar = (uint64_t*)(smem + PG_STAGES * stage_bytes);
+  uint8_t* stg_base = smem + PG_STAGES * stage_bytes;              // epilogue staging, 2560 B per warp
+  uint64_t* full_bar = (uint64_t*)(smem + PG_STAGES * stage_bytes + 4 * kStgWarpBytes);
   uint64_t* empty_bar = full_bar + PG_STAGES;
   uint64_t* tmem_full = empty_bar + PG_STAGES;
   uint32_t* tmem_slot = (uint32_t*)(tmem_full + 1);
@@ -214,7 +216,14 @@ __global__ void __launch_bounds__(256, 1) pgemm_kernel(const __grid_constant__ C
             "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
           : "r"(taddr));
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (row < g.M) {
+      const int row_w = m0 + q * 32, col0w = n0 + c0;
+      if (g.out_mode <= 1 && row_w + 32 <= g.M && col0w + 32 <= g.N && (g.ldc & 3) == 0 &&
+          ((reinterpret_cast<uintptr_t>(g.C) + (int64_t(b) * g.strideC) * 4) & 15) == 0) {
+        // whole 32 x 32 fp32 block in range: coalesced store through shared memory (warp-uniform branch)
+        staged_store_32x32(stg_base + q * kStgWarpBytes, lane, v,
+                           (float*)g.C + int64_t(b) * g.strideC + int64_t(row_w) * g.ldc + col0w, g.ldc,
+                           g.out_mode == 1);
+      } else if (row < g.M) {
         const int col0 = n0 + c0;
         if (g.out_mode <= 1) {
           float* crow = (float*)g.C + int64_t(b) * g.strideC + int64_t(row) * g.ldc + col0;
@@ -356,7 +365,7 @@ int pgemm_launch(const PGemm& a, cudaStream_t st) {
                           a.b_kmajor != 0)) return e;
   // N tile: 256 when the staged planes fit two stages in shared memory, else 128
   int TN = 256;
-  auto smem_for = [&](int tn) { return PG_STAGES * (a.pa * PG_M * 128 + a.pb * tn * 128) + 1024 + 256; };
+  auto smem_for = [&](int tn) { return PG_STAGES * (a.pa * PG_M * 128 + a.pb * tn * 128) + 4 * kStgWarpBytes + 1024 + 256; };
   if (smem_for(256) > 220 * 1024 || a.N <= 128) TN = 128;
   R3D_CHECK(smem_for(TN) <= 227 * 1024, "pgemm: too many planes for shared memory");
   PGemmDev g;
