@@ -152,7 +152,15 @@ __device__ __forceinline__ TileInfo decode_tile(int tile, int njobs, int B, int 
   ti.mt = r % mtiles;
   ti.run = true;
   if (sweep > 0 && cnt[ti.b * JMAXS + sweep - 1] == 0) ti.run = false;            // matrix converged
-  else if ((ti.job == 0 ? pj.skip_on_qflag0 : pj.skip_on_qflag1) && qflag[ti.b * nt + ti.c] == 0) ti.run = false;
+  else if ((ti.job == 0 ? pj.skip_on_qflag0 : pj.skip_on_qflag1)) {
+    if (qflag[ti.b * nt + ti.c] == 0) ti.run = false;                               // in-place job: identity task
+  } else {
+    // ping-pong G passes: an identity task still has to be copied through, but if NO task of this matrix rotated
+    // in this round, G is unchanged and both passes can be skipped for the whole matrix
+    int any = 0;
+    for (int c = 0; c < nt; ++c) any |= qflag[ti.b * nt + c];
+    if (!any) ti.run = false;
+  }
   (void)njobs;
   return ti;
 }
