@@ -141,7 +141,7 @@ static int sgemm_launch(bool ta, bool tb, const TA* A, const TB* Bm, TC* Cm, int
 //   nu  (1) absolute significance floor
 // ------------------------------------------------------------------------------
 struct JacobiWs {
-  float* Gp; float* Vt; float* H; float* Qb[2]; int* cnt; int* qflag[2]; float* nu;
+  float* Gp; float* Vt; float* H; float* Qb[2]; int* cnt; int* qflag[2]; float* nu;   // nact = cnt + B*JMAX_SWEEPS
   int np, nb, nt;
 };
 
@@ -157,7 +157,7 @@ __host__ __device__ __forceinline__ int64_t boff(int np, int r, int c) {
 static size_t jacobi_ws_bytes(int64_t B, int64_t n) {   // includes slack so that two half-batch carvings fit
   const size_t np = jacobi_np(n), nt = np / JM;
   size_t f = size_t(B) * (3 * np * np + 2 * nt * JM * JM + 1);
-  size_t i = size_t(B) * (JMAX_SWEEPS + 2 * nt);
+  size_t i = size_t(B) * (JMAX_SWEEPS + 2 * nt) + JMAX_SWEEPS;
   return f * 4 + i * 4 + 2048;
 }
 
@@ -173,7 +173,7 @@ static JacobiWs jacobi_carve(void* ws, int64_t B, int64_t n) {
   w.Qb[0] = (float*)p; p += size_t(B) * w.nt * JM * JM * 4;
   w.Qb[1] = (float*)p; p += size_t(B) * w.nt * JM * JM * 4;
   w.nu = (float*)p; p += size_t(B) * 4;
-  w.cnt = (int*)p; p += size_t(B) * JMAX_SWEEPS * 4;
+  w.cnt = (int*)p; p += (size_t(B) * JMAX_SWEEPS + JMAX_SWEEPS) * 4;   // per-matrix counts, then nact[JMAX_SWEEPS]
   w.qflag[0] = (int*)p; p += size_t(B) * w.nt * 4;
   w.qflag[1] = (int*)p;
   return w;
@@ -208,6 +208,19 @@ __global__ void jacobi_init_kernel(const float* __restrict__ G, int n, int np, f
     if (threadIdx.x == 0) nu[b] = smax[0] * 4.76837158e-7f;   // 4 * 2^-23
     for (int i = threadIdx.x; i < JMAX_SWEEPS; i += blockDim.x) cnt[b * JMAX_SWEEPS + i] = 0;
   }
+}
+
+// nact[sweep] = number of matrices that still rotated something significant in sweep-1.  Every Jacobi kernel
+// returns at once when it is zero, so the launches after global convergence cost launch latency only.
+__global__ void jacobi_active_kernel(int* __restrict__ cnt, int B, int sweep) {
+  __shared__ int total;
+  if (threadIdx.x == 0) total = 0;
+  __syncthreads();
+  int local = 0;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) local += (cnt[b * JMAX_SWEEPS + sweep - 1] != 0);
+  if (local) atomicAdd(&total, local);
+  __syncthreads();
+  if (threadIdx.x == 0) cnt[B * JMAX_SWEEPS + sweep] = total;
 }
 
 // circle-method round robin over m (even) players: pair t of round r
@@ -271,6 +284,7 @@ __global__ void __launch_bounds__(256, 5) jacobi_inner_kernel(float* __restrict_
                                                               float tol, const float* __restrict__ nu,
                                                               int max_inner) {
   const int b = blockIdx.y, t = blockIdx.x;
+  if (sweep > 0 && cnt[gridDim.y * JMAX_SWEEPS + sweep] == 0) return;   // every matrix converged
   if (sweep > 0 && cnt[b * JMAX_SWEEPS + sweep - 1] == 0) return;   // this matrix converged
   __shared__ __align__(16) float S[JM][SP];          // S~
   __shared__ __align__(16) float Qt[JM][SP];         // Q~^T: Qt[i][k] = Q[k][i] / d_i
@@ -433,6 +447,7 @@ __global__ void __launch_bounds__(256) jacobi_update_kernel(float* __restrict__ 
                                                             const int* __restrict__ qflag,
                                                             const float* __restrict__ Qb) {
   const int b = blockIdx.y;
+  if (sweep > 0 && cnt[gridDim.y * JMAX_SWEEPS + sweep] == 0) return;
   if (sweep > 0 && cnt[b * JMAX_SWEEPS + sweep - 1] == 0) return;
   extern __shared__ float sm[];
   float (*Tm)[JM + 4] = reinterpret_cast<float (*)[JM + 4]>(sm);
@@ -702,6 +717,9 @@ extern "C" int r3d_set_option(const char* key, double value) {
   else if (k == "jacobi_overlap_v") options().jacobi_overlap_v = value != 0.0;
   else if (k == "jacobi_chunks") options().jacobi_chunks = (int)value;
   else if (k == "gemm_tc") options().gemm_tc = value != 0.0;
+  else if (k == "erank_passes") options().erank_passes = (int)value;
+  else if (k == "erank_pass2_sweeps") options().erank_pass2_sweeps = (int)value;
+  else if (k == "jacobi_tol_pass1") options().jacobi_tol_pass1 = (float)value;
   else if (k == "jacobi_v_after_g") options().jacobi_v_after_g = value != 0.0;
   else if (k == "panel_debug") g_panel_debug = (int)value;
   else if (k == "panel_grid_cap") g_panel_grid_cap = (int)value;
@@ -715,6 +733,7 @@ extern "C" size_t r3d_jacobi_workspace_bytes(int64_t B, int64_t n) { return jaco
 // X (3,B,T,C), the last only for fp32 inputs]
 struct ErankWs {
   float* G; float* coef; void* jws; __nv_bfloat16* Upl; __nv_bfloat16* Ypl; __nv_bfloat16* Xpl;
+  float* U2; __nv_bfloat16* U2pl;     // second refinement pass only
 };
 static size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
 static ErankWs erank_carve(void* workspace, int64_t B, int64_t T, int64_t C, int dtype) {
@@ -727,6 +746,9 @@ static ErankWs erank_carve(void* workspace, int64_t B, int64_t T, int64_t C, int
   w.Upl = (__nv_bfloat16*)p; p += align256(size_t(3) * B * n * n * 2);
   w.Ypl = (__nv_bfloat16*)p; p += align256(size_t(3) * B * n * m * 2);
   w.Xpl = (dtype == R3D_F32) ? (__nv_bfloat16*)p : nullptr;
+  if (dtype == R3D_F32) p += align256(size_t(3) * B * T * C * 2);
+  w.U2 = (float*)p; p += align256(size_t(B) * n * n * 4);
+  w.U2pl = (__nv_bfloat16*)p;
   return w;
 }
 
@@ -735,6 +757,7 @@ extern "C" size_t r3d_erank_workspace_bytes(int64_t B, int64_t T, int64_t C, int
   size_t bytes = align256(size_t(B) * n * n * 4) + align256(size_t(B) * n * 4) + align256(jacobi_ws_bytes(B, n)) +
                  align256(size_t(3) * B * n * n * 2) + align256(size_t(3) * B * n * m * 2) + 1024;
   if (dtype == R3D_F32) bytes += align256(size_t(3) * B * T * C * 2);
+  bytes += align256(size_t(B) * n * n * 4) + align256(size_t(3) * B * n * n * 2);   // second refinement pass
   return bytes;
 }
 
@@ -782,6 +805,60 @@ static int bwd_gemm_tc(const float* Ut, const float* Y, const float* coef, const
   g.out_mode = (dtype == R3D_F32 ? 0 : 2) + (accumulate ? 1 : 0);
   g.C = dx; g.ldc = C; g.strideC = T * C;
   return pgemm_launch(g, st);
+}
+
+static int jacobi_run_chunked(const float* G, int64_t B, int64_t n, void* workspace, float* lambda_out, float* U_out,
+                              int32_t* sweeps_out, int max_sweeps, cudaStream_t st, float tol_override = 0.f);
+
+// Optional second refinement pass.  After the first pass the rows of Y = U^T A are orthogonal only up to the
+// absolute error of an fp32 Gram (eps * lambda_max), which is large relative to the smallest singular directions.
+// G2 = Y Y^T is nearly diagonal and GRADED (its small entries are represented to fp32 relative accuracy), which
+// two-sided Jacobi resolves to relative accuracy (Demmel-Veselic): G2 = V2^T diag V2, then U <- V2 U, Y <- V2 Y.
+static int second_pass_tc(const ErankWs& w, int64_t B, int64_t n, int64_t m, float* U, float* Y, cudaStream_t st) {
+  if (int e = split_planes(Y, R3D_F32, w.Ypl, B * n * m, 3, m, nullptr, st)) return e;
+  {
+    R3D_STAGE(ST_GRAM, st);
+    PGemm g{};
+    g.A = w.Ypl; g.B = w.Ypl; g.batch = (int)B; g.pa = 3; g.pb = 3; g.a_kmajor = 1; g.b_kmajor = 1;
+    g.M = (int)n; g.N = (int)n; g.K = (int)m;
+    pgemm_products(g, 3, 3, true);
+    g.out_mode = 0; g.C = w.G; g.ldc = n; g.strideC = n * n;
+    if (int e = pgemm_launch(g, st)) return e;
+  }
+  if (int e = jacobi_run_chunked(w.G, B, n, w.jws, nullptr, w.U2, nullptr, options().erank_pass2_sweeps, st)) return e;
+  R3D_STAGE(ST_REFINE_Y, st);
+  if (int e = split_planes(w.U2, R3D_F32, w.U2pl, B * n * n, 3, n, nullptr, st)) return e;
+  if (int e = split_planes(U, R3D_F32, w.Upl, B * n * n, 3, n, nullptr, st)) return e;
+  PGemm g{};
+  g.A = w.U2pl; g.batch = (int)B; g.pa = 3; g.pb = 3; g.a_kmajor = 1; g.b_kmajor = 0;   // B operand: [rows j = K][cols]
+  g.M = (int)n; g.K = (int)n;
+  pgemm_products(g, 3, 3, true);
+  g.out_mode = 0;
+  g.B = w.Upl; g.N = (int)n; g.C = U; g.ldc = n; g.strideC = n * n;          // U <- V2 U
+  if (int e = pgemm_launch(g, st)) return e;
+  g.B = w.Ypl; g.N = (int)m; g.C = Y; g.ldc = m; g.strideC = n * m;          // Y <- V2 Y
+  return pgemm_launch(g, st);
+}
+
+// The same pass with the SIMT GEMMs (shapes the tensor-core path does not take: T or C not a multiple of 8,
+// unaligned x).  The plane buffers are free at this point and serve as the fp32 temporaries.
+static int second_pass_simt(const ErankWs& w, int64_t B, int64_t n, int64_t m, float* U, float* Y, cudaStream_t st) {
+  {
+    R3D_STAGE(ST_GRAM, st);
+    if (int e = sgemm_launch<float, float, float>(false, true, Y, Y, w.G, int(n), int(n), int(m), m, m, n, n * m, n * m,
+                                                  n * n, nullptr, 0, 0, int(B), st)) return e;
+  }
+  if (int e = jacobi_run_chunked(w.G, B, n, w.jws, nullptr, w.U2, nullptr, options().erank_pass2_sweeps, st)) return e;
+  R3D_STAGE(ST_REFINE_Y, st);
+  float* Un = reinterpret_cast<float*>(w.Upl);
+  float* Yn = reinterpret_cast<float*>(w.Ypl);
+  if (int e = sgemm_launch<float, float, float>(false, false, w.U2, U, Un, int(n), int(n), int(n), n, n, n, n * n, n * n,
+                                                n * n, nullptr, 0, 0, int(B), st)) return e;
+  if (int e = sgemm_launch<float, float, float>(false, false, w.U2, Y, Yn, int(n), int(m), int(n), n, m, m, n * n, n * m,
+                                                n * m, nullptr, 0, 0, int(B), st)) return e;
+  R3D_CUDA(cudaMemcpyAsync(U, Un, size_t(B) * n * n * 4, cudaMemcpyDeviceToDevice, st));
+  R3D_CUDA(cudaMemcpyAsync(Y, Yn, size_t(B) * n * m * 4, cudaMemcpyDeviceToDevice, st));
+  return 0;
 }
 
 // Gram of an fp32 input on tensor cores: 6 products of the 3 bf16 planes
@@ -853,11 +930,11 @@ struct StreamSet {
 static thread_local StreamSet g_streams;
 
 static int jacobi_run(const float* G, int64_t B, int64_t n, void* workspace, float* lambda_out, float* U_out,
-                      int32_t* sweeps_out, int max_sweeps, cudaStream_t st, int chunk = 0) {
+                      int32_t* sweeps_out, int max_sweeps, cudaStream_t st, int chunk = 0, float tol_override = 0.f) {
   if (max_sweeps <= 0 || max_sweeps > JMAX_SWEEPS) max_sweeps = options().jacobi_max_sweeps;
   if (max_sweeps <= 0 || max_sweeps > JMAX_SWEEPS) max_sweeps = 16;
   JacobiWs w = jacobi_carve(workspace, B, n);
-  const float tol = options().jacobi_tol;
+  const float tol = tol_override > 0.f ? tol_override : options().jacobi_tol;
   const bool tc = options().jacobi_update_tc != 0 && panel_tc_supported(w.np);
   PanelTc ptc;
   const bool overlap = tc && options().jacobi_overlap_v != 0;
@@ -878,6 +955,10 @@ static int jacobi_run(const float* G, int64_t B, int64_t n, void* workspace, flo
   int iter = 0;
   bool v_pending[2] = {false, false};
   for (int sweep = 0; sweep < max_sweeps; ++sweep) {
+    if (sweep > 0) {
+      jacobi_active_kernel<<<1, 256, 0, st>>>(w.cnt, (int)B, sweep);
+      R3D_LAUNCH_CHECK();
+    }
     for (int r = 0; r < rounds; ++r, ++iter) {
       const int qb = tc ? (iter & 1) : 0;
       if (overlap && v_pending[qb]) {        // the V update that last read this Q buffer must be done
@@ -934,21 +1015,21 @@ static int jacobi_run(const float* G, int64_t B, int64_t n, void* workspace, flo
 
 // Split the batch into two chunks on two streams when it is large enough to fill the GPU twice over.
 static int jacobi_run_chunked(const float* G, int64_t B, int64_t n, void* workspace, float* lambda_out, float* U_out,
-                              int32_t* sweeps_out, int max_sweeps, cudaStream_t st) {
+                              int32_t* sweeps_out, int max_sweeps, cudaStream_t st, float tol_override) {
   const int np = jacobi_np(n);
   const bool split = options().jacobi_chunks >= 2 && B >= 2 && panel_tc_supported(np) &&
                      options().jacobi_update_tc != 0 && (B / 2) * (np / JM) >= 2 * kNumSMs;
-  if (!split) return jacobi_run(G, B, n, workspace, lambda_out, U_out, sweeps_out, max_sweeps, st, 0);
+  if (!split) return jacobi_run(G, B, n, workspace, lambda_out, U_out, sweeps_out, max_sweeps, st, 0, tol_override);
   if (int e = g_streams.ensure()) return e;
   const int64_t B0 = (B + 1) / 2, B1 = B - B0;
   char* ws1 = (char*)workspace + ((jacobi_ws_bytes(B0, n) + 255) & ~size_t(255));
   cudaStream_t s1 = g_streams.chunk[1];
   R3D_CUDA(cudaEventRecord(g_streams.ev_fork, st));
   R3D_CUDA(cudaStreamWaitEvent(s1, g_streams.ev_fork, 0));
-  if (int e = jacobi_run(G, B0, n, workspace, lambda_out, U_out, sweeps_out, max_sweeps, st, 0)) return e;
+  if (int e = jacobi_run(G, B0, n, workspace, lambda_out, U_out, sweeps_out, max_sweeps, st, 0, tol_override)) return e;
   if (int e = jacobi_run(G + B0 * n * n, B1, n, ws1, lambda_out ? lambda_out + B0 * n : nullptr,
                          U_out ? U_out + B0 * n * n : nullptr, sweeps_out ? sweeps_out + B0 : nullptr, max_sweeps,
-                         s1, 1)) return e;
+                         s1, 1, tol_override)) return e;
   R3D_CUDA(cudaEventRecord(g_streams.ev_join[1], s1));
   R3D_CUDA(cudaStreamWaitEvent(st, g_streams.ev_join[1], 0));
   return 0;
@@ -984,12 +1065,20 @@ extern "C" int r3d_erank_fwd(const void* x, int64_t B, int64_t T, int64_t C, int
   R3D_CHECK(n <= 8192, "min(T, C) = %lld exceeds 8192", (long long)n);
   const ErankWs w = erank_carve(workspace, B, T, C, dtype);
   if (int e = r3d_gram(x, B, T, C, dtype, gram_impl, workspace, w.G, st)) return e;
-  if (int e = jacobi_run_chunked(w.G, B, n, w.jws, nullptr, U_out, sweeps_out, 0, st)) return e;
+  const bool two_pass = options().erank_passes >= 2;
+  if (int e = jacobi_run_chunked(w.G, B, n, w.jws, nullptr, U_out, sweeps_out, 0, st,
+                                 two_pass ? options().jacobi_tol_pass1 : 0.f)) return e;
   if (tc_gemm_ok(T, C) && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
     if (int e = refine_Y_tc(x, dtype, U_out, w, B, T, C, Y_out, st)) return e;
+    if (two_pass) {
+      if (int e = second_pass_tc(w, B, n, m, U_out, Y_out, st)) return e;
+    }
   } else {
     if (int e = (dtype == R3D_F32 ? refine_Y<float>(x, U_out, B, T, C, Y_out, st)
                                   : refine_Y<__nv_bfloat16>(x, U_out, B, T, C, Y_out, st))) return e;
+    if (two_pass) {
+      if (int e = second_pass_simt(w, B, n, m, U_out, Y_out, st)) return e;
+    }
   }
   {
     R3D_STAGE(ST_SIGMA, st);

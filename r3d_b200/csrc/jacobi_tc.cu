@@ -181,6 +181,7 @@ __global__ void __launch_bounds__(384, 2) panel_update_tc_kernel(const __grid_co
   uint64_t* tmem_empty = tmem_full + 2;                          // epilogue -> MMA (count 128)
   uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 2);
 
+  if (sweep > 0 && cnt[B * JMAXS + sweep] == 0) return;          // every matrix converged: nothing to do
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int mtiles = np / TM;
   const int total_tiles = njobs * B * nt * mtiles;

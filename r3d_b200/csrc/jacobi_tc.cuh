@@ -23,6 +23,12 @@ struct Options {
   float jacobi_tol = 1e-5f;     // relative off-diagonal threshold
   int jacobi_max_sweeps = 16;
   int jacobi_chunks = 1;        // 2: run two half-batches on two streams (measured slower at the headline shape: 69.8 vs 65.9 ms)
+  float jacobi_tol_pass1 = 1e-5f; // first-pass threshold when a second pass follows (looser values measured slower:
+                                  // 1e-4 -> 70.4 ms, 1e-3 -> 73.7 ms vs 69.2 ms; the second pass then needs more sweeps)
+  int erank_pass2_sweeps = 3;   // sweep cap of the second pass (0 = jacobi_max_sweeps); it converges in 2 (quadratic phase)
+  int erank_passes = 2;         // 2: second refinement pass (G2 = Y Y^T -> Jacobi -> U, Y updated): relative accuracy for the
+                                //    smallest singular directions (gradients <= 1e-4 on square samples), +15 % time;
+                                //    1: single pass (erank itself is already <= 3e-6; gradients 2e-4 .. 1e-2)
   int gemm_tc = 1;              // 1: refinement / backward / fp32 Gram GEMMs on tcgen05 via bf16 planes, 0: SIMT
   int jacobi_v_after_g = 1;     // 1: start V(r) after the G passes of round r, so it overlaps inner(r+1) instead of competing for HBM
   int jacobi_overlap_v = 1;     // run V <- V Q on a side stream, overlapped with the next inner solve

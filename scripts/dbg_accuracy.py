@@ -10,9 +10,10 @@ def spectra(kind, B, T, C, seed):
     if kind == "gauss": return rng.standard_normal((B, T, C)).astype(np.float32)
     if kind == "decay": return (rng.standard_normal((B, T, C)) * np.exp(-np.arange(C) / (C / 8))).astype(np.float32)
 cases = [("gauss", 1, 512, 512), ("relu", 1, 512, 512), ("gauss", 2, 128, 128), ("relu", 2, 128, 128), ("decay", 2, 256, 512), ("relu", 2, 256, 512)]
-for tc in (1,):
+for passes in (1, 2):
     for tol in (1e-5,):
-        _lib.set_option("jacobi_update_tc", tc); _lib.set_option("jacobi_tol", tol); _lib.set_option("jacobi_max_sweeps", 24)
+        tc = 1
+        _lib.set_option("erank_passes", passes); _lib.set_option("jacobi_tol", tol); _lib.set_option("jacobi_max_sweeps", 24)
         out = []
         for kind, B, T, C in cases:
             x = spectra(kind, B, T, C, T * 1000 + C)
@@ -24,4 +25,4 @@ for tc in (1,):
             e1 = np.abs(er.detach().cpu().numpy() - ref).max() / ref.max()
             e2 = np.abs(xt.grad.cpu().numpy() - gref).max() / np.abs(gref).max()
             out.append(f"{kind}{T}x{C}: er {e1:.1e} grad {e2:.1e} sw {int(sw.max())}")
-        print(f"tc={tc} tol={tol:g} | " + " | ".join(out))
+        print(f"passes={passes} tol={tol:g} | " + " | ".join(out))
