@@ -437,6 +437,183 @@ __global__ void __launch_bounds__(256, 5) jacobi_inner_kernel(float* __restrict_
 }
 
 // ------------------------------------------------------------------------------
+// Register-resident inner solver for the cross rounds (round > 0).
+//
+// The shared-memory solver above moves all of S and Q^T through shared memory every step (64 KB per CTA-step),
+// which is what bounds it (7 CTAs per SM x 32 steps x 512 cycles of LDS/STS bandwidth).  Here the whole state
+// lives in registers.  With the pairing (a, 32 + (a ^ sigma)), a "pair block" (a, b) of S is
+//     TL = S[a][b]   TR = S[a][32+(b^sigma)]   BL = S[32+(a^sigma)][b]   BR = S[32+(a^sigma)][32+(b^sigma)]
+// and both the row rotation of pair a and the column rotation of pair b act inside it.  A thread owns the 2x2
+// pair blocks a in {2A, 2A+1}, b in {2B, 2B+1} (A, B: 4 bits each = the thread id) and, of Q~^T, rows a and
+// 32+(a^sigma) over columns 4B..4B+3: 32 state registers.  sigma runs through the 5-bit Gray code, so between
+// steps exactly one bit beta of sigma flips and TR moves to the thread whose b differs in bit beta, BL (and the
+// bottom rows of Q~^T) to the one whose a differs, BR both:
+//     beta = 0 (16 of 31 transitions): inside the thread -- a register renaming;
+//     beta = 1, 2 (12 transitions):    A, B bits held in the lane id -- 20 __shfl_xor per thread;
+//     beta = 3, 4 (3 transitions):     warp-id bits -- the state goes through shared memory once.
+// Per step: the 16 threads with A == B hold the diagonal pair blocks and derive the 32 rotations, one barrier,
+// then 48 FFMAs per thread.  Same rotations, thresholds and outputs (Q^T, qflag, cnt) as the kernel above.
+// ------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 4) jacobi_inner_cross_kernel(float* __restrict__ Gp, int np, int nb, int nt,
+                                                                    int round, int sweep, int* __restrict__ cnt,
+                                                                    int* __restrict__ qflag, float* __restrict__ Qb,
+                                                                    float tol, const float* __restrict__ nu) {
+  const int b = blockIdx.y, t = blockIdx.x;
+  if (sweep > 0 && cnt[gridDim.y * JMAX_SWEEPS + sweep] == 0) return;   // every matrix converged
+  if (sweep > 0 && cnt[b * JMAX_SWEEPS + sweep - 1] == 0) return;       // this matrix converged
+  __shared__ __align__(16) float S[JM][SP];
+  __shared__ __align__(16) float Qt[JM][SP];
+  __shared__ __align__(16) float2 par[2][JB];      // {tau_pq, tau_qp} of pair a, double buffered by step parity
+  __shared__ float dsc[JM];
+  __shared__ int s_sig, s_tot;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int A = (lane & 1) | (((lane >> 2) & 1) << 1) | (((lane >> 4) & 1) << 2) | (((warp >> 1) & 1) << 3);
+  const int Bc = ((lane >> 1) & 1) | (((lane >> 3) & 1) << 1) | ((warp & 1) << 2) | (((warp >> 2) & 1) << 3);
+  int I, J;
+  rr_pair(nb, round, t, I, J);
+  const float* g = Gp + int64_t(b) * np * np;
+  for (int e = tid; e < JM * JM; e += 256) {
+    const int i = e / JM, j = e % JM;
+    S[i][j] = g[boff(np, blk_row(I, J, i), blk_row(I, J, j))];
+  }
+  if (tid < JM) dsc[tid] = 1.f;
+  if (tid == 0) { s_tot = 0; s_sig = 0; }
+  __syncthreads();
+
+  float TL[2][2], TR[2][2], BL[2][2], BR[2][2], QT[2][4], QB[2][4];
+  int sg = 0;                                       // current sigma
+  // initial state: symmetrised S (the tile updates leave eps-level asymmetry), Q~^T = I
+#pragma unroll
+  for (int ra = 0; ra < 2; ++ra) {
+    const int a = 2 * A + ra, u = JB + a;
+#pragma unroll
+    for (int rb = 0; rb < 2; ++rb) {
+      const int c = 2 * Bc + rb, v = JB + c;
+      TL[ra][rb] = 0.5f * (S[a][c] + S[c][a]);
+      TR[ra][rb] = 0.5f * (S[a][v] + S[v][a]);
+      BL[ra][rb] = 0.5f * (S[u][c] + S[c][u]);
+      BR[ra][rb] = 0.5f * (S[u][v] + S[v][u]);
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      QT[ra][c] = (a == 4 * Bc + c) ? 1.f : 0.f;
+      QB[ra][c] = (u == 4 * Bc + c) ? 1.f : 0.f;
+    }
+  }
+  const float nu_abs = nu[b];
+  int n_tot = 0, n_sig = 0;
+
+  for (int s2 = 0; s2 < JB; s2 += 2) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int k = s2 + h;
+      if (A == Bc) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const int p = 2 * A + r, q = JB + (p ^ sg);
+          float tpq, tqp, c; bool sgn;
+          const float dp = dsc[p], dq = dsc[q];
+          const bool rt = jacobi_rotation(TL[r][r], BR[r][r], TR[r][r], dp, dq, tol, nu_abs, tpq, tqp, c, sgn);
+          par[h][p] = make_float2(tpq, tqp);
+          if (rt) { dsc[p] = dp * c; dsc[q] = dq * c; ++n_tot; }
+          if (sgn) ++n_sig;
+        }
+      }
+      __syncthreads();
+      const float4 pa = *reinterpret_cast<const float4*>(&par[h][2 * A]);    // {tau_pq, tau_qp} of a = 2A, 2A+1
+      const float4 pb = *reinterpret_cast<const float4*>(&par[h][2 * Bc]);
+#pragma unroll
+      for (int ra = 0; ra < 2; ++ra) {
+        const float ta = ra ? pa.z : pa.x, ua = ra ? pa.w : pa.y;
+#pragma unroll
+        for (int rb = 0; rb < 2; ++rb) {
+          const float tb = rb ? pb.z : pb.x, ub = rb ? pb.w : pb.y;
+          const float x00 = TL[ra][rb], x01 = TR[ra][rb], x10 = BL[ra][rb], x11 = BR[ra][rb];
+          const float y00 = fmaf(-ta, x10, x00), y10 = fmaf(ua, x00, x10);
+          const float y01 = fmaf(-ta, x11, x01), y11 = fmaf(ua, x01, x11);
+          TL[ra][rb] = fmaf(-tb, y01, y00); TR[ra][rb] = fmaf(ub, y00, y01);
+          BL[ra][rb] = fmaf(-tb, y11, y10); BR[ra][rb] = fmaf(ub, y10, y11);
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float vp = QT[ra][c], vq = QB[ra][c];
+          QT[ra][c] = fmaf(-ta, vq, vp);
+          QB[ra][c] = fmaf(ua, vp, vq);
+        }
+      }
+      // ---- move to the next sigma ----
+      if (h == 0) {                                  // bit 0 flips: renaming inside the thread
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          float x = BL[0][i]; BL[0][i] = BL[1][i]; BL[1][i] = x;
+          x = TR[i][0]; TR[i][0] = TR[i][1]; TR[i][1] = x;
+        }
+        float x = BR[0][0]; BR[0][0] = BR[1][1]; BR[1][1] = x;
+        x = BR[0][1]; BR[0][1] = BR[1][0]; BR[1][0] = x;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { const float y = QB[0][c]; QB[0][c] = QB[1][c]; QB[1][c] = y; }
+        sg ^= 1;
+      } else if (k + 1 < JB) {
+        const int beta = __ffs(k + 1) - 1;           // Gray code: sigma_{k+1} = sigma_k ^ (1 << ctz(k+1)), beta >= 1
+        if (beta <= 2) {
+          const int ma = (beta == 1) ? 1 : 4, mb = 2 * ma;
+#pragma unroll
+          for (int ra = 0; ra < 2; ++ra) {
+#pragma unroll
+            for (int rb = 0; rb < 2; ++rb) {
+              BL[ra][rb] = __shfl_xor_sync(0xffffffffu, BL[ra][rb], ma);
+              TR[ra][rb] = __shfl_xor_sync(0xffffffffu, TR[ra][rb], mb);
+              BR[ra][rb] = __shfl_xor_sync(0xffffffffu, BR[ra][rb], ma | mb);
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) QB[ra][c] = __shfl_xor_sync(0xffffffffu, QB[ra][c], ma);
+          }
+          sg ^= 1 << beta;
+        } else {                                     // warp-id bits: through shared memory
+#pragma unroll
+          for (int ra = 0; ra < 2; ++ra) {
+            const int a = 2 * A + ra, u = JB + (a ^ sg);
+#pragma unroll
+            for (int rb = 0; rb < 2; ++rb) {
+              const int c = 2 * Bc + rb, v = JB + (c ^ sg);
+              S[a][v] = TR[ra][rb]; S[u][c] = BL[ra][rb]; S[u][v] = BR[ra][rb];
+            }
+            *reinterpret_cast<float4*>(&Qt[u][4 * Bc]) = make_float4(QB[ra][0], QB[ra][1], QB[ra][2], QB[ra][3]);
+          }
+          __syncthreads();
+          sg ^= 1 << beta;
+#pragma unroll
+          for (int ra = 0; ra < 2; ++ra) {
+            const int a = 2 * A + ra, u = JB + (a ^ sg);
+#pragma unroll
+            for (int rb = 0; rb < 2; ++rb) {
+              const int c = 2 * Bc + rb, v = JB + (c ^ sg);
+              TR[ra][rb] = S[a][v]; BL[ra][rb] = S[u][c]; BR[ra][rb] = S[u][v];
+            }
+            const float4 q4 = *reinterpret_cast<const float4*>(&Qt[u][4 * Bc]);
+            QB[ra][0] = q4.x; QB[ra][1] = q4.y; QB[ra][2] = q4.z; QB[ra][3] = q4.w;
+          }
+        }
+      }
+    }
+  }
+  if (n_tot) atomicAdd(&s_tot, n_tot);
+  if (n_sig) atomicAdd(&s_sig, n_sig);
+  // Q~^T to shared memory in canonical order, then Q^T = D Q~^T out, row-major and coalesced
+#pragma unroll
+  for (int ra = 0; ra < 2; ++ra) {
+    const int a = 2 * A + ra, u = JB + (a ^ sg);
+    *reinterpret_cast<float4*>(&Qt[a][4 * Bc]) = make_float4(QT[ra][0], QT[ra][1], QT[ra][2], QT[ra][3]);
+    *reinterpret_cast<float4*>(&Qt[u][4 * Bc]) = make_float4(QB[ra][0], QB[ra][1], QB[ra][2], QB[ra][3]);
+  }
+  __syncthreads();
+  if (tid == 0 && s_sig > 0) atomicAdd(&cnt[b * JMAX_SWEEPS + sweep], s_sig);
+  float* qo = Qb + (int64_t(b) * nt + t) * JM * JM;
+  for (int e = tid; e < JM * JM; e += 256) qo[e] = dsc[e / JM] * Qt[e / JM][e % JM];
+  if (tid == 0) qflag[b * nt + t] = (s_tot > 0);
+}
+
+// ------------------------------------------------------------------------------
 // Tile update of one round:  G[IJ_a, IJ_c] <- Q_a^T G[IJ_a, IJ_c] Q_c  (nt*nt tiles)
 // and Vt[IJ_a, slab] <- Q_a^T Vt[IJ_a, slab]  (nt * np/64 tiles).  64x64x64 products
 // from shared memory, 4x4 outputs per thread.
@@ -720,6 +897,7 @@ extern "C" int r3d_set_option(const char* key, double value) {
   else if (k == "erank_passes") options().erank_passes = (int)value;
   else if (k == "erank_pass2_sweeps") options().erank_pass2_sweeps = (int)value;
   else if (k == "jacobi_tol_pass1") options().jacobi_tol_pass1 = (float)value;
+  else if (k == "jacobi_inner_regs") options().jacobi_inner_regs = (int)value;
   else if (k == "jacobi_v_after_g") options().jacobi_v_after_g = value != 0.0;
   else if (k == "panel_debug") g_panel_debug = (int)value;
   else if (k == "panel_grid_cap") g_panel_grid_cap = (int)value;
@@ -967,8 +1145,12 @@ static int jacobi_run(const float* G, int64_t B, int64_t n, void* workspace, flo
       }
       {
         R3D_STAGE(ST_JACOBI_INNER, st);
-        jacobi_inner_kernel<<<dim3(w.nt, (unsigned)B), 256, 0, st>>>(w.Gp, w.np, w.nb, w.nt, r, sweep, w.cnt,
-                                                                    w.qflag[qb], w.Qb[qb], tol, w.nu, 1);
+        if (r > 0 && options().jacobi_inner_regs != 0)
+          jacobi_inner_cross_kernel<<<dim3(w.nt, (unsigned)B), 256, 0, st>>>(w.Gp, w.np, w.nb, w.nt, r, sweep, w.cnt,
+                                                                            w.qflag[qb], w.Qb[qb], tol, w.nu);
+        else
+          jacobi_inner_kernel<<<dim3(w.nt, (unsigned)B), 256, 0, st>>>(w.Gp, w.np, w.nb, w.nt, r, sweep, w.cnt,
+                                                                      w.qflag[qb], w.Qb[qb], tol, w.nu, 1);
         R3D_LAUNCH_CHECK();
       }
       if (tc) {

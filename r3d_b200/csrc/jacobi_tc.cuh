@@ -29,6 +29,7 @@ struct Options {
   int erank_passes = 2;         // 2: second refinement pass (G2 = Y Y^T -> Jacobi -> U, Y updated): relative accuracy for the
                                 //    smallest singular directions (gradients <= 1e-4 on square samples), +15 % time;
                                 //    1: single pass (erank itself is already <= 3e-6; gradients 2e-4 .. 1e-2)
+  int jacobi_inner_regs = 1;    // 1: register-resident inner solver for the cross rounds, 0: shared-memory solver everywhere
   int gemm_tc = 1;              // 1: refinement / backward / fp32 Gram GEMMs on tcgen05 via bf16 planes, 0: SIMT
   int jacobi_v_after_g = 1;     // 1: start V(r) after the G passes of round r, so it overlaps inner(r+1) instead of competing for HBM
   int jacobi_overlap_v = 1;     // run V <- V Q on a side stream, overlapped with the next inner solve
