@@ -142,6 +142,7 @@ static int sgemm_launch(bool ta, bool tb, const TA* A, const TB* Bm, TC* Cm, int
 // ------------------------------------------------------------------------------
 struct JacobiWs {
   float* Gp; float* Vt; float* H; float* Qb[2]; int* cnt; int* qflag[2]; float* nu;   // nact = cnt + B*JMAX_SWEEPS
+  int* psync;   // 2 * kPanelSyncGroups + 1 counters of the merged panel schedule (cleared by the inner solver)
   int np, nb, nt;
 };
 
@@ -157,7 +158,7 @@ __host__ __device__ __forceinline__ int64_t boff(int np, int r, int c) {
 static size_t jacobi_ws_bytes(int64_t B, int64_t n) {   // includes slack so that two half-batch carvings fit
   const size_t np = jacobi_np(n), nt = np / JM;
   size_t f = size_t(B) * (3 * np * np + 2 * nt * JM * JM + 1);
-  size_t i = size_t(B) * (JMAX_SWEEPS + 2 * nt) + JMAX_SWEEPS;
+  size_t i = size_t(B) * (JMAX_SWEEPS + 2 * nt) + JMAX_SWEEPS + 2 * (2 * kPanelSyncGroups + 8);
   return f * 4 + i * 4 + 2048;
 }
 
@@ -175,7 +176,8 @@ static JacobiWs jacobi_carve(void* ws, int64_t B, int64_t n) {
   w.nu = (float*)p; p += size_t(B) * 4;
   w.cnt = (int*)p; p += (size_t(B) * JMAX_SWEEPS + JMAX_SWEEPS) * 4;   // per-matrix counts, then nact[JMAX_SWEEPS]
   w.qflag[0] = (int*)p; p += size_t(B) * w.nt * 4;
-  w.qflag[1] = (int*)p;
+  w.qflag[1] = (int*)p; p += size_t(B) * w.nt * 4;
+  w.psync = (int*)p;
   return w;
 }
 
@@ -282,9 +284,11 @@ __global__ void __launch_bounds__(256, 5) jacobi_inner_kernel(float* __restrict_
                                                               int sweep, int* __restrict__ cnt,
                                                               int* __restrict__ qflag, float* __restrict__ Qb,
                                                               float tol, const float* __restrict__ nu,
-                                                              int max_inner) {
+                                                              int max_inner, int* __restrict__ psync) {
   const int b = blockIdx.y, t = blockIdx.x;
   if (sweep > 0 && cnt[gridDim.y * JMAX_SWEEPS + sweep] == 0) return;   // every matrix converged
+  if (psync != nullptr && b == 0 && t == 0)                             // counters of this round's merged panel launch
+    for (int i = threadIdx.x; i < 2 * kPanelSyncGroups + 1; i += 256) psync[i] = 0;
   if (sweep > 0 && cnt[b * JMAX_SWEEPS + sweep - 1] == 0) return;   // this matrix converged
   __shared__ __align__(16) float S[JM][SP];          // S~
   __shared__ __align__(16) float Qt[JM][SP];         // Q~^T: Qt[i][k] = Q[k][i] / d_i
@@ -439,42 +443,84 @@ __global__ void __launch_bounds__(256, 5) jacobi_inner_kernel(float* __restrict_
 // ------------------------------------------------------------------------------
 // Register-resident inner solver for the cross rounds (round > 0).
 //
-// The shared-memory solver above moves all of S and Q^T through shared memory every step (64 KB per CTA-step),
-// which is what bounds it (7 CTAs per SM x 32 steps x 512 cycles of LDS/STS bandwidth).  Here the whole state
-// lives in registers.  With the pairing (a, 32 + (a ^ sigma)), a "pair block" (a, b) of S is
+// The shared-memory solver above moves all of S and Q^T through shared memory every step (64 KB per CTA-step).
+// Here the whole state lives in registers.  With the pairing (a, 32 + (a ^ sigma)), a "pair block" (a, b) of S is
 //     TL = S[a][b]   TR = S[a][32+(b^sigma)]   BL = S[32+(a^sigma)][b]   BR = S[32+(a^sigma)][32+(b^sigma)]
 // and both the row rotation of pair a and the column rotation of pair b act inside it.  A thread owns the 2x2
-// pair blocks a in {2A, 2A+1}, b in {2B, 2B+1} (A, B: 4 bits each = the thread id) and, of Q~^T, rows a and
-// 32+(a^sigma) over columns 4B..4B+3: 32 state registers.  sigma runs through the 5-bit Gray code, so between
-// steps exactly one bit beta of sigma flips and TR moves to the thread whose b differs in bit beta, BL (and the
-// bottom rows of Q~^T) to the one whose a differs, BR both:
+// pair blocks a in {2A, 2A+1}, b in {2B, 2B+1} (A, B: 4 bits each) and, of Q~^T, rows a and 32+(a^sigma) over
+// columns 4B..4B+3: 32 state registers.  sigma runs through the 5-bit Gray code, so between steps exactly one
+// bit beta of sigma flips and TR moves to the thread whose b differs in bit beta, BL (and the bottom rows of
+// Q~^T) to the one whose a differs, BR both.  Threads are numbered by (A, D = A ^ B):
+//     lane = A0 | A1<<1 | D0<<2 | D1<<3 | A2<<4,   warp = D2 | D3<<1 | A3<<2
+// so that
 //     beta = 0 (16 of 31 transitions): inside the thread -- a register renaming;
-//     beta = 1, 2 (12 transitions):    A, B bits held in the lane id -- 20 __shfl_xor per thread;
-//     beta = 3, 4 (3 transitions):     warp-id bits -- the state goes through shared memory once.
-// Per step: the 16 threads with A == B hold the diagonal pair blocks and derive the 32 rotations, one barrier,
-// then 48 FFMAs per thread.  Same rotations, thresholds and outputs (Q^T, qflag, cnt) as the kernel above.
+//     beta = 1, 2 (12 transitions):    lane bits only -- 20 __shfl_xor per thread;
+//     beta = 3, 4 (3 transitions):     warp bits -- the moving state goes through shared memory once;
+// and the 16 threads holding the diagonal pair blocks (D = 0) sit in two warps (0 and 4), which derive the 32
+// rotations of a step one per lane (the second rotation of a diagonal thread is handed to lane ^ 4).  Per step:
+// rotations in 2 warps, one barrier, 48 FFMAs per thread.  Same thresholds and outputs (Q^T, qflag, cnt) as the
+// kernel above; the rotation uses 5 MUFU ops (no IEEE sqrt/div: c and tau only have to be consistent to ~2 ulp,
+// the final row normalisation of the eigenvectors absorbs the drift, as it does for rsqrtf above).
 // ------------------------------------------------------------------------------
+__device__ __forceinline__ bool jacobi_rotation_fast(float spp, float sqq, float spq, float dp, float dq, float tol2,
+                                                     float nu_abs, float& tau_pq, float& tau_qp, float& c, bool& sig) {
+  const float dpq = dp * dq;
+  const bool rt = spq * spq > tol2 * fabsf(spp * sqq);
+  sig = rt && (fabsf(spq) * dpq > nu_abs);
+  tau_pq = 0.f; tau_qp = 0.f; c = 1.f;
+  if (rt) {
+    const float rp = __frcp_rn(dpq);                 // dp, dq in [2^-32, 1]: dpq >= 2^-64, no overflow
+    const float num = dq * dq * sqq - dp * dp * spp; // (S_qq - S_pp) on true values, times dp dq
+    float zeta = num * rp * __fdividef(0.5f, spq);   // (S_qq - S_pp) / (2 S_pq)
+    const float az = fminf(fabsf(zeta), 1e18f);
+    const float zz = fmaf(az, az, 1.f);
+    const float tt = copysignf(__fdividef(1.f, az + zz * rsqrtf(zz)), zeta);
+    c = rsqrtf(fmaf(tt, tt, 1.f));
+    tau_pq = tt * dq * dq * rp;                      // t d_q / d_p
+    tau_qp = tt * dp * dp * rp;                      // t d_p / d_q
+  }
+  return rt;
+}
+
 __global__ void __launch_bounds__(256, 4) jacobi_inner_cross_kernel(float* __restrict__ Gp, int np, int nb, int nt,
                                                                     int round, int sweep, int* __restrict__ cnt,
                                                                     int* __restrict__ qflag, float* __restrict__ Qb,
-                                                                    float tol, const float* __restrict__ nu) {
+                                                                    float tol, const float* __restrict__ nu,
+                                                                    int* __restrict__ psync) {
   const int b = blockIdx.y, t = blockIdx.x;
   if (sweep > 0 && cnt[gridDim.y * JMAX_SWEEPS + sweep] == 0) return;   // every matrix converged
+  if (psync != nullptr && b == 0 && t == 0)                             // counters of this round's merged panel launch
+    for (int i = threadIdx.x; i < 2 * kPanelSyncGroups + 1; i += 256) psync[i] = 0;
   if (sweep > 0 && cnt[b * JMAX_SWEEPS + sweep - 1] == 0) return;       // this matrix converged
   __shared__ __align__(16) float S[JM][SP];
   __shared__ __align__(16) float Qt[JM][SP];
   __shared__ __align__(16) float2 par[2][JB];      // {tau_pq, tau_qp} of pair a, double buffered by step parity
   __shared__ float dsc[JM];
   __shared__ int s_sig, s_tot;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int A = (lane & 1) | (((lane >> 2) & 1) << 1) | (((lane >> 4) & 1) << 2) | (((warp >> 1) & 1) << 3);
-  const int Bc = ((lane >> 1) & 1) | (((lane >> 3) & 1) << 1) | ((warp & 1) << 2) | (((warp >> 2) & 1) << 3);
+  const int tid = threadIdx.x, lane = tid & 31;
+  // Logical warp id.  The two rotation warps (logical 0 and 4) issue about twice the instructions of the others;
+  // they are placed on physical warps {0,1} or {2,3} (alternating with the CTA's position in the launch order), so
+  // that the four schedulers of an SM, which serve physical warps w % 4 of several resident CTAs, stay balanced.
+  const int pw = (tid >> 5) ^ ((((blockIdx.y * gridDim.x + blockIdx.x) / kNumSMs) & 1) << 1);
+  const int warp = ((pw & 1) << 2) | (pw >> 1);
+  const int A = (lane & 3) | (((lane >> 4) & 1) << 2) | (((warp >> 2) & 1) << 3);
+  const int D = ((lane >> 2) & 3) | ((warp & 3) << 2);
+  const int Bc = A ^ D;
   int I, J;
   rr_pair(nb, round, t, I, J);
   const float* g = Gp + int64_t(b) * np * np;
-  for (int e = tid; e < JM * JM; e += 256) {
-    const int i = e / JM, j = e % JM;
-    S[i][j] = g[boff(np, blk_row(I, J, i), blk_row(I, J, j))];
+  {
+    float v[JM * JM / 256];
+#pragma unroll
+    for (int u = 0; u < JM * JM / 256; ++u) {
+      const int e = tid + u * 256, i = e / JM, j = e % JM;
+      v[u] = g[boff(np, blk_row(I, J, i), blk_row(I, J, j))];
+    }
+#pragma unroll
+    for (int u = 0; u < JM * JM / 256; ++u) {
+      const int e = tid + u * 256;
+      S[e / JM][e % JM] = v[u];
+    }
   }
   if (tid < JM) dsc[tid] = 1.f;
   if (tid == 0) { s_tot = 0; s_sig = 0; }
@@ -500,20 +546,27 @@ __global__ void __launch_bounds__(256, 4) jacobi_inner_cross_kernel(float* __res
       QB[ra][c] = (u == 4 * Bc + c) ? 1.f : 0.f;
     }
   }
-  const float nu_abs = nu[b];
+  const float nu_abs = nu[b], tol2 = tol * tol;
+  const bool rot_warp = (warp & 3) == 0;            // warps 0 and 4 hold the diagonal pair blocks (D == 0) ...
+  const bool rot_lane = rot_warp && (lane & 8) == 0; // ... in lanes with D1 == 0; lane bit 2 (D0) picks the rotation
+  const int rsel = (lane >> 2) & 1;
   int n_tot = 0, n_sig = 0;
 
   for (int s2 = 0; s2 < JB; s2 += 2) {
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int k = s2 + h;
-      if (A == Bc) {
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-          const int p = 2 * A + r, q = JB + (p ^ sg);
+      if (rot_warp) {
+        // the diagonal thread (lane & ~4) holds both rotations of its two pairs; lane | 4 takes the second one
+        const float pp1 = __shfl_sync(0xffffffffu, TL[1][1], lane & ~4);
+        const float qq1 = __shfl_sync(0xffffffffu, BR[1][1], lane & ~4);
+        const float pq1 = __shfl_sync(0xffffffffu, TR[1][1], lane & ~4);
+        if (rot_lane) {
+          const int p = 2 * A + rsel, q = JB + (p ^ sg);
+          const float spp = rsel ? pp1 : TL[0][0], sqq = rsel ? qq1 : BR[0][0], spq = rsel ? pq1 : TR[0][0];
           float tpq, tqp, c; bool sgn;
           const float dp = dsc[p], dq = dsc[q];
-          const bool rt = jacobi_rotation(TL[r][r], BR[r][r], TR[r][r], dp, dq, tol, nu_abs, tpq, tqp, c, sgn);
+          const bool rt = jacobi_rotation_fast(spp, sqq, spq, dp, dq, tol2, nu_abs, tpq, tqp, c, sgn);
           par[h][p] = make_float2(tpq, tqp);
           if (rt) { dsc[p] = dp * c; dsc[q] = dq * c; ++n_tot; }
           if (sgn) ++n_sig;
@@ -556,17 +609,19 @@ __global__ void __launch_bounds__(256, 4) jacobi_inner_cross_kernel(float* __res
       } else if (k + 1 < JB) {
         const int beta = __ffs(k + 1) - 1;           // Gray code: sigma_{k+1} = sigma_k ^ (1 << ctz(k+1)), beta >= 1
         if (beta <= 2) {
-          const int ma = (beta == 1) ? 1 : 4, mb = 2 * ma;
+          // bit beta-1 of A and of B: TR moves along D (lane mask 4 << (beta-1)), BR along A (1 << (beta-1)),
+          // BL and the bottom rows of Q~^T along both
+          const int ma = 1 << (beta - 1), md = 4 << (beta - 1);
 #pragma unroll
           for (int ra = 0; ra < 2; ++ra) {
 #pragma unroll
             for (int rb = 0; rb < 2; ++rb) {
-              BL[ra][rb] = __shfl_xor_sync(0xffffffffu, BL[ra][rb], ma);
-              TR[ra][rb] = __shfl_xor_sync(0xffffffffu, TR[ra][rb], mb);
-              BR[ra][rb] = __shfl_xor_sync(0xffffffffu, BR[ra][rb], ma | mb);
+              BL[ra][rb] = __shfl_xor_sync(0xffffffffu, BL[ra][rb], ma | md);
+              TR[ra][rb] = __shfl_xor_sync(0xffffffffu, TR[ra][rb], md);
+              BR[ra][rb] = __shfl_xor_sync(0xffffffffu, BR[ra][rb], ma);
             }
 #pragma unroll
-            for (int c = 0; c < 4; ++c) QB[ra][c] = __shfl_xor_sync(0xffffffffu, QB[ra][c], ma);
+            for (int c = 0; c < 4; ++c) QB[ra][c] = __shfl_xor_sync(0xffffffffu, QB[ra][c], ma | md);
           }
           sg ^= 1 << beta;
         } else {                                     // warp-id bits: through shared memory
@@ -608,8 +663,14 @@ __global__ void __launch_bounds__(256, 4) jacobi_inner_cross_kernel(float* __res
   }
   __syncthreads();
   if (tid == 0 && s_sig > 0) atomicAdd(&cnt[b * JMAX_SWEEPS + sweep], s_sig);
-  float* qo = Qb + (int64_t(b) * nt + t) * JM * JM;
-  for (int e = tid; e < JM * JM; e += 256) qo[e] = dsc[e / JM] * Qt[e / JM][e % JM];
+  float4* qo = reinterpret_cast<float4*>(Qb + (int64_t(b) * nt + t) * JM * JM);
+#pragma unroll
+  for (int u = 0; u < JM * JM / 4 / 256; ++u) {
+    const int e = tid + u * 256, i = e / (JM / 4), j4 = (e % (JM / 4)) * 4;
+    const float d = dsc[i];
+    const float4 q4 = *reinterpret_cast<const float4*>(&Qt[i][j4]);
+    qo[e] = make_float4(d * q4.x, d * q4.y, d * q4.z, d * q4.w);
+  }
   if (tid == 0) qflag[b * nt + t] = (s_tot > 0);
 }
 
@@ -898,6 +959,9 @@ extern "C" int r3d_set_option(const char* key, double value) {
   else if (k == "erank_pass2_sweeps") options().erank_pass2_sweeps = (int)value;
   else if (k == "jacobi_tol_pass1") options().jacobi_tol_pass1 = (float)value;
   else if (k == "jacobi_inner_regs") options().jacobi_inner_regs = (int)value;
+  else if (k == "panel_merged") options().panel_merged = (int)value;
+  else if (k == "panel_group_mb") options().panel_group_mb = std::max(1, (int)value);
+  else if (k == "panel_ring") options().panel_ring = (int)value;
   else if (k == "jacobi_v_after_g") options().jacobi_v_after_g = value != 0.0;
   else if (k == "panel_debug") g_panel_debug = (int)value;
   else if (k == "panel_grid_cap") g_panel_grid_cap = (int)value;
@@ -1147,10 +1211,10 @@ static int jacobi_run(const float* G, int64_t B, int64_t n, void* workspace, flo
         R3D_STAGE(ST_JACOBI_INNER, st);
         if (r > 0 && options().jacobi_inner_regs != 0)
           jacobi_inner_cross_kernel<<<dim3(w.nt, (unsigned)B), 256, 0, st>>>(w.Gp, w.np, w.nb, w.nt, r, sweep, w.cnt,
-                                                                            w.qflag[qb], w.Qb[qb], tol, w.nu);
+                                                                            w.qflag[qb], w.Qb[qb], tol, w.nu, w.psync);
         else
           jacobi_inner_kernel<<<dim3(w.nt, (unsigned)B), 256, 0, st>>>(w.Gp, w.np, w.nb, w.nt, r, sweep, w.cnt,
-                                                                      w.qflag[qb], w.Qb[qb], tol, w.nu, 1);
+                                                                      w.qflag[qb], w.Qb[qb], tol, w.nu, 1, w.psync);
         R3D_LAUNCH_CHECK();
       }
       if (tc) {
@@ -1164,7 +1228,7 @@ static int jacobi_run(const float* G, int64_t B, int64_t n, void* workspace, flo
         } else if (!overlap) {
           if (int e = panel_tc_update_v(&ptc, qb, r, sweep, w.cnt, w.qflag[qb], st)) return e;
         }
-        if (int e = panel_tc_update_g(&ptc, qb, r, sweep, w.cnt, w.qflag[qb], st)) return e;
+        if (int e = panel_tc_update_g(&ptc, qb, r, sweep, w.cnt, w.qflag[qb], st, w.psync)) return e;
         if (overlap && options().jacobi_v_after_g != 0) {
           // start V(r) only when the G passes of round r are done, so that it overlaps inner(r+1) instead of
           // competing with the G passes for HBM bandwidth

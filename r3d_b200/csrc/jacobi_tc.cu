@@ -130,23 +130,59 @@ __device__ __forceinline__ void rr_pair_tc(int m, int r, int t, int& a, int& b) 
 }
 
 struct PanelJob {
-  // job 0 and job 1 may run in the same launch (e.g. G pass 1 and the V update)
+  // job 0 and job 1 may run in the same launch
   float* out0; float* out1;
   int transposed0, transposed1;
   int skip_on_qflag0, skip_on_qflag1;   // in-place jobs may skip tasks whose Q is the identity
+  // merged mode (both passes of G <- Q^T G Q in ONE launch, see decode_merged): job 0 = pass 1 (G -> H ring),
+  // job 1 = pass 2 (H ring -> G)
+  int merged;
+  int gs, ng, ring, lag;                // matrices per group, groups, ring slots (in groups), pass-2 lag (in groups)
+  int* done1; int* done2; int* err;     // per-group completion counters (4 per tile), error flag
 };
 
 // tile index -> (job, matrix b, task c, row tile mt); returns false when the tile must be skipped
-struct TileInfo { int job, b, c, mt; bool run; };
+struct TileInfo { int job, b, c, mt, hb, group; bool run, valid; };
 
 __device__ __forceinline__ TileInfo decode_tile(int tile, int njobs, int B, int nt, int mtiles, int sweep,
                                                 const int* __restrict__ cnt, const int* __restrict__ qflag,
                                                 const PanelJob& pj) {
   TileInfo ti;
+  ti.valid = true; ti.group = 0;
+  if (pj.merged) {
+    // Merged schedule.  The batch is cut into groups of gs matrices; block s of the tile list interleaves the
+    // pass-1 tiles of group s with the pass-2 tiles of group s - lag.  A pass-2 tile waits (done1) until every
+    // pass-1 tile of its group has stored H; H lives in a ring of `ring` groups that stays in L2, so it never
+    // travels to HBM; a pass-1 tile of group g >= ring waits (done2) for pass 2 of group g - ring before it
+    // overwrites that ring slot.  Every wait targets tiles that precede the waiter in every CTA's list, and all
+    // CTAs of the persistent grid are resident or will become resident, so the schedule cannot deadlock.
+    const int per_mat = nt * mtiles, gsz = pj.gs * per_mat;
+    const int s = tile / (2 * gsz), j = tile % (2 * gsz);
+    ti.job = j & 1;
+    const int idx = j >> 1;
+    ti.group = ti.job == 0 ? s : s - pj.lag;
+    const int bl = idx / per_mat, r = idx % per_mat;
+    ti.b = ti.group * pj.gs + bl;
+    ti.c = r / mtiles;
+    ti.mt = r % mtiles;
+    ti.valid = ti.group >= 0 && ti.group < pj.ng && ti.b < B;
+    ti.hb = (ti.group % pj.ring) * pj.gs + bl;
+    ti.run = ti.valid;
+    if (ti.valid) {
+      if (sweep > 0 && cnt[ti.b * JMAXS + sweep - 1] == 0) ti.run = false;          // matrix converged
+      else {
+        int any = 0;
+        for (int c = 0; c < nt; ++c) any |= qflag[ti.b * nt + c];
+        if (!any) ti.run = false;                                                   // nothing rotated this round
+      }
+    }
+    return ti;
+  }
   const int per_job = B * nt * mtiles;
   ti.job = tile / per_job;
   int r = tile % per_job;
   ti.b = r / (nt * mtiles);
+  ti.hb = ti.b;
   r %= nt * mtiles;
   ti.c = r / mtiles;
   ti.mt = r % mtiles;
@@ -163,6 +199,23 @@ __device__ __forceinline__ TileInfo decode_tile(int tile, int njobs, int B, int 
   }
   (void)njobs;
   return ti;
+}
+
+// tiles of group g (the counters advance by 4 per tile: one per epilogue warp)
+__device__ __forceinline__ int group_target(const PanelJob& pj, int g, int B, int nt, int mtiles) {
+  return 4 * min(pj.gs, B - g * pj.gs) * nt * mtiles;
+}
+// bounded spin (about one second) on a device-scope counter; on timeout the error flag is raised and the caller
+// proceeds, so that a scheduling bug shows up as a wrong result and an error code, never as a hung GPU
+__device__ __forceinline__ void spin_until(const int* p, int target, int* err) {
+  const long long t0 = clock64();
+  for (;;) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    if (v >= target) break;
+    if (clock64() - t0 > (1ll << 31)) { atomicExch(err, 1); break; }
+    __nanosleep(100);
+  }
 }
 
 __global__ void __launch_bounds__(384, 2) panel_update_tc_kernel(const __grid_constant__ CUtensorMap map_in0,
@@ -184,7 +237,7 @@ __global__ void __launch_bounds__(384, 2) panel_update_tc_kernel(const __grid_co
   if (sweep > 0 && cnt[B * JMAXS + sweep] == 0) return;          // every matrix converged: nothing to do
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int mtiles = np / TM;
-  const int total_tiles = njobs * B * nt * mtiles;
+  const int total_tiles = pj.merged ? (pj.ng + pj.lag) * 2 * pj.gs * nt * mtiles : njobs * B * nt * mtiles;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_in0) : "memory");
@@ -218,11 +271,17 @@ __global__ void __launch_bounds__(384, 2) panel_update_tc_kernel(const __grid_co
         uint8_t* st = smem + s * STAGE;
         int I, J;
         rr_pair_tc(nb, round, ti.c, I, J);
+        if (pj.merged && ti.job == 1) {
+          // pass 2 reads what pass 1 of this group stored (generic proxy, other CTAs) through the async proxy
+          spin_until(&pj.done1[ti.group], group_target(pj, ti.group, B, nt, mtiles), pj.err);
+          asm volatile("fence.proxy.async;" ::: "memory");
+        }
         bar_expect_tx(&raw_full[s], A_RAW + Q_RAW);
         const CUtensorMap* mp = ti.job == 0 ? &map_in0 : &map_in1;
+        const int mb = (pj.merged && ti.job == 1) ? ti.hb : ti.b;
         // panel tile: rows [mt*128, +128), column blocks I and J (32 floats = 128 B each)
-        tma_3d(st, mp, &raw_full[s], 0, ti.mt * TM, ti.b * nb + I);      // 16 KB contiguous in HBM
-        tma_3d(st + TM * 128, mp, &raw_full[s], 0, ti.mt * TM, ti.b * nb + J);
+        tma_3d(st, mp, &raw_full[s], 0, ti.mt * TM, mb * nb + I);      // 16 KB contiguous in HBM
+        tma_3d(st + TM * 128, mp, &raw_full[s], 0, ti.mt * TM, mb * nb + J);
         // Q_c^T: 64 rows (j) x two 32-column halves of k
         const int qrow = (ti.b * nt + ti.c) * PM;
         tma_2d(st + 2 * A_RAW, &map_q, &raw_full[s], 0, qrow);
@@ -316,14 +375,24 @@ __global__ void __launch_bounds__(384, 2) panel_update_tc_kernel(const __grid_co
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const TileInfo ti = decode_tile(tile, njobs, B, nt, mtiles, sweep, cnt, qflag, pj);
-      if (!ti.run) continue;
+      if (!ti.run) {
+        // merged mode: a skipped tile still counts as done for the waiters of its group
+        if (pj.merged && ti.valid && lane == 0) atomicAdd(ti.job == 0 ? &pj.done1[ti.group] : &pj.done2[ti.group], 1);
+        continue;
+      }
       const int acc = it & 1;
       const uint32_t aph = (it >> 1) & 1;
       bar_wait(&tmem_full[acc], aph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       int I, J;
       rr_pair_tc(nb, round, ti.c, I, J);
-      float* out = (ti.job == 0 ? pj.out0 : pj.out1) + int64_t(ti.b) * np * np;
+      if (pj.merged && ti.job == 0 && ti.group >= pj.ring) {
+        // the ring slot is reused: pass 2 of group - ring must have read it
+        if (lane == 0) spin_until(&pj.done2[ti.group - pj.ring], group_target(pj, ti.group - pj.ring, B, nt, mtiles), pj.err);
+        __syncwarp();
+      }
+      float* out = (ti.job == 0 ? pj.out0 : pj.out1) +
+                   int64_t((pj.merged && ti.job == 0) ? ti.hb : ti.b) * np * np;
       const bool tr = (ti.job == 0 ? pj.transposed0 : pj.transposed1) != 0;
       const int row = ti.mt * TM + q * 32 + lane;
 #pragma unroll
@@ -368,6 +437,13 @@ __global__ void __launch_bounds__(384, 2) panel_update_tc_kernel(const __grid_co
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       bar_arrive(&tmem_empty[acc]);
+      if (pj.merged) {
+        // publish this warp's stores (pass 1) / its tile's completed reads (pass 2) at device scope
+        asm volatile("fence.proxy.async;" ::: "memory");
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) atomicAdd(ti.job == 0 ? &pj.done1[ti.group] : &pj.done2[ti.group], 1);
+      }
       ++it;
     }
   }
@@ -449,7 +525,7 @@ static int panel_launch(PanelTc* h, const CUtensorMap& in, const CUtensorMap& q,
                         cudaStream_t st) {
   const int mtiles = h->np / TM;
   const int64_t tiles = h->B * h->nt * mtiles;
-  PanelJob pj;
+  PanelJob pj{};
   pj.out0 = out; pj.transposed0 = transposed; pj.skip_on_qflag0 = skip_on_qflag;
   pj.out1 = nullptr; pj.transposed1 = 0; pj.skip_on_qflag1 = 0;
   int grid = (int)std::min<int64_t>(tiles, 2 * kNumSMs);
@@ -461,7 +537,44 @@ static int panel_launch(PanelTc* h, const CUtensorMap& in, const CUtensorMap& q,
   return 0;
 }
 
-int panel_tc_update_g(PanelTc* h, int qbuf, int round, int sweep, const int* cnt, const int* qflag, cudaStream_t st) {
+// Both passes in one launch (merged schedule, H ring resident in L2).  `sync` holds 2 * kPanelSyncGroups counters
+// + 1 error flag, all zero when the launch starts (the inner solver of the round clears them).
+static int panel_launch_merged(PanelTc* h, const CUtensorMap& q, int round, int sweep, const int* cnt,
+                               const int* qflag, int* sync, cudaStream_t st) {
+  const int mtiles = h->np / TM;
+  const int per_mat = h->nt * mtiles;
+  PanelJob pj{};
+  pj.out0 = h->H; pj.transposed0 = 1;
+  pj.out1 = h->G; pj.transposed1 = 1;
+  pj.merged = 1;
+  const int64_t mat_bytes = int64_t(h->np) * h->np * 4;
+  pj.gs = (int)std::max<int64_t>(1, std::min<int64_t>(h->B, (int64_t(options().panel_group_mb) << 20) / mat_bytes));
+  pj.ng = (int)((h->B + pj.gs - 1) / pj.gs);
+  pj.ring = std::min(pj.ng, std::max(3, options().panel_ring));
+  pj.lag = 2;
+  if (pj.ring <= pj.lag) pj.ring = pj.ng;             // tiny batches: no slot reuse at all
+  pj.done1 = sync; pj.done2 = sync + kPanelSyncGroups; pj.err = sync + 2 * kPanelSyncGroups;
+  const int64_t tiles = int64_t(pj.ng + pj.lag) * 2 * pj.gs * per_mat;
+  int grid = (int)std::min<int64_t>(tiles, 2 * kNumSMs);
+  if (g_panel_grid_cap > 0) grid = std::min(grid, g_panel_grid_cap);
+  StageScope scope(ST_JACOBI_UPDATE, st);
+  panel_update_tc_kernel<<<grid, 384, SMEM_TOTAL, st>>>(h->map_g, h->map_h, q, pj, 2, (int)h->B, h->np, h->nb, h->nt,
+                                                        round, sweep, cnt, qflag, g_panel_debug);
+  R3D_LAUNCH_CHECK();
+  return 0;
+}
+
+bool panel_tc_merged_ok(const PanelTc* h) {
+  if (options().panel_merged == 0) return false;
+  const int64_t mat_bytes = int64_t(h->np) * h->np * 4;
+  const int64_t gs = std::max<int64_t>(1, std::min<int64_t>(h->B, (int64_t(options().panel_group_mb) << 20) / mat_bytes));
+  return (h->B + gs - 1) / gs <= kPanelSyncGroups;
+}
+
+int panel_tc_update_g(PanelTc* h, int qbuf, int round, int sweep, const int* cnt, const int* qflag, cudaStream_t st,
+                      int* sync) {
+  if (sync != nullptr && panel_tc_merged_ok(h))
+    return panel_launch_merged(h, h->map_q[qbuf], round, sweep, cnt, qflag, sync, st);
   // pass 1: H^T = (G Q)^T (transposed store);  pass 2: G = H^T Q.  Identity tasks cannot be skipped (ping-pong).
   if (int e = panel_launch(h, h->map_g, h->map_q[qbuf], h->H, 1, 0, round, sweep, cnt, qflag, ST_JACOBI_UPDATE, st))
     return e;

@@ -14,7 +14,10 @@ struct PanelTc {
 bool panel_tc_supported(int np);
 int panel_tc_prepare(PanelTc* h, float* G, float* H, float* V, const float* Qb0, const float* Qb1, int64_t B, int np);
 // G <- Q^T G Q for one round (two launches on `st`): pass 1 writes (G Q)^T into H, pass 2 H Q back into G.
-int panel_tc_update_g(PanelTc* h, int qbuf, int round, int sweep, const int* cnt, const int* qflag, cudaStream_t st);
+// With `sync` (2 * kPanelSyncGroups + 1 zeroed ints) both passes run in ONE launch on a merged schedule that keeps H in L2.
+constexpr int kPanelSyncGroups = 512;
+int panel_tc_update_g(PanelTc* h, int qbuf, int round, int sweep, const int* cnt, const int* qflag, cudaStream_t st,
+                      int* sync = nullptr);
 // V <- V Q for one round (one launch on `st`); independent of the G update and of the next inner solve.
 int panel_tc_update_v(PanelTc* h, int qbuf, int round, int sweep, const int* cnt, const int* qflag, cudaStream_t st);
 
@@ -29,6 +32,11 @@ struct Options {
   int erank_passes = 2;         // 2: second refinement pass (G2 = Y Y^T -> Jacobi -> U, Y updated): relative accuracy for the
                                 //    smallest singular directions (gradients <= 1e-4 on square samples), +15 % time;
                                 //    1: single pass (erank itself is already <= 3e-6; gradients 2e-4 .. 1e-2)
+  int panel_merged = 0;         // 1: both G passes in one launch, H in an L2-resident ring (DRAM traffic 570 -> 402 MB per round,
+                                //    but measured slower, 31.8 vs 29.2 ms/step: the per-CTA tile pipeline, not HBM, bounds that
+                                //    schedule); 0: two launches through HBM (default)
+  int panel_group_mb = 8;       // merged schedule: MB of G per group
+  int panel_ring = 6;           // merged schedule: ring slots (groups) of H
   int jacobi_inner_regs = 1;    // 1: register-resident inner solver for the cross rounds, 0: shared-memory solver everywhere
   int gemm_tc = 1;              // 1: refinement / backward / fp32 Gram GEMMs on tcgen05 via bf16 planes, 0: SIMT
   int jacobi_v_after_g = 1;     // 1: start V(r) after the G passes of round r, so it overlaps inner(r+1) instead of competing for HBM

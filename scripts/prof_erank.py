@@ -1,0 +1,12 @@
+"""One effective-rank forward at the headline shape (for ncu captures of the Jacobi kernels)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from r3d_b200 import ops
+
+B, T, C = (int(v) for v in (sys.argv[1:4] if len(sys.argv) >= 4 else (128, 512, 512)))
+torch.manual_seed(0)
+x = torch.randn(B, T, C, device="cuda").relu_().to(torch.bfloat16)
+er = ops.erank(x)
+torch.cuda.synchronize()
+print("erank mean", er.mean().item())
