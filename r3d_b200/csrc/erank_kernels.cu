@@ -21,6 +21,7 @@
 namespace r3d {
 
 extern int g_panel_debug;
+extern int g_row_chunk_mult;
 extern int g_panel_grid_cap;
 static thread_local Options g_opts;
 Options& options() { return g_opts; }
@@ -492,8 +493,9 @@ __global__ void __launch_bounds__(256, 4) jacobi_inner_cross_kernel(float* __res
   if (psync != nullptr && b == 0 && t == 0)                             // counters of this round's merged panel launch
     for (int i = threadIdx.x; i < 2 * kPanelSyncGroups + 1; i += 256) psync[i] = 0;
   if (sweep > 0 && cnt[b * JMAX_SWEEPS + sweep - 1] == 0) return;       // this matrix converged
+  // ONE 17 KB staging buffer (initial tile, the three cross-warp transitions, final Q^T): small enough that a CTA
+  // of this kernel fits next to two resident CTAs of the panel update (V on the side stream)
   __shared__ __align__(16) float S[JM][SP];
-  __shared__ __align__(16) float Qt[JM][SP];
   __shared__ __align__(16) float2 par[2][JB];      // {tau_pq, tau_qp} of pair a, double buffered by step parity
   __shared__ float dsc[JM];
   __shared__ int s_sig, s_tot;
@@ -624,7 +626,7 @@ __global__ void __launch_bounds__(256, 4) jacobi_inner_cross_kernel(float* __res
             for (int c = 0; c < 4; ++c) QB[ra][c] = __shfl_xor_sync(0xffffffffu, QB[ra][c], ma | md);
           }
           sg ^= 1 << beta;
-        } else {                                     // warp-id bits: through shared memory
+        } else {                                     // warp-id bits: through shared memory, S part then Q part
 #pragma unroll
           for (int ra = 0; ra < 2; ++ra) {
             const int a = 2 * A + ra, u = JB + (a ^ sg);
@@ -633,21 +635,32 @@ __global__ void __launch_bounds__(256, 4) jacobi_inner_cross_kernel(float* __res
               const int c = 2 * Bc + rb, v = JB + (c ^ sg);
               S[a][v] = TR[ra][rb]; S[u][c] = BL[ra][rb]; S[u][v] = BR[ra][rb];
             }
-            *reinterpret_cast<float4*>(&Qt[u][4 * Bc]) = make_float4(QB[ra][0], QB[ra][1], QB[ra][2], QB[ra][3]);
           }
           __syncthreads();
-          sg ^= 1 << beta;
+          const int sg2 = sg ^ (1 << beta);
 #pragma unroll
           for (int ra = 0; ra < 2; ++ra) {
-            const int a = 2 * A + ra, u = JB + (a ^ sg);
+            const int a = 2 * A + ra, u = JB + (a ^ sg2);
 #pragma unroll
             for (int rb = 0; rb < 2; ++rb) {
-              const int c = 2 * Bc + rb, v = JB + (c ^ sg);
+              const int c = 2 * Bc + rb, v = JB + (c ^ sg2);
               TR[ra][rb] = S[a][v]; BL[ra][rb] = S[u][c]; BR[ra][rb] = S[u][v];
             }
-            const float4 q4 = *reinterpret_cast<const float4*>(&Qt[u][4 * Bc]);
+          }
+          __syncthreads();
+#pragma unroll
+          for (int ra = 0; ra < 2; ++ra) {
+            const int u = (2 * A + ra) ^ sg;         // bottom row of Q~^T, stored at row u of the buffer
+            *reinterpret_cast<float4*>(&S[u][4 * Bc]) = make_float4(QB[ra][0], QB[ra][1], QB[ra][2], QB[ra][3]);
+          }
+          __syncthreads();
+#pragma unroll
+          for (int ra = 0; ra < 2; ++ra) {
+            const int u = (2 * A + ra) ^ sg2;
+            const float4 q4 = *reinterpret_cast<const float4*>(&S[u][4 * Bc]);
             QB[ra][0] = q4.x; QB[ra][1] = q4.y; QB[ra][2] = q4.z; QB[ra][3] = q4.w;
           }
+          sg = sg2;
         }
       }
     }
@@ -658,8 +671,8 @@ __global__ void __launch_bounds__(256, 4) jacobi_inner_cross_kernel(float* __res
 #pragma unroll
   for (int ra = 0; ra < 2; ++ra) {
     const int a = 2 * A + ra, u = JB + (a ^ sg);
-    *reinterpret_cast<float4*>(&Qt[a][4 * Bc]) = make_float4(QT[ra][0], QT[ra][1], QT[ra][2], QT[ra][3]);
-    *reinterpret_cast<float4*>(&Qt[u][4 * Bc]) = make_float4(QB[ra][0], QB[ra][1], QB[ra][2], QB[ra][3]);
+    *reinterpret_cast<float4*>(&S[a][4 * Bc]) = make_float4(QT[ra][0], QT[ra][1], QT[ra][2], QT[ra][3]);
+    *reinterpret_cast<float4*>(&S[u][4 * Bc]) = make_float4(QB[ra][0], QB[ra][1], QB[ra][2], QB[ra][3]);
   }
   __syncthreads();
   if (tid == 0 && s_sig > 0) atomicAdd(&cnt[b * JMAX_SWEEPS + sweep], s_sig);
@@ -668,7 +681,7 @@ __global__ void __launch_bounds__(256, 4) jacobi_inner_cross_kernel(float* __res
   for (int u = 0; u < JM * JM / 4 / 256; ++u) {
     const int e = tid + u * 256, i = e / (JM / 4), j4 = (e % (JM / 4)) * 4;
     const float d = dsc[i];
-    const float4 q4 = *reinterpret_cast<const float4*>(&Qt[i][j4]);
+    const float4 q4 = *reinterpret_cast<const float4*>(&S[i][j4]);
     qo[e] = make_float4(d * q4.x, d * q4.y, d * q4.z, d * q4.w);
   }
   if (tid == 0) qflag[b * nt + t] = (s_tot > 0);
@@ -960,6 +973,7 @@ extern "C" int r3d_set_option(const char* key, double value) {
   else if (k == "jacobi_tol_pass1") options().jacobi_tol_pass1 = (float)value;
   else if (k == "jacobi_inner_regs") options().jacobi_inner_regs = (int)value;
   else if (k == "panel_merged") options().panel_merged = (int)value;
+  else if (k == "row_chunk_mult") g_row_chunk_mult = std::max(1, std::min(16, (int)value));
   else if (k == "panel_group_mb") options().panel_group_mb = std::max(1, (int)value);
   else if (k == "panel_ring") options().panel_ring = (int)value;
   else if (k == "jacobi_v_after_g") options().jacobi_v_after_g = value != 0.0;

@@ -90,10 +90,11 @@ __device__ __forceinline__ void store_vec<__nv_bfloat16, 4>(__nv_bfloat16* __res
 
 // Row chunking is a function of `rows` alone so that the finalize kernels can
 // recompute it without knowing dtype or vector width.
+int g_row_chunk_mult = 4;   // row chunks are capped at this many per SM (tuning knob "row_chunk_mult")
 static inline int fixed_row_chunks(int64_t rows) {
   int64_t rc = rows / 16;
   if (rc < 1) rc = 1;
-  if (rc > kNumSMs * 4) rc = kNumSMs * 4;
+  if (rc > kNumSMs * g_row_chunk_mult) rc = kNumSMs * g_row_chunk_mult;
   return int(rc);
 }
 
@@ -134,30 +135,21 @@ __global__ void __launch_bounds__(256) score_partial_kernel(const T* __restrict_
   for (int i = 0; i < V; ++i) acc[i] = 0.f;
   if (active) {
     const T* p = x + cv * V;
-    int64_t r = r0 + ty;
-    for (; r + 7 * TY < r1; r += 8 * TY) {   // 8 independent 128-bit loads in flight per thread (~10 MB chip-wide)
+    // batches of 8 independent 128-bit loads per thread; rows past the end contribute +0 (fixed summation order)
+    for (int64_t r = r0 + ty; r < r1; r += 8 * TY) {
       float a[8][V];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) load_vec<T, V>(p + (r + u * TY) * C, a[u]);
+      for (int u = 0; u < 8; ++u) {
+        if (r + u * TY < r1) load_vec<T, V>(p + (r + u * TY) * C, a[u]);
+        else {
+#pragma unroll
+          for (int i = 0; i < V; ++i) a[u][i] = 0.f;
+        }
+      }
 #pragma unroll
       for (int i = 0; i < V; ++i)
         acc[i] += ((fabsf(a[0][i]) + fabsf(a[1][i])) + (fabsf(a[2][i]) + fabsf(a[3][i]))) +
                   ((fabsf(a[4][i]) + fabsf(a[5][i])) + (fabsf(a[6][i]) + fabsf(a[7][i])));
-    }
-    for (; r + 3 * TY < r1; r += 4 * TY) {
-      float a[V], b[V], c[V], d[V];
-      load_vec<T, V>(p + r * C, a);
-      load_vec<T, V>(p + (r + TY) * C, b);
-      load_vec<T, V>(p + (r + 2 * TY) * C, c);
-      load_vec<T, V>(p + (r + 3 * TY) * C, d);
-#pragma unroll
-      for (int i = 0; i < V; ++i) acc[i] += (fabsf(a[i]) + fabsf(b[i])) + (fabsf(c[i]) + fabsf(d[i]));
-    }
-    for (; r < r1; r += TY) {
-      float a[V];
-      load_vec<T, V>(p + r * C, a);
-#pragma unroll
-      for (int i = 0; i < V; ++i) acc[i] += fabsf(a[i]);
     }
   }
 #pragma unroll

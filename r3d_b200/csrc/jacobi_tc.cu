@@ -16,10 +16,10 @@
 // Pipeline per CTA (persistent over a strided tile list):
 //   warp 0      TMA producer: panel tile (two 32-column boxes of 128 rows, K-major
 //               SWIZZLE_128B) + Q^T (two 32-column boxes of 64 rows, K-major SWIZZLE_128B)
-//   warps 4-7   splitters: hi/lo split in shared memory (same swizzled addresses)
+//   warps 2-5   splitters: hi/lo split in shared memory (same swizzled addresses)
 //   warp 1      MMA issuer: 24 x tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=64, K=8)
-//   warps 8-11  epilogue: tcgen05.ld 32x32b.x64 -> (transposed) global stores
-//   warp 2      TMEM allocator (2 accumulator stages x 64 columns)
+//   warps 6-9   epilogue: tcgen05.ld 32x32b.x64 -> (transposed) global stores
+//   (warp 0 also allocates TMEM: 2 accumulator stages x 64 columns)
 // SASS evidence: UTCHMMA/UTCMMA (tcgen05.mma), UTMALDG (TMA), LDTM (tcgen05.ld).
 #include <cuda.h>
 
@@ -44,6 +44,10 @@ constexpr int STG_WARP = kStgWarpBytes;              // 2560 B of store staging 
 constexpr int SMEM_TOTAL = NSTAGE * STAGE + 4 * STG_WARP + 1024 + 256;
 constexpr int TMEM_COLS_P = 128;       // 2 accumulator stages x 64 fp32 columns
 constexpr int JMAXS = 32;              // must equal JMAX_SWEEPS
+// 10 warps: 0 = TMA producer + TMEM allocator, 1 = MMA issuer, 2-5 = splitters, 6-9 = epilogue.  320 threads x 72
+// registers x 2 CTAs leave room (registers and shared memory) for one CTA of the inner solver on the same SM, so
+// that the side-stream V update and the next inner solve can actually run together.
+constexpr int kPanelThreads = 320;
 
 __device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void bar_init(uint64_t* bar, uint32_t count) {
@@ -218,7 +222,7 @@ __device__ __forceinline__ void spin_until(const int* p, int target, int* err) {
   }
 }
 
-__global__ void __launch_bounds__(384, 2) panel_update_tc_kernel(const __grid_constant__ CUtensorMap map_in0,
+__global__ void __maxnreg__(72) panel_update_tc_kernel(const __grid_constant__ CUtensorMap map_in0,
                                                                  const __grid_constant__ CUtensorMap map_in1,
                                                                  const __grid_constant__ CUtensorMap map_q,
                                                                  PanelJob pj, int njobs, int B, int np, int nb, int nt,
@@ -248,7 +252,8 @@ __global__ void __launch_bounds__(384, 2) panel_update_tc_kernel(const __grid_co
     for (int s = 0; s < 2; ++s) { bar_init(&tmem_full[s], 1); bar_init(&tmem_empty[s], 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 2) {
+  if (warp == 0) {
+    __syncwarp();
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_slot)),
                  "n"(TMEM_COLS_P) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -328,9 +333,9 @@ __global__ void __launch_bounds__(384, 2) panel_update_tc_kernel(const __grid_co
         ++it;
       }
     }
-  } else if (warp >= 4 && warp < 8) {
+  } else if (warp >= 2 && warp < 6) {
     // ===================== splitters: x -> (hi, lo) in shared memory =====================
-    const int t = threadIdx.x - 128;
+    const int t = threadIdx.x - 64;
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const TileInfo ti = decode_tile(tile, njobs, B, nt, mtiles, sweep, cnt, qflag, pj);
@@ -369,7 +374,7 @@ __global__ void __launch_bounds__(384, 2) panel_update_tc_kernel(const __grid_co
       bar_arrive(&split_done[s]);
       ++it;
     }
-  } else if (warp >= 8) {
+  } else if (warp >= 6) {
     // ===================== epilogue: TMEM -> global =====================
     const int q = warp & 3;                      // TMEM lanes [32q, 32q+32)
     int it = 0;
@@ -449,7 +454,8 @@ __global__ void __launch_bounds__(384, 2) panel_update_tc_kernel(const __grid_co
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 2) {
+  if (warp == 0) {
+    __syncwarp();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS_P) : "memory");
   }
 }
@@ -531,7 +537,7 @@ static int panel_launch(PanelTc* h, const CUtensorMap& in, const CUtensorMap& q,
   int grid = (int)std::min<int64_t>(tiles, 2 * kNumSMs);
   if (g_panel_grid_cap > 0) grid = std::min(grid, g_panel_grid_cap);
   StageScope scope(stage_id, st);
-  panel_update_tc_kernel<<<grid, 384, SMEM_TOTAL, st>>>(in, in, q, pj, 1, (int)h->B, h->np, h->nb, h->nt, round, sweep,
+  panel_update_tc_kernel<<<grid, kPanelThreads, SMEM_TOTAL, st>>>(in, in, q, pj, 1, (int)h->B, h->np, h->nb, h->nt, round, sweep,
                                                         cnt, qflag, g_panel_debug);
   R3D_LAUNCH_CHECK();
   return 0;
@@ -558,7 +564,7 @@ static int panel_launch_merged(PanelTc* h, const CUtensorMap& q, int round, int 
   int grid = (int)std::min<int64_t>(tiles, 2 * kNumSMs);
   if (g_panel_grid_cap > 0) grid = std::min(grid, g_panel_grid_cap);
   StageScope scope(ST_JACOBI_UPDATE, st);
-  panel_update_tc_kernel<<<grid, 384, SMEM_TOTAL, st>>>(h->map_g, h->map_h, q, pj, 2, (int)h->B, h->np, h->nb, h->nt,
+  panel_update_tc_kernel<<<grid, kPanelThreads, SMEM_TOTAL, st>>>(h->map_g, h->map_h, q, pj, 2, (int)h->B, h->np, h->nb, h->nt,
                                                         round, sweep, cnt, qflag, g_panel_debug);
   R3D_LAUNCH_CHECK();
   return 0;

@@ -39,7 +39,8 @@ struct Options {
   int panel_ring = 6;           // merged schedule: ring slots (groups) of H
   int jacobi_inner_regs = 1;    // 1: register-resident inner solver for the cross rounds, 0: shared-memory solver everywhere
   int gemm_tc = 1;              // 1: refinement / backward / fp32 Gram GEMMs on tcgen05 via bf16 planes, 0: SIMT
-  int jacobi_v_after_g = 1;     // 1: start V(r) after the G passes of round r, so it overlaps inner(r+1) instead of competing for HBM
+  int jacobi_v_after_g = 0;     // 0: V(r) starts right after inner(r) and runs beside the G passes (58.9 ms); 1: V(r) starts after the
+                                //    G passes of round r and runs beside inner(r+1) (60.1 ms with the register-resident inner solver)
   int jacobi_overlap_v = 1;     // run V <- V Q on a side stream, overlapped with the next inner solve
 };
 Options& options();
