@@ -21,11 +21,17 @@ for B, T, C in shapes:
     er, sigma, sw = ops.erank(x, return_aux=True)
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
+    _lib.profile_enable(True); _lib.profile_read(reset=True)
+    ops.erank(x)
+    prof = _lib.profile_read(reset=True); _lib.profile_enable(False)
+    gram_ms = prof.get("gram", {}).get("ms", 0.0)      # two-pass solver: X X^T (tcgen05 bf16) + Y Y^T (bf16-plane GEMM)
+    jac_ms = sum(prof.get(k, {}).get("ms", 0.0) for k in ("jacobi_init", "jacobi_inner", "jacobi_update", "jacobi_extract"))
     nchk = min(B, 2)
     ref = EO.erank(x[:nchk].float().cpu().numpy())
     rel = float(np.abs(er[:nchk].cpu().numpy() - ref).max() / ref.max())
     rows.append(dict(B=B, T=T, C=C, n=min(T, C), ms=ms, samples_per_s=B / ms * 1e3, sweeps=float(sw.float().mean()),
-                     erank_mean=float(er.mean()), rel_err_vs_f64=rel))
+                     erank_mean=float(er.mean()), rel_err_vs_f64=rel, gram_ms=gram_ms, jacobi_ms=jac_ms,
+                     jacobi_over_gram=jac_ms / max(gram_ms, 1e-9)))
     print(json.dumps(rows[-1]))
     del x, er, sigma, sw
     torch.cuda.empty_cache()
