@@ -374,6 +374,51 @@ def test_erank_backward_bf16(kind, B, T, C, dev):
     assert np.abs(got - ref).max() <= 1e-2 * np.abs(ref).max()
 
 
+@pytest.mark.parametrize("B,T,C,dtype", [(3, 128, 256, torch.float32), (2, 256, 256, torch.float32),
+                                         (2, 512, 512, torch.bfloat16)])
+def test_fuser_step_matches_oracle(B, T, C, dtype, dev):
+    """ops.FuserStep is the fused fwd/bwd step bench.py times (erank of both modalities, score -> bottom-k -> exchange,
+    exchange backward + d(mean erank)/dX accumulated): every output against the oracle on the same inputs."""
+    from r3d_b200 import ops
+    rgb, dep = synth(B, T, C, 77, dtype)
+    g = torch.randn(B, T, 2, C, generator=torch.Generator().manual_seed(4321)).to(dtype)
+    buf = torch.stack([rgb, dep]).to(dev).contiguous()
+    step = ops.FuserStep(B, T, C, dtype, dev)
+    out, er, dgrad = step(buf, g.to(dev))
+    rn, dn, gn = rgb.float().numpy(), dep.float().numpy(), g.float().numpy()
+    k = C // 4
+    ir, idd = O.bottomk(O.channel_score(rn), k), O.bottomk(O.channel_score(dn), k)
+    np.testing.assert_array_equal(np.sort(step.idx[0].cpu().numpy()), np.sort(ir))        # bit-exact selections
+    np.testing.assert_array_equal(np.sort(step.idx[1].cpu().numpy()), np.sort(idd))
+    np.testing.assert_array_equal(out.float().cpu().numpy(), O.exchange_fwd(rn, dn, ir, idd))
+    x2 = np.concatenate([rn, dn])                                                         # (2B, T, C)
+    er_ref = EO.erank(x2)
+    np.testing.assert_allclose(er.cpu().numpy(), er_ref, rtol=1e-4)
+    gr, gd, _ = O.exchange_bwd(gn, rn, dn, ir, idd)
+    de = EO.erank_bwd(x2, np.full(2 * B, 1.0 / (2 * B), np.float32))
+    ref = np.stack([gr + de[:B], gd + de[B:]])
+    got = dgrad.float().cpu().numpy()
+    tol = 1e-4 if dtype == torch.float32 else 1e-2
+    assert np.abs(got - ref).max() <= tol * np.abs(ref).max()
+    # the erank part alone (what the tolerance is really about): subtract the bit-exact exchange gradient
+    if dtype == torch.float32:
+        part = got - np.stack([gr, gd])
+        assert np.abs(part - np.stack([de[:B], de[B:]])).max() <= 1e-4 * np.abs(de).max() + 1e-7 * np.abs(ref).max()
+
+
+def test_erank_c5_shape(dev):
+    """BASELINE.json configs[4] shape (T=2048, C=1024 per sample, bf16): forward and gradient against the oracle."""
+    from r3d_b200 import ops
+    x = torch.from_numpy(_spectra("relu", 2, 2048, 1024, 3)).to(torch.bfloat16)
+    xt = x.to(dev).requires_grad_(True)
+    er = ops.erank(xt)
+    er.sum().backward()
+    xn = x.float().numpy()
+    np.testing.assert_allclose(er.detach().cpu().numpy(), EO.erank(xn), rtol=1e-4)
+    ref = EO.erank_bwd(xn, np.ones(2, np.float32))
+    assert np.abs(xt.grad.float().cpu().numpy() - ref).max() <= 1e-2 * np.abs(ref).max()
+
+
 def test_gram_and_jacobi_stages(dev):
     from r3d_b200 import ops
     x = _spectra("relu", 3, 96, 160, 1)
