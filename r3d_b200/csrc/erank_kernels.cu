@@ -184,7 +184,8 @@ static JacobiWs jacobi_carve(void* ws, int64_t B, int64_t n) {
 
 // Gp <- zero-padded copy of G; Vt <- I; cnt <- 0; nu <- 2^-21 * max |diag|.
 __global__ void jacobi_init_kernel(const float* __restrict__ G, int n, int np, float* __restrict__ Gp,
-                                   float* __restrict__ Vt, int* __restrict__ cnt, float* __restrict__ nu) {
+                                   float* __restrict__ Vt, int* __restrict__ cnt, float* __restrict__ nu,
+                                   float nu_ulps) {
   const int b = blockIdx.y;
   const float* g = G + int64_t(b) * n * n;
   float* gp = Gp + int64_t(b) * np * np;
@@ -208,7 +209,7 @@ __global__ void jacobi_init_kernel(const float* __restrict__ G, int n, int np, f
       if (threadIdx.x < s) smax[threadIdx.x] = fmaxf(smax[threadIdx.x], smax[threadIdx.x + s]);
       __syncthreads();
     }
-    if (threadIdx.x == 0) nu[b] = smax[0] * 4.76837158e-7f;   // 4 * 2^-23
+    if (threadIdx.x == 0) nu[b] = smax[0] * nu_ulps * 1.1920929e-7f;   // nu_ulps * 2^-23 (default 4)
     for (int i = threadIdx.x; i < JMAX_SWEEPS; i += blockDim.x) cnt[b * JMAX_SWEEPS + i] = 0;
   }
 }
@@ -971,6 +972,7 @@ extern "C" int r3d_set_option(const char* key, double value) {
   else if (k == "erank_passes") options().erank_passes = (int)value;
   else if (k == "erank_pass2_sweeps") options().erank_pass2_sweeps = (int)value;
   else if (k == "jacobi_tol_pass1") options().jacobi_tol_pass1 = (float)value;
+  else if (k == "jacobi_nu_pass1") options().jacobi_nu_pass1 = (float)value;
   else if (k == "jacobi_inner_regs") options().jacobi_inner_regs = (int)value;
   else if (k == "panel_merged") options().panel_merged = (int)value;
   else if (k == "row_chunk_mult") g_row_chunk_mult = std::max(1, std::min(16, (int)value));
@@ -1201,7 +1203,8 @@ static int jacobi_run(const float* G, int64_t B, int64_t n, void* workspace, flo
   {
     dim3 grid(std::min<int64_t>((int64_t(w.np) * w.np + 255) / 256, 64), (unsigned)B);
     R3D_STAGE(ST_JACOBI_INIT, st);
-    jacobi_init_kernel<<<grid, 256, 0, st>>>(G, int(n), w.np, w.Gp, w.Vt, w.cnt, w.nu);
+    jacobi_init_kernel<<<grid, 256, 0, st>>>(G, int(n), w.np, w.Gp, w.Vt, w.cnt, w.nu,
+                                             tol_override > 0.f ? options().jacobi_nu_pass1 : 4.f);
     R3D_LAUNCH_CHECK();
   }
   const size_t upd_smem = size_t(3) * JM * (JM + 4) * sizeof(float);

@@ -28,7 +28,13 @@ struct Options {
   int jacobi_chunks = 1;        // 2: run two half-batches on two streams (measured slower at the headline shape: 69.8 vs 65.9 ms)
   float jacobi_tol_pass1 = 1e-5f; // first-pass threshold when a second pass follows (looser values measured slower:
                                   // 1e-4 -> 70.4 ms, 1e-3 -> 73.7 ms vs 69.2 ms; the second pass then needs more sweeps)
-  int erank_pass2_sweeps = 3;   // sweep cap of the second pass (0 = jacobi_max_sweeps); it converges in 2 (quadratic phase)
+  float jacobi_nu_pass1 = 2048.f; // first pass of the two-pass solver: absolute significance floor in units of 2^-23 max|diag|
+                                  // (single-pass solver and second pass: 4).  The second pass removes what the first leaves,
+                                  // so the first may stop ~2.5 sweeps earlier: 4 -> 55.1 ms, 1024 -> 50.7, 4096 -> 48.8 with
+                                  // unchanged gradients (<= 8e-5); from 16384 on the hardest spectrum (channel decay 512x512)
+                                  // loses its smallest directions (9e-3)
+  int erank_pass2_sweeps = 6;   // sweep cap of the second pass (0 = jacobi_max_sweeps); it usually converges in 2-3, and the
+                                // sweeps after convergence cost launch latency only (48.8 -> 49.4 ms for 3 -> 6)
   int erank_passes = 2;         // 2: second refinement pass (G2 = Y Y^T -> Jacobi -> U, Y updated): relative accuracy for the
                                 //    smallest singular directions (gradients <= 1e-4 on square samples), +15 % time;
                                 //    1: single pass (erank itself is already <= 3e-6; gradients 2e-4 .. 1e-2)

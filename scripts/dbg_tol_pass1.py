@@ -1,0 +1,28 @@
+"""Two-pass solver: first-pass threshold vs accuracy (fp32 gradient error vs float64) -- time comes from bench.py --opt."""
+import sys, numpy as np, torch
+sys.path.insert(0, '.')
+from r3d_b200 import _lib, ops
+from oracle import erank_oracle as EO
+dev = torch.device('cuda')
+def spectra(kind, B, T, C, seed):
+    rng = np.random.default_rng(seed)
+    if kind == "relu": return np.maximum(rng.standard_normal((B, T, C)), 0).astype(np.float32)
+    if kind == "gauss": return rng.standard_normal((B, T, C)).astype(np.float32)
+    if kind == "rankdef":
+        r = min(T, C) // 4
+        return (rng.standard_normal((B, T, r)) @ rng.standard_normal((B, r, C))).astype(np.float32)
+    if kind == "decay": return (rng.standard_normal((B, T, C)) * np.exp(-np.arange(C) / (C / 8))).astype(np.float32)
+cases = [("gauss", 1, 512, 512), ("relu", 1, 512, 512), ("gauss", 2, 128, 128), ("decay", 2, 256, 512), ("relu", 2, 256, 512), ("decay", 1, 512, 512), ("rankdef", 1, 512, 512)]
+for tol1, cap in ((4096, 6), (16384, 6), (65536, 6), (262144, 6), (262144, 8)):
+    _lib.set_option("erank_passes", 2); _lib.set_option("jacobi_nu_pass1", tol1); _lib.set_option("erank_pass2_sweeps", cap)
+    out = []
+    for kind, B, T, C in cases:
+        x = spectra(kind, B, T, C, T * 1000 + C)
+        xt = torch.from_numpy(x).to(dev).requires_grad_(True)
+        er, sigma, sw = ops.erank(xt, return_aux=True)
+        er.sum().backward()
+        ref = EO.erank(x); gref = EO.erank_bwd(x, np.ones(B, np.float32))
+        e1 = np.abs(er.detach().cpu().numpy() - ref).max() / ref.max()
+        e2 = np.abs(xt.grad.cpu().numpy() - gref).max() / np.abs(gref).max()
+        out.append(f"{kind}{T}x{C}: er {e1:.1e} grad {e2:.1e} sw {int(sw.max())}")
+    print(f"nu_pass1={tol1:g} cap={cap} | " + " | ".join(out), flush=True)
