@@ -812,6 +812,58 @@ __global__ void __launch_bounds__(256) jacobi_extract_kernel(const float* __rest
   }
 }
 
+// Same outputs for the tensor-core path, where eigenvector i is COLUMN i of V (blocked layout: a 32-column block
+// is np contiguous 128-byte rows).  One CTA per (column block, matrix): column norms from coalesced row reads,
+// then 32x32 tiles transposed through shared memory so that both the reads and the writes of U^T are full lines
+// (the row-per-warp kernel above reads one float per 128-byte line in this layout: 258 -> ~50 us per launch).
+__global__ void __launch_bounds__(256) jacobi_extract_cols_kernel(const float* __restrict__ Gp,
+                                                                  const float* __restrict__ V, int n, int np,
+                                                                  const int* __restrict__ cnt, int max_sweeps,
+                                                                  float* __restrict__ lambda, float* __restrict__ Ut,
+                                                                  int* __restrict__ sweeps) {
+  __shared__ float red[8][33];
+  __shared__ float inv[32];
+  __shared__ float tile[32][33];
+  const int b = blockIdx.y, ib = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float* vb = V + int64_t(b) * np * np + int64_t(ib) * np * JB;   // rows j = 0..np-1 of this column block, 32 floats each
+  float ss = 0.f;
+  for (int j = warp; j < n; j += 8) {
+    const float v = vb[int64_t(j) * JB + lane];
+    ss = fmaf(v, v, ss);
+  }
+  red[warp][lane] = ss;
+  __syncthreads();
+  if (warp == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w][lane];
+    inv[lane] = t > 0.f ? rsqrtf(t) : 0.f;
+    const int i = ib * JB + lane;
+    if (lambda && i < n) lambda[int64_t(b) * n + i] = Gp[int64_t(b) * np * np + boff(np, i, i)];
+  }
+  __syncthreads();
+  if (Ut) {
+    float* ub = Ut + int64_t(b) * n * n;
+    for (int j0 = 0; j0 < n; j0 += 32) {
+#pragma unroll
+      for (int r = warp; r < 32; r += 8) tile[r][lane] = (j0 + r < n) ? vb[int64_t(j0 + r) * JB + lane] : 0.f;
+      __syncthreads();
+#pragma unroll
+      for (int c = warp; c < 32; c += 8) {
+        const int i = ib * JB + c, j = j0 + lane;
+        if (i < n && j < n) ub[int64_t(i) * n + j] = tile[lane][c] * inv[c];
+      }
+      __syncthreads();
+    }
+  }
+  if (ib == 0 && threadIdx.x == 0 && sweeps) {
+    int s = 0;
+    while (s < max_sweeps && cnt[b * JMAX_SWEEPS + s] != 0) ++s;
+    sweeps[b] = s + (s < max_sweeps ? 1 : 0);
+  }
+}
+
 // ------------------------------------------------------------------------------
 // sigma_j = ||Y[j,:]|| / ||Ut[j,:]||   (one warp per row)
 // ------------------------------------------------------------------------------
@@ -971,6 +1023,7 @@ extern "C" int r3d_set_option(const char* key, double value) {
   else if (k == "gemm_tc") options().gemm_tc = value != 0.0;
   else if (k == "erank_passes") options().erank_passes = (int)value;
   else if (k == "erank_pass2_sweeps") options().erank_pass2_sweeps = (int)value;
+  else if (k == "erank_pass1_sweeps") options().erank_pass1_sweeps = (int)value;
   else if (k == "jacobi_tol_pass1") options().jacobi_tol_pass1 = (float)value;
   else if (k == "jacobi_nu_pass1") options().jacobi_nu_pass1 = (float)value;
   else if (k == "jacobi_inner_regs") options().jacobi_inner_regs = (int)value;
@@ -1269,8 +1322,12 @@ static int jacobi_run(const float* G, int64_t B, int64_t n, void* workspace, flo
   {
     dim3 grid((unsigned)std::min<int64_t>((n + 7) / 8, 64), (unsigned)B);
     R3D_STAGE(ST_JACOBI_EXTRACT, st);
-    jacobi_extract_kernel<<<grid, 256, 0, st>>>(w.Gp, w.Vt, int(n), w.np, w.cnt, max_sweeps, lambda_out, U_out,
-                                                sweeps_out, tc ? 1 : 0);
+    if (tc)
+      jacobi_extract_cols_kernel<<<dim3((unsigned)((n + JB - 1) / JB), (unsigned)B), 256, 0, st>>>(
+          w.Gp, w.Vt, int(n), w.np, w.cnt, max_sweeps, lambda_out, U_out, sweeps_out);
+    else
+      jacobi_extract_kernel<<<grid, 256, 0, st>>>(w.Gp, w.Vt, int(n), w.np, w.cnt, max_sweeps, lambda_out, U_out,
+                                                  sweeps_out, 0);
     R3D_LAUNCH_CHECK();
   }
   return 0;
@@ -1329,7 +1386,8 @@ extern "C" int r3d_erank_fwd(const void* x, int64_t B, int64_t T, int64_t C, int
   const ErankWs w = erank_carve(workspace, B, T, C, dtype);
   if (int e = r3d_gram(x, B, T, C, dtype, gram_impl, workspace, w.G, st)) return e;
   const bool two_pass = options().erank_passes >= 2;
-  if (int e = jacobi_run_chunked(w.G, B, n, w.jws, nullptr, U_out, sweeps_out, 0, st,
+  if (int e = jacobi_run_chunked(w.G, B, n, w.jws, nullptr, U_out, sweeps_out,
+                                 two_pass ? options().erank_pass1_sweeps : 0, st,
                                  two_pass ? options().jacobi_tol_pass1 : 0.f)) return e;
   if (tc_gemm_ok(T, C) && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
     if (int e = refine_Y_tc(x, dtype, U_out, w, B, T, C, Y_out, st)) return e;

@@ -33,6 +33,8 @@ struct Options {
                                   // so the first may stop ~2.5 sweeps earlier: 4 -> 55.1 ms, 1024 -> 50.7, 4096 -> 48.8 with
                                   // unchanged gradients (<= 8e-5); from 16384 on the hardest spectrum (channel decay 512x512)
                                   // loses its smallest directions (9e-3)
+  int erank_pass1_sweeps = 12;  // sweep cap of the first pass of the two-pass solver (it converges in 8-11 with the raised floor;
+                                // whatever a capped matrix still needs, the second pass does); 0 = jacobi_max_sweeps
   int erank_pass2_sweeps = 6;   // sweep cap of the second pass (0 = jacobi_max_sweeps); it usually converges in 2-3, and the
                                 // sweeps after convergence cost launch latency only (48.8 -> 49.4 ms for 3 -> 6)
   int erank_passes = 2;         // 2: second refinement pass (G2 = Y Y^T -> Jacobi -> U, Y updated): relative accuracy for the
