@@ -24,6 +24,7 @@ import os
 import subprocess
 import sys
 import tempfile
+import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -115,54 +116,103 @@ def main_reference(args):
 
 # ------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock and throttle reasons of one GPU DURING the timed region: an NVML polling thread (10 ms period, so even a
+    250 ms region yields >20 samples); falls back to `nvidia-smi -lms` when pynvml is missing."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    BITS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
     def __init__(self, gpu_index):
         self.idx = gpu_index
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.p = None
+        self.f = None
+        self.thread = None
+        self.stop_flag = False
+        self.sm, self.mx, self.reasons = [], [], set()
+        # CUDA_VISIBLE_DEVICES remapping: NVML wants the physical index
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        self.phys = gpu_index
+        if vis:
+            try:
+                self.phys = int(vis.split(",")[gpu_index])
+            except Exception:
+                self.phys = gpu_index
+
+    def _poll(self):
+        import pynvml
+        h = pynvml.nvmlDeviceGetHandleByIndex(self.phys)
+        try:
+            mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            mx = None
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                if mx is not None:
+                    self.mx.append(float(mx))
+                r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for nm, bit in self.BITS.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(0.01)
 
     def start(self):
         try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
+        try:
+            self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
-                                       str(self.idx), "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       str(self.phys), "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        if self.p is None:
-            return out
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except Exception:
-            self.p.kill()
-        self.f.flush()
-        self.f.seek(0)
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.f.read().splitlines():
-            parts = [x.strip() for x in ln.split(",")]
-            if len(parts) < 9:
-                continue
+        if self.thread is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            sm, mx, reasons = list(self.sm), list(self.mx), set(self.reasons)
+        elif self.p is not None:
+            self.p.terminate()
             try:
-                sm.append(float(parts[1])); mx.append(float(parts[2]))
-            except ValueError:
-                continue
-            for nm, v in zip(names, parts[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        self.f.close()
-        try:
-            os.unlink(self.f.name)
-        except OSError:
-            pass
+                self.p.wait(timeout=5)
+            except Exception:
+                self.p.kill()
+            self.f.flush()
+            self.f.seek(0)
+            sm, mx, reasons = [], [], set()
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            for ln in self.f.read().splitlines():
+                parts = [x.strip() for x in ln.split(",")]
+                if len(parts) < 9:
+                    continue
+                try:
+                    sm.append(float(parts[1])); mx.append(float(parts[2]))
+                except ValueError:
+                    continue
+                for nm, v in zip(names, parts[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            self.f.close()
+            try:
+                os.unlink(self.f.name)
+            except OSError:
+                pass
+        else:
+            return out
         if sm:
             sm.sort()
-            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=(max(mx) if mx else None), reasons=sorted(reasons),
+                       samples=len(sm))
         return out
 
 
@@ -319,8 +369,10 @@ def main_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the single JSON line
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() in ("VERSION", "WARN"):
+            # NCCL prints its version banner on stdout at every level >= VERSION (WARN included); stdout must carry
+            # the single JSON line only.  An explicit INFO/TRACE request is respected.
+            os.environ["NCCL_DEBUG"] = "NONE"
         dist.init_process_group("nccl", device_id=dev)
     import r3d_b200
     from r3d_b200 import _lib, ops
