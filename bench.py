@@ -412,11 +412,33 @@ def main_ours(args):
     def resident(i):
         step(dev_in[i % NSETS], dev_g[i % NSETS])
 
+    # End to end the way a training loop with a prefetching loader runs it: the pinned-host -> device copy of step
+    # i+1 is issued on a copy stream while step i computes (two staging buffers); every step's input still crosses
+    # PCIe inside the timed region and every step ends with the device -> host read of its statistic.
+    copy_stream = torch.cuda.Stream(device=dev)
+    stage = [stage_buf, torch.empty_like(stage_buf)]
+    ev_copied = [torch.cuda.Event(), torch.cuda.Event()]
+    ev_consumed = [torch.cuda.Event(), torch.cuda.Event()]
+    e2e_state = {"steps": 0}
+
+    def issue_copy(i):
+        s_ = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(ev_consumed[s_])                     # the step that last read this buffer is done
+            stage[s_].copy_(host_in[i % NSETS], non_blocking=True)      # H2D of step i's inputs
+            ev_copied[s_].record(copy_stream)
+
     def end_to_end(i):
-        stage_buf.copy_(host_in[i % NSETS], non_blocking=True)          # H2D of this step's inputs
-        _, er, _ = step(stage_buf, dev_g[i % NSETS])
+        main = torch.cuda.current_stream()
+        if i == 0:
+            issue_copy(0)
+        if i + 1 < e2e_state["steps"]:
+            issue_copy(i + 1)
+        main.wait_event(ev_copied[i % 2])
+        _, er, _ = step(stage[i % 2], dev_g[i % NSETS])
+        ev_consumed[i % 2].record(main)
         er_host.copy_(er, non_blocking=True)                            # D2H of the step's statistic
-        torch.cuda.current_stream().synchronize()
+        main.synchronize()
 
     for i in range(max(args.warmup, 3)):
         resident(i)
@@ -438,8 +460,10 @@ def main_ours(args):
     sweeps = step.sweeps.float().mean().item()
     er_mean = step.er.mean().item()
     # ---- end to end
+    e2e_state["steps"] = 2
     for i in range(2):
         end_to_end(i)
+    e2e_state["steps"] = args.steps
     ms_e2e = timed(end_to_end, args.steps)
 
     value = world * B * args.steps / (ms * 1e-3)
