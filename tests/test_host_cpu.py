@@ -180,3 +180,33 @@ def test_two_rank_gloo_matches_single_process_oracle():
         np.testing.assert_allclose(g2, 0.0)
         np.testing.assert_allclose(g3, 15.0)
     np.testing.assert_array_equal(outs[0][3], outs[1][3])
+
+
+# ------------------------------------------------------------------ bench.py contract (CPU-runnable parts)
+def test_bench_reference_arm_prints_one_json_line():
+    """`bench.py --impl reference` (the reference's CPU algorithm on the host cores) prints exactly one JSON line with
+    the keys the driver reads."""
+    import json, subprocess, sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0", "--cpu-sample", "1"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "clips/s" and d["higher_is_better"] is True
+    assert d["vs_baseline"] is None and d["value"] > 0 and d["steps"] == 1
+    assert set(d["cpu_baseline"]) >= {"value", "unit", "cores", "kind", "sample"} and d["cpu_baseline"]["kind"] == "port"
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert "workload" in d["config"]
+
+
+def test_bench_ours_refuses_without_gpu():
+    """The product arm has no CPU fallback: without a CUDA device it exits with an error instead of timing the oracle."""
+    import subprocess, sys
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("needs a box without a GPU")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert out.returncode != 0
+    assert "CUDA" in (out.stderr + out.stdout)
