@@ -11,6 +11,22 @@ namespace r3d {
 
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 
+// cudaFuncSetAttribute and streams/events belong to ONE device; a process that drives several GPUs from several
+// threads (nn.DataParallel) needs them once per device.  Returns true the first time it is called for the current
+// device with this flag array (benign race: the guarded calls are idempotent).
+constexpr int kMaxDevices = 64;
+inline int current_device_index() {
+  int d = 0;
+  cudaGetDevice(&d);
+  return (d >= 0 && d < kMaxDevices) ? d : 0;
+}
+inline bool per_device_once(bool (&done)[kMaxDevices]) {
+  const int d = current_device_index();
+  if (done[d]) return false;
+  done[d] = true;
+  return true;
+}
+
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
 

@@ -1238,7 +1238,8 @@ struct StreamSet {
     return 0;
   }
 };
-static thread_local StreamSet g_streams;
+static thread_local StreamSet g_streams_dev[kMaxDevices];   // per host thread AND per device
+#define g_streams (g_streams_dev[current_device_index()])
 
 static int jacobi_run(const float* G, int64_t B, int64_t n, void* workspace, float* lambda_out, float* U_out,
                       int32_t* sweeps_out, int max_sweeps, cudaStream_t st, int chunk = 0, float tol_override = 0.f) {

@@ -291,11 +291,10 @@ int gram_tcgen05_launch(const void* x, int64_t B, int64_t T, int64_t C, int dtyp
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   R3D_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with %d", (int)r);
-  static bool attr_done = false;
-  if (!attr_done) {
+  static bool attr_done[kMaxDevices] = {};
+  if (per_device_once(attr_done)) {
     R3D_CUDA(cudaFuncSetAttribute(gram_bf16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     R3D_CUDA(cudaFuncSetAttribute(gram_bf16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_done = true;
   }
   const int grid = int(B * ((n + TILE_M - 1) / TILE_M) * ((n + TILE_N - 1) / TILE_N));
   R3D_STAGE(ST_GRAM, st);

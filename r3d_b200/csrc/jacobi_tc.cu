@@ -515,10 +515,9 @@ int panel_tc_prepare(PanelTc* h, float* G, float* H, float* V, const float* Qb0,
   if (int e = make_map_panel(&h->map_v, V, B, np)) return e;
   if (int e = make_map_q(&h->map_q[0], Qb0, B * h->nt * PM)) return e;
   if (int e = make_map_q(&h->map_q[1], Qb1, B * h->nt * PM)) return e;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static bool attr_done[kMaxDevices] = {};
+  if (per_device_once(attr_done)) {
     R3D_CUDA(cudaFuncSetAttribute(panel_update_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
-    attr_done = true;
   }
   return 0;
 }

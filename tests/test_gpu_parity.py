@@ -524,3 +524,74 @@ def test_tensor_core_gemms_match_simt(B, T, C, dtype, dev):
     if T == C:
         tol = max(tol, 1e-2)     # square hard-edge spectrum: gradient is ill-conditioned (see test_erank_backward_vs_oracle)
     assert np.abs(outs[1][2] - outs[0][2]).max() / gmax < tol
+
+
+# ------------------------------------------------------------------ several devices in one process (nn.DataParallel pattern)
+def test_two_devices_one_process():
+    """The reference trains under nn.DataParallel (main_utkinects.py:129): one process, one host thread per device.
+    Kernel attributes, tensor maps and the library's side streams are per device; the same thread must also be able
+    to use one device after another."""
+    import threading
+    from r3d_b200 import ops
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    x = _spectra("relu", 2, 128, 256, 9)
+    ref = EO.erank(x)
+    rgb, dep = synth(2, 64, 256, 5)
+    sref = O.channel_score(rgb.numpy())
+    # same thread, device after device
+    for d in (0, 1, 0):
+        dv = torch.device("cuda", d)
+        er = ops.erank(torch.from_numpy(x).to(dv))
+        np.testing.assert_allclose(er.cpu().numpy(), ref, rtol=1e-4)
+        sc = ops.channel_score(rgb.to(dv), dep.to(dv))
+        np.testing.assert_allclose(sc[0].cpu().numpy(), sref, rtol=1e-5)
+    # one thread per device, concurrently
+    out, err = {}, []
+
+    def work(d):
+        try:
+            dv = torch.device("cuda", d)
+            with torch.cuda.device(dv):
+                xt = torch.from_numpy(x).to(dv).requires_grad_(True)
+                for _ in range(3):
+                    er = ops.erank(xt)
+                er.sum().backward()
+                torch.cuda.synchronize(dv)
+                out[d] = (er.detach().cpu().numpy(), xt.grad.cpu().numpy())
+        except Exception as ex:   # pragma: no cover
+            err.append(repr(ex))
+
+    ts = [threading.Thread(target=work, args=(d,)) for d in (0, 1)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not err, err
+    gref = EO.erank_bwd(x, np.ones(2, np.float32))
+    for d in (0, 1):
+        np.testing.assert_allclose(out[d][0], ref, rtol=1e-4)
+        assert np.abs(out[d][1] - gref).max() <= 1e-4 * np.abs(gref).max()
+
+
+def test_cmfuser_under_dataparallel():
+    """nn.DataParallel over two GPUs (main_utkinects.py:129): every replica scores its own shard, so the result equals
+    the single-device module applied to each shard (score_scope='local' semantics), forward and backward."""
+    import r3d_b200
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    B, T, C = 4, 40, 128
+    rgb, dep = synth(B, T, C, 31)
+    torch.manual_seed(0)
+    fuser = r3d_b200.CMFuser(C, depth=1, num_heads=4, score_scope="local").to("cuda:0").eval()
+    dp = torch.nn.DataParallel(fuser, device_ids=[0, 1])
+    r = rgb.to("cuda:0").requires_grad_(True)
+    d = dep.to("cuda:0").requires_grad_(True)
+    y = dp({"rgb": r, "depth": d}, "test")
+    gy = torch.randn(B, T, C, generator=torch.Generator().manual_seed(3)).to("cuda:0")
+    y.backward(gy)
+    r2 = rgb.to("cuda:0").requires_grad_(True)
+    d2 = dep.to("cuda:0").requires_grad_(True)
+    ys = [fuser({"rgb": r2[i:i + 2], "depth": d2[i:i + 2]}, "test") for i in (0, 2)]
+    yref = torch.cat(ys)
+    yref.backward(gy)
+    assert torch.allclose(y, yref, rtol=1e-4, atol=1e-5)
+    assert torch.allclose(r.grad, r2.grad, rtol=1e-4, atol=1e-5) and torch.allclose(d.grad, d2.grad, rtol=1e-4, atol=1e-5)
