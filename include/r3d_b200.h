@@ -154,6 +154,21 @@ size_t r3d_jacobi_workspace_bytes(int64_t B, int64_t n);
 int r3d_token_informativeness(const float* sigma, const float* U, int64_t B, int64_t n, float rtol,
                               float* score_out, void* stream);
 
+/* ---- f1 (next row, first step): row LayerNorm of the fuser Block ------------------
+ * Replaces the three nn.LayerNorm of a fuser call and their autograd backward:
+ *   Block.norm1 / Block.norm2  model/extras/transformerblock.py:122,127 (used :132,:134)
+ *   CMFuser.norm               model/futr_safuser_tokenfusion.py:25 (used :93), same lines in the
+ *                              _vary / _batchnormalization / futr_safuser_depth variants.
+ * x, y, dy, dx: (rows, C) row-major in `dtype`; gamma, beta in the same dtype (nn.LayerNorm keeps its
+ * parameters in the module dtype); mean, rstd: (rows) fp32 saved by the forward for the backward.
+ * C must be a multiple of 8 (bf16) / 4 (fp32) and at most 2048 (bf16) / 1024 (fp32); tensors 16-byte aligned.
+ * r3d_ln_bwd writes dx and dgamma_dbeta = (2, C) fp32 [dgamma | dbeta] (deterministic two-stage reduction). */
+size_t r3d_ln_bwd_workspace_floats(int64_t rows, int64_t C);
+int r3d_ln_fwd(const void* x, const void* gamma, const void* beta, int64_t rows, int64_t C, int dtype, float eps,
+               void* y, float* mean, float* rstd, void* stream);
+int r3d_ln_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const void* gamma, int64_t rows,
+               int64_t C, int dtype, void* dx, float* workspace, float* dgamma_dbeta, void* stream);
+
 /* ---- host-buffer convenience (what a non-Python caller binds; used for `e2e`) ----
  * All pointers are HOST pointers (pinned for full speed); the call copies in,
  * runs score -> bottom-k -> exchange on the given stream, copies the stacked

@@ -55,6 +55,16 @@ class MLP(nn.Module):
         return self.mlp(x)
 
 
+def _ln(mod: nn.LayerNorm, x: torch.Tensor) -> torch.Tensor:
+    """nn.LayerNorm through the hand-written row kernels (ops.layer_norm) whenever they cover the shape; the module
+    object stays an nn.LayerNorm so that state_dict names and checkpoints are the reference's."""
+    C = x.shape[-1]
+    if mod.elementwise_affine and mod.weight is not None and mod.bias is not None \
+            and tuple(mod.normalized_shape) == (C,) and ops.layer_norm_supported(x, C):
+        return ops.layer_norm(x, mod.weight, mod.bias, mod.eps)
+    return mod(x)
+
+
 class Block(nn.Module):
     """model/extras/transformerblock.py:118-135 specialised to the fuser's use:
     two tokens per row and a -inf diagonal mask.  softmax([-inf, a]) == [0, 1]
@@ -70,12 +80,12 @@ class Block(nn.Module):
 
     def forward(self, x: torch.Tensor, attn_mask=None):
         C = self.dim
-        h = self.norm1(x)
+        h = _ln(self.norm1, x)
         w_v = self.attn.qkv.weight[2 * C:]
         b_v = None if self.attn.qkv.bias is None else self.attn.qkv.bias[2 * C:]
         v = F.linear(h, w_v, b_v)                       # (R, 2, C): only the V third of qkv
         x = x + self.attn.proj(v.flip(1))               # token m <- V of token 1-m
-        x = x + self.mlp(self.norm2(x))
+        x = x + self.mlp(_ln(self.norm2, x))
         return x, None
 
 
@@ -203,7 +213,7 @@ class CMFuser(nn.Module):
             x, _ = blk(x)
         if self.variant == "tokenfusion":
             x = x + x_res                                     # tokenfusion.py:92
-        y = self.norm(x).mean(dim=1).view(B, T, C)
+        y = _ln(self.norm, x).mean(dim=1).view(B, T, C)
         if self.variant == "safuser":
             # attention weights are the constant [[0,1],[1,0]]:
             # (B, depth, T, heads, 2, 2) as futr_safuser_depth.py:64 returns

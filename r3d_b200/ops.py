@@ -369,6 +369,64 @@ def jacobi_eigh(G: torch.Tensor, max_sweeps: int = 30) -> Tuple[torch.Tensor, to
     return lam, U, sw
 
 
+# ---------------------------------------------------------------------------------
+# f1 (first step): row LayerNorm of the fuser Block
+# (reference: model/extras/transformerblock.py:122,127,132,134; model/futr_safuser_tokenfusion.py:25,93)
+# ---------------------------------------------------------------------------------
+def layer_norm_supported(x: torch.Tensor, C: int) -> bool:
+    """Shapes the hand-written kernel takes; anything else is the caller's business (CMFuser falls back to
+    torch's LayerNorm -- library code on the same device, not a CPU path -- for widths it does not cover)."""
+    if not x.is_cuda or x.dtype not in _DT:
+        return False
+    v = 4 if x.dtype == torch.float32 else 8
+    return C % v == 0 and C <= 32 * v * 8
+
+
+class _LayerNorm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps):
+        C = x.shape[-1]
+        xc = x.contiguous()
+        rows = xc.numel() // C
+        w = weight.to(xc.dtype).contiguous()
+        b = bias.to(xc.dtype).contiguous()
+        L = _lib.lib()
+        with _on(xc.device):
+            y = torch.empty_like(xc)
+            mean = torch.empty(rows, dtype=torch.float32, device=xc.device)
+            rstd = torch.empty(rows, dtype=torch.float32, device=xc.device)
+            check(L.r3d_ln_fwd(_p(xc), _p(w), _p(b), rows, C, _dt(xc), float(eps), _p(y), _p(mean), _p(rstd), _stream()))
+        ctx.save_for_backward(xc, w, mean, rstd)
+        ctx.wdtype, ctx.bdtype = weight.dtype, bias.dtype
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        xc, w, mean, rstd = ctx.saved_tensors
+        C = xc.shape[-1]
+        rows = xc.numel() // C
+        g = gy.contiguous()
+        L = _lib.lib()
+        with _on(xc.device):
+            dx = torch.empty_like(xc)
+            ws = torch.empty(L.r3d_ln_bwd_workspace_floats(rows, C), dtype=torch.float32, device=xc.device)
+            dgb = torch.empty(2, C, dtype=torch.float32, device=xc.device)
+            check(L.r3d_ln_bwd(_p(g), _p(xc), _p(mean), _p(rstd), _p(w), rows, C, _dt(xc), _p(dx), _p(ws), _p(dgb),
+                               _stream()))
+        return dx, dgb[0].to(ctx.wdtype), dgb[1].to(ctx.bdtype), None
+
+
+def layer_norm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
+    """F.layer_norm(x, (C,), weight, bias, eps) over the last dimension, differentiable in x, weight and bias."""
+    _need_cuda(x, weight, bias)
+    C = x.shape[-1]
+    if weight.shape != (C,) or bias.shape != (C,):
+        raise R3DError(f"layer_norm: weight/bias must have shape ({C},)")
+    if not layer_norm_supported(x, C):
+        raise R3DError(f"layer_norm: unsupported dtype/width {x.dtype}, C={C} (see include/r3d_b200.h)")
+    return _LayerNorm.apply(x, weight, bias, eps)
+
+
 def token_informativeness(sigma: torch.Tensor, U: torch.Tensor, rtol: float = DEFAULT_RTOL) -> torch.Tensor:
     """s_t = sum_j p_j U[t, j]^2 over the short side (B, n)."""
     _need_cuda(sigma, U)

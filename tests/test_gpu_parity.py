@@ -595,3 +595,40 @@ def test_cmfuser_under_dataparallel():
     yref.backward(gy)
     assert torch.allclose(y, yref, rtol=1e-4, atol=1e-5)
     assert torch.allclose(r.grad, r2.grad, rtol=1e-4, atol=1e-5) and torch.allclose(d.grad, d2.grad, rtol=1e-4, atol=1e-5)
+
+
+# ------------------------------------------------------------------ f1, first step: LayerNorm kernels
+@pytest.mark.parametrize("rows,C,dtype", [(7, 128, torch.float32), (1000, 512, torch.float32), (333, 40, torch.float32),
+                                          (4096, 512, torch.bfloat16), (50, 1024, torch.bfloat16),
+                                          (9, 2048, torch.bfloat16), (65, 136, torch.bfloat16)])
+def test_layer_norm_vs_torch(rows, C, dtype, dev):
+    """ops.layer_norm against F.layer_norm in fp32 on the same (rounded) inputs: forward, dx, dgamma, dbeta."""
+    from r3d_b200 import ops
+    g = torch.Generator().manual_seed(rows + C)
+    x = (torch.randn(rows, C, generator=g) * 2 + 0.5).to(dtype)
+    w = (1 + 0.1 * torch.randn(C, generator=g)).to(dtype)
+    b = (0.1 * torch.randn(C, generator=g)).to(dtype)
+    gy = torch.randn(rows, C, generator=g).to(dtype)
+    xr, wr, br = (t.float().clone().requires_grad_(True) for t in (x, w, b))
+    yr = torch.nn.functional.layer_norm(xr, (C,), wr, br, 1e-5)
+    yr.backward(gy.float())
+    xd, wd, bd = (t.detach().clone().to(dev).requires_grad_(True) for t in (x, w, b))
+    y = ops.layer_norm(xd, wd, bd, 1e-5)
+    y.backward(gy.to(dev))
+    tol = 1e-5 if dtype == torch.float32 else 1e-2
+    def close(a, ref, scale_tol):
+        a = a.float().cpu(); ref = ref.float()
+        return (a - ref).abs().max() <= scale_tol * ref.abs().max() + 1e-6
+    assert close(y, yr, tol)
+    assert close(xd.grad, xr.grad, 4 * tol)
+    assert close(wd.grad, wr.grad, 4 * tol)
+    assert close(bd.grad, br.grad, 4 * tol)
+
+
+def test_layer_norm_rejects_cpu_and_bad_width(dev):
+    from r3d_b200 import ops
+    from r3d_b200._lib import R3DError
+    with pytest.raises(R3DError):
+        ops.layer_norm(torch.randn(4, 128), torch.ones(128), torch.zeros(128))
+    with pytest.raises(R3DError):
+        ops.layer_norm(torch.randn(4, 30, device=dev), torch.ones(30, device=dev), torch.zeros(30, device=dev))
