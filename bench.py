@@ -316,7 +316,7 @@ def isolated_stage_numbers(dev_in, dev_g, pk, n=40):
     return res
 
 
-def full_fuser_numbers(dev, dtype, steps=5):
+def full_fuser_numbers(dev, dtype, steps=10):
     """Whole CMFuser forward+backward (token fusion + Block + LN + mean) at the headline shape: this repo's module
     vs the reference's own op sequence (oracle/torch_port.py: full qkv GEMM, 2x2 masked softmax, clone + index_put
     + stack) run eagerly on the same GPU.  Reported as an extra; the Block still uses library GEMMs."""
@@ -332,9 +332,14 @@ def full_fuser_numbers(dev, dtype, steps=5):
     ours.load_state_dict(ref.state_dict())
     ref.embd_drop.p = ours.embd_drop.p = 0.0
 
+    r = buf[0].clone().requires_grad_(True)
+    d = buf[1].clone().requires_grad_(True)
+
     def run(mod):
-        r = buf[0].clone().requires_grad_(True)
-        d = buf[1].clone().requires_grad_(True)
+        r.grad = None
+        d.grad = None
+        for p_ in mod.parameters():
+            p_.grad = None
         y = mod({"rgb": r, "depth": d}, "test")
         y.backward(gy)
         return y

@@ -162,12 +162,19 @@ int r3d_token_informativeness(const float* sigma, const float* U, int64_t B, int
  * x, y, dy, dx: (rows, C) row-major in `dtype`; gamma, beta in the same dtype (nn.LayerNorm keeps its
  * parameters in the module dtype); mean, rstd: (rows) fp32 saved by the forward for the backward.
  * C must be a multiple of 8 (bf16) / 4 (fp32) and at most 2048 (bf16) / 1024 (fp32); tensors 16-byte aligned.
- * r3d_ln_bwd writes dx and dgamma_dbeta = (2, C) fp32 [dgamma | dbeta] (deterministic two-stage reduction). */
+ * r3d_ln_bwd writes dx and dgamma_dbeta = (2, C) fp32 [dgamma | dbeta] (deterministic two-stage reduction).
+ * pair_mean = 1 fuses the mean over the fuser's two modality tokens that follows the final norm
+ * (tokenfusion.py:93-95  x = self.norm(x); x = x.mean(dim=1)): rows come in pairs, y and dy have rows/2 rows,
+ * y[r] = (LN(x[2r]) + LN(x[2r+1])) / 2. */
 size_t r3d_ln_bwd_workspace_floats(int64_t rows, int64_t C);
 int r3d_ln_fwd(const void* x, const void* gamma, const void* beta, int64_t rows, int64_t C, int dtype, float eps,
-               void* y, float* mean, float* rstd, void* stream);
+               int pair_mean, void* y, float* mean, float* rstd, void* stream);
 int r3d_ln_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const void* gamma, int64_t rows,
-               int64_t C, int dtype, void* dx, float* workspace, float* dgamma_dbeta, void* stream);
+               int64_t C, int dtype, int pair_mean, void* dx, float* workspace, float* dgamma_dbeta, void* stream);
+/* Residual add of the closed-form 2-token attention: out[row] = a[row] + b[row ^ 1] (token m receives the projected
+ * V of token 1-m: transformerblock.py:19-36 with the -inf diagonal mask of tokenfusion.py:68-72), which
+ * replaces  x + proj(v.flip(1)).  a == NULL gives the pair-swapped copy (its backward).  rows even. */
+int r3d_swap_add(const void* a, const void* b, int64_t rows, int64_t C, int dtype, void* out, void* stream);
 
 /* ---- host-buffer convenience (what a non-Python caller binds; used for `e2e`) ----
  * All pointers are HOST pointers (pinned for full speed); the call copies in,

@@ -52,10 +52,11 @@ SIGNATURES = {
     "r3d_jacobi_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "r3d_token_informativeness": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_float, c_void_p, c_void_p]),
     "r3d_ln_bwd_workspace_floats": (c_size_t, [c_int64, c_int64]),
-    "r3d_ln_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_float, c_void_p, c_void_p,
+    "r3d_ln_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_float, c_int, c_void_p, c_void_p,
                            c_void_p, c_void_p]),
-    "r3d_ln_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p,
+    "r3d_ln_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p,
                            c_void_p, c_void_p, c_void_p]),
+    "r3d_swap_add": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p]),
     "r3d_token_fusion_host": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_int64, c_void_p,
                                       c_void_p, c_void_p, c_void_p]),
 }

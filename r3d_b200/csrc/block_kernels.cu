@@ -18,7 +18,9 @@ namespace {
 
 constexpr int LN_WARPS = 8;
 
-template <typename T, int V, int NCH>
+// PAIR: the rows come in pairs (the fuser's two modality tokens per (b, t)); y has rows/2 rows and receives the mean
+// of the two normalised tokens (model/futr_safuser_tokenfusion.py:93-95: norm, then mean over the token dimension).
+template <typename T, int V, int NCH, bool PAIR>
 __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(const T* __restrict__ x, const T* __restrict__ gamma,
                                                                const T* __restrict__ beta, int64_t rows, int C,
                                                                float eps, T* __restrict__ y,
@@ -36,50 +38,59 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(const T* __restri
     }
   }
   const float invC = 1.f / float(C);
-  for (int64_t row = int64_t(blockIdx.x) * LN_WARPS + warp; row < rows; row += int64_t(gridDim.x) * LN_WARPS) {
-    float xv[NCH][V];
-    float s = 0.f;
+  const int64_t units = PAIR ? rows / 2 : rows;          // a warp handles one row, or one pair of rows
+  for (int64_t unit = int64_t(blockIdx.x) * LN_WARPS + warp; unit < units; unit += int64_t(gridDim.x) * LN_WARPS) {
+    float acc[NCH][V];
+#pragma unroll
+    for (int h = 0; h < (PAIR ? 2 : 1); ++h) {
+      const int64_t row = PAIR ? 2 * unit + h : unit;
+      float xv[NCH][V];
+      float s = 0.f;
+#pragma unroll
+      for (int k = 0; k < NCH; ++k) {
+        const int col = (lane + 32 * k) * V;
+        if (col < C) load_vec<T, V>(x + row * C + col, xv[k]);
+        else {
+#pragma unroll
+          for (int i = 0; i < V; ++i) xv[k][i] = 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < V; ++i) s += xv[k][i];
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      const float mean = s * invC;
+      float q = 0.f;
+#pragma unroll
+      for (int k = 0; k < NCH; ++k) {
+        const int col = (lane + 32 * k) * V;
+        if (col < C) {
+#pragma unroll
+          for (int i = 0; i < V; ++i) { const float d = xv[k][i] - mean; q = fmaf(d, d, q); }
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+      const float rstd = rsqrtf(q * invC + eps);
+#pragma unroll
+      for (int k = 0; k < NCH; ++k) {
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+          const float o = fmaf((xv[k][i] - mean) * rstd, gm[k][i], bt[k][i]);
+          acc[k][i] = (PAIR && h == 1) ? 0.5f * (acc[k][i] + o) : o;
+        }
+      }
+      if (lane == 0) { mean_out[row] = mean; rstd_out[row] = rstd; }
+    }
 #pragma unroll
     for (int k = 0; k < NCH; ++k) {
       const int col = (lane + 32 * k) * V;
-      if (col < C) load_vec<T, V>(x + row * C + col, xv[k]);
-      else {
-#pragma unroll
-        for (int i = 0; i < V; ++i) xv[k][i] = 0.f;
-      }
-#pragma unroll
-      for (int i = 0; i < V; ++i) s += xv[k][i];
+      if (col < C) store_vec<T, V>(y + unit * C + col, acc[k]);
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    const float mean = s * invC;
-    float q = 0.f;
-#pragma unroll
-    for (int k = 0; k < NCH; ++k) {
-      const int col = (lane + 32 * k) * V;
-      if (col < C) {
-#pragma unroll
-        for (int i = 0; i < V; ++i) { const float d = xv[k][i] - mean; q = fmaf(d, d, q); }
-      }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-    const float rstd = rsqrtf(q * invC + eps);
-#pragma unroll
-    for (int k = 0; k < NCH; ++k) {
-      const int col = (lane + 32 * k) * V;
-      if (col < C) {
-        float o[V];
-#pragma unroll
-        for (int i = 0; i < V; ++i) o[i] = fmaf((xv[k][i] - mean) * rstd, gm[k][i], bt[k][i]);
-        store_vec<T, V>(y + row * C + col, o);
-      }
-    }
-    if (lane == 0) { mean_out[row] = mean; rstd_out[row] = rstd; }
   }
 }
 
-template <typename T, int V, int NCH>
+template <typename T, int V, int NCH, bool PAIR>
 __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x,
                                                                const float* __restrict__ mean_in,
                                                                const float* __restrict__ rstd_in,
@@ -108,9 +119,10 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const T* __restri
       if (col < C) {
         float xv[V], dv[V];
         load_vec<T, V>(x + row * C + col, xv);
-        load_vec<T, V>(dy + row * C + col, dv);
+        load_vec<T, V>(dy + (PAIR ? (row >> 1) : row) * C + col, dv);
 #pragma unroll
         for (int i = 0; i < V; ++i) {
+          if (PAIR) dv[i] *= 0.5f;
           xh[k][i] = (xv[i] - mean) * rstd;
           g[k][i] = dv[i] * gm[k][i];
           s1 += g[k][i];
@@ -185,19 +197,45 @@ __global__ void __launch_bounds__(256) ln_finalize_kernel(const float* __restric
   }
 }
 
+// out[row] = (a ? a[row] : 0) + b[row ^ 1]: the closed-form 2-token attention hands token m the projected V of token
+// 1-m, so the residual add reads its second operand with the two rows of a pair swapped; with a == null
+// it is the backward of that operand (a pair-swapped copy).
+template <typename T, int V>
+__global__ void __launch_bounds__(256) swap_add_kernel(const T* __restrict__ a, const T* __restrict__ b,
+                                                       T* __restrict__ out, int64_t rows, int C) {
+  const int vec_per_row = C / V;
+  const int64_t total = rows * vec_per_row;
+  for (int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; e < total; e += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t row = e / vec_per_row;
+    const int col = int(e % vec_per_row) * V;
+    float bv[V], o[V];
+    load_vec<T, V>(b + (row ^ 1) * C + col, bv);
+    if (a != nullptr) {
+      float av[V];
+      load_vec<T, V>(a + row * C + col, av);
+#pragma unroll
+      for (int i = 0; i < V; ++i) o[i] = av[i] + bv[i];
+    } else {
+#pragma unroll
+      for (int i = 0; i < V; ++i) o[i] = bv[i];
+    }
+    store_vec<T, V>(out + row * C + col, o);
+  }
+}
+
 inline int ln_grid(int64_t rows) {
   const int64_t want = (rows + LN_WARPS - 1) / LN_WARPS;
   return int(std::max<int64_t>(1, std::min<int64_t>(want, int64_t(kNumSMs) * 2)));
 }
 
-template <typename T, int V>
+template <typename T, int V, bool PAIR>
 int ln_fwd_t(const void* x, const void* gamma, const void* beta, int64_t rows, int C, float eps, void* y, float* mean,
              float* rstd, cudaStream_t st) {
   const int nch = (C + 32 * V - 1) / (32 * V);
-  const int grid = ln_grid(rows);
-#define R3D_LN_FWD(N)                                                                                              \
-  ln_fwd_kernel<T, V, N><<<grid, LN_WARPS * 32, 0, st>>>((const T*)x, (const T*)gamma, (const T*)beta, rows, C, eps, \
-                                                         (T*)y, mean, rstd)
+  const int grid = ln_grid(PAIR ? rows / 2 : rows);
+#define R3D_LN_FWD(N)                                                                                         \
+  ln_fwd_kernel<T, V, N, PAIR><<<grid, LN_WARPS * 32, 0, st>>>((const T*)x, (const T*)gamma, (const T*)beta, rows, C, \
+                                                               eps, (T*)y, mean, rstd)
   if (nch <= 1) R3D_LN_FWD(1);
   else if (nch <= 2) R3D_LN_FWD(2);
   else if (nch <= 4) R3D_LN_FWD(4);
@@ -207,14 +245,14 @@ int ln_fwd_t(const void* x, const void* gamma, const void* beta, int64_t rows, i
   return 0;
 }
 
-template <typename T, int V>
+template <typename T, int V, bool PAIR>
 int ln_bwd_t(const void* dy, const void* x, const float* mean, const float* rstd, const void* gamma, int64_t rows, int C,
              void* dx, float* partial, cudaStream_t st) {
   const int nch = (C + 32 * V - 1) / (32 * V);
   const int grid = ln_grid(rows);
 #define R3D_LN_BWD(N)                                                                                             \
-  ln_bwd_kernel<T, V, N><<<grid, LN_WARPS * 32, 0, st>>>((const T*)dy, (const T*)x, mean, rstd, (const T*)gamma, rows, \
-                                                         C, (T*)dx, partial)
+  ln_bwd_kernel<T, V, N, PAIR><<<grid, LN_WARPS * 32, 0, st>>>((const T*)dy, (const T*)x, mean, rstd, (const T*)gamma, \
+                                                               rows, C, (T*)dx, partial)
   if (nch <= 1) R3D_LN_BWD(1);
   else if (nch <= 2) R3D_LN_BWD(2);
   else if (nch <= 4) R3D_LN_BWD(4);
@@ -247,19 +285,23 @@ extern "C" size_t r3d_ln_bwd_workspace_floats(int64_t rows, int64_t C) {
 }
 
 extern "C" int r3d_ln_fwd(const void* x, const void* gamma, const void* beta, int64_t rows, int64_t C, int dtype,
-                          float eps, void* y, float* mean, float* rstd, void* stream) {
+                          float eps, int pair_mean, void* y, float* mean, float* rstd, void* stream) {
   if (int e = ln_check(x, y, rows, C, dtype)) return e;
   R3D_CHECK(gamma && beta && mean && rstd, "null pointer");
+  R3D_CHECK(!pair_mean || rows % 2 == 0, "pair_mean needs an even number of rows");
   if (rows == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   R3D_STAGE(ST_BLOCK, st);
-  return dtype == R3D_F32 ? ln_fwd_t<float, 4>(x, gamma, beta, rows, int(C), eps, y, mean, rstd, st)
-                          : ln_fwd_t<__nv_bfloat16, 8>(x, gamma, beta, rows, int(C), eps, y, mean, rstd, st);
+  if (pair_mean)
+    return dtype == R3D_F32 ? ln_fwd_t<float, 4, true>(x, gamma, beta, rows, int(C), eps, y, mean, rstd, st)
+                            : ln_fwd_t<__nv_bfloat16, 8, true>(x, gamma, beta, rows, int(C), eps, y, mean, rstd, st);
+  return dtype == R3D_F32 ? ln_fwd_t<float, 4, false>(x, gamma, beta, rows, int(C), eps, y, mean, rstd, st)
+                          : ln_fwd_t<__nv_bfloat16, 8, false>(x, gamma, beta, rows, int(C), eps, y, mean, rstd, st);
 }
 
 extern "C" int r3d_ln_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const void* gamma,
-                          int64_t rows, int64_t C, int dtype, void* dx, float* workspace, float* dgamma_dbeta,
-                          void* stream) {
+                          int64_t rows, int64_t C, int dtype, int pair_mean, void* dx, float* workspace,
+                          float* dgamma_dbeta, void* stream) {
   if (int e = ln_check(dy, x, rows, C, dtype)) return e;
   R3D_CHECK(mean && rstd && gamma && dx && workspace && dgamma_dbeta, "null pointer");
   R3D_CHECK((reinterpret_cast<uintptr_t>(dx) & 15) == 0, "dx must be 16-byte aligned");
@@ -269,10 +311,37 @@ extern "C" int r3d_ln_bwd(const void* dy, const void* x, const float* mean, cons
     return 0;
   }
   R3D_STAGE(ST_BLOCK, st);
-  if (int e = (dtype == R3D_F32 ? ln_bwd_t<float, 4>(dy, x, mean, rstd, gamma, rows, int(C), dx, workspace, st)
-                                : ln_bwd_t<__nv_bfloat16, 8>(dy, x, mean, rstd, gamma, rows, int(C), dx, workspace, st)))
-    return e;
+  int e;
+  if (pair_mean)
+    e = dtype == R3D_F32 ? ln_bwd_t<float, 4, true>(dy, x, mean, rstd, gamma, rows, int(C), dx, workspace, st)
+                         : ln_bwd_t<__nv_bfloat16, 8, true>(dy, x, mean, rstd, gamma, rows, int(C), dx, workspace, st);
+  else
+    e = dtype == R3D_F32 ? ln_bwd_t<float, 4, false>(dy, x, mean, rstd, gamma, rows, int(C), dx, workspace, st)
+                         : ln_bwd_t<__nv_bfloat16, 8, false>(dy, x, mean, rstd, gamma, rows, int(C), dx, workspace, st);
+  if (e) return e;
   ln_finalize_kernel<<<dim3((unsigned)((C + 31) / 32), 2), 256, 0, st>>>(workspace, ln_grid(rows), int(C), dgamma_dbeta);
+  R3D_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int r3d_swap_add(const void* a, const void* b, int64_t rows, int64_t C, int dtype, void* out, void* stream) {
+  R3D_CHECK(b && out, "null pointer");
+  R3D_CHECK(rows >= 0 && rows % 2 == 0 && C >= 1, "bad shape (rows must be even)");
+  R3D_CHECK(dtype == R3D_F32 || dtype == R3D_BF16, "bad dtype %d", dtype);
+  const int V = dtype == R3D_F32 ? 4 : 8;
+  R3D_CHECK(C % V == 0, "C=%lld must be a multiple of %d for this dtype", (long long)C, V);
+  R3D_CHECK((reinterpret_cast<uintptr_t>(b) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
+                (reinterpret_cast<uintptr_t>(a) & 15) == 0, "tensors must be 16-byte aligned");
+  if (rows == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t total = rows * (C / V);
+  const int grid = int(std::max<int64_t>(1, std::min<int64_t>((total + 255) / 256, int64_t(kNumSMs) * 16)));
+  R3D_STAGE(ST_BLOCK, st);
+  if (dtype == R3D_F32)
+    swap_add_kernel<float, 4><<<grid, 256, 0, st>>>((const float*)a, (const float*)b, (float*)out, rows, int(C));
+  else
+    swap_add_kernel<__nv_bfloat16, 8><<<grid, 256, 0, st>>>((const __nv_bfloat16*)a, (const __nv_bfloat16*)b,
+                                                            (__nv_bfloat16*)out, rows, int(C));
   R3D_LAUNCH_CHECK();
   return 0;
 }

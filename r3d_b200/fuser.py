@@ -84,7 +84,11 @@ class Block(nn.Module):
         w_v = self.attn.qkv.weight[2 * C:]
         b_v = None if self.attn.qkv.bias is None else self.attn.qkv.bias[2 * C:]
         v = F.linear(h, w_v, b_v)                       # (R, 2, C): only the V third of qkv
-        x = x + self.attn.proj(v.flip(1))               # token m <- V of token 1-m
+        p = self.attn.proj(v)                           # per-token projection commutes with the token swap
+        if p.dtype == x.dtype and ops.swap_add_supported(x):
+            x = ops.swap_add(x, p)                      # token m <- projected V of token 1-m, fused with the residual
+        else:
+            x = x + p.flip(1)
         x = x + self.mlp(_ln(self.norm2, x))
         return x, None
 
@@ -213,7 +217,11 @@ class CMFuser(nn.Module):
             x, _ = blk(x)
         if self.variant == "tokenfusion":
             x = x + x_res                                     # tokenfusion.py:92
-        y = _ln(self.norm, x).mean(dim=1).view(B, T, C)
+        nm = self.norm
+        if nm.elementwise_affine and x.dim() == 3 and x.shape[1] == 2 and ops.layer_norm_supported(x, C):
+            y = ops.layer_norm_mean2(x, nm.weight, nm.bias, nm.eps).view(B, T, C)   # norm + mean over the 2 tokens
+        else:
+            y = _ln(nm, x).mean(dim=1).view(B, T, C)
         if self.variant == "safuser":
             # attention weights are the constant [[0,1],[1,0]]:
             # (B, depth, T, heads, 2, 2) as futr_safuser_depth.py:64 returns

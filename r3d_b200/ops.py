@@ -384,7 +384,7 @@ def layer_norm_supported(x: torch.Tensor, C: int) -> bool:
 
 class _LayerNorm(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, eps):
+    def forward(ctx, x, weight, bias, eps, pair_mean):
         C = x.shape[-1]
         xc = x.contiguous()
         rows = xc.numel() // C
@@ -392,12 +392,16 @@ class _LayerNorm(torch.autograd.Function):
         b = bias.to(xc.dtype).contiguous()
         L = _lib.lib()
         with _on(xc.device):
-            y = torch.empty_like(xc)
+            if pair_mean:
+                y = torch.empty(xc.shape[:-2] + (C,), dtype=xc.dtype, device=xc.device)
+            else:
+                y = torch.empty_like(xc)
             mean = torch.empty(rows, dtype=torch.float32, device=xc.device)
             rstd = torch.empty(rows, dtype=torch.float32, device=xc.device)
-            check(L.r3d_ln_fwd(_p(xc), _p(w), _p(b), rows, C, _dt(xc), float(eps), _p(y), _p(mean), _p(rstd), _stream()))
+            check(L.r3d_ln_fwd(_p(xc), _p(w), _p(b), rows, C, _dt(xc), float(eps), int(pair_mean), _p(y), _p(mean),
+                               _p(rstd), _stream()))
         ctx.save_for_backward(xc, w, mean, rstd)
-        ctx.wdtype, ctx.bdtype = weight.dtype, bias.dtype
+        ctx.wdtype, ctx.bdtype, ctx.pair = weight.dtype, bias.dtype, bool(pair_mean)
         return y
 
     @staticmethod
@@ -411,20 +415,70 @@ class _LayerNorm(torch.autograd.Function):
             dx = torch.empty_like(xc)
             ws = torch.empty(L.r3d_ln_bwd_workspace_floats(rows, C), dtype=torch.float32, device=xc.device)
             dgb = torch.empty(2, C, dtype=torch.float32, device=xc.device)
-            check(L.r3d_ln_bwd(_p(g), _p(xc), _p(mean), _p(rstd), _p(w), rows, C, _dt(xc), _p(dx), _p(ws), _p(dgb),
-                               _stream()))
-        return dx, dgb[0].to(ctx.wdtype), dgb[1].to(ctx.bdtype), None
+            check(L.r3d_ln_bwd(_p(g), _p(xc), _p(mean), _p(rstd), _p(w), rows, C, _dt(xc), int(ctx.pair), _p(dx), _p(ws),
+                               _p(dgb), _stream()))
+        return dx, dgb[0].to(ctx.wdtype), dgb[1].to(ctx.bdtype), None, None
 
 
-def layer_norm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
-    """F.layer_norm(x, (C,), weight, bias, eps) over the last dimension, differentiable in x, weight and bias."""
+def _ln_args(x, weight, bias):
     _need_cuda(x, weight, bias)
     C = x.shape[-1]
     if weight.shape != (C,) or bias.shape != (C,):
         raise R3DError(f"layer_norm: weight/bias must have shape ({C},)")
     if not layer_norm_supported(x, C):
         raise R3DError(f"layer_norm: unsupported dtype/width {x.dtype}, C={C} (see include/r3d_b200.h)")
-    return _LayerNorm.apply(x, weight, bias, eps)
+
+
+def layer_norm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
+    """F.layer_norm(x, (C,), weight, bias, eps) over the last dimension, differentiable in x, weight and bias."""
+    _ln_args(x, weight, bias)
+    return _LayerNorm.apply(x, weight, bias, eps, False)
+
+
+def layer_norm_mean2(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
+    """x (..., 2, C) -> (..., C): F.layer_norm over C followed by the mean over the two tokens, in one kernel
+    (reference: model/futr_safuser_tokenfusion.py:93-95)."""
+    _ln_args(x, weight, bias)
+    if x.dim() < 2 or x.shape[-2] != 2:
+        raise R3DError(f"layer_norm_mean2 expects (..., 2, C), got {tuple(x.shape)}")
+    return _LayerNorm.apply(x, weight, bias, eps, True)
+
+
+class _SwapAdd(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, p):
+        xc, pc = x.contiguous(), p.contiguous()
+        C = xc.shape[-1]
+        rows = xc.numel() // C
+        out = torch.empty_like(xc)
+        with _on(xc.device):
+            check(_lib.lib().r3d_swap_add(_p(xc), _p(pc), rows, C, _dt(xc), _p(out), _stream()))
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        gc = g.contiguous()
+        C = gc.shape[-1]
+        rows = gc.numel() // C
+        dp = torch.empty_like(gc)
+        with _on(gc.device):
+            check(_lib.lib().r3d_swap_add(None, _p(gc), rows, C, _dt(gc), _p(dp), _stream()))
+        return g, dp
+
+
+def swap_add_supported(x: torch.Tensor) -> bool:
+    return x.is_cuda and x.dtype in _DT and x.dim() >= 2 and x.shape[-2] == 2 and \
+        x.shape[-1] % (4 if x.dtype == torch.float32 else 8) == 0
+
+
+def swap_add(x: torch.Tensor, p: torch.Tensor) -> torch.Tensor:
+    """x + p.flip(-2) for (..., 2, C) tensors: the residual add of the closed-form 2-token attention, where token m
+    receives the projected V of token 1-m."""
+    _need_cuda(x, p)
+    if x.shape != p.shape or x.dtype != p.dtype or not swap_add_supported(x):
+        raise R3DError(f"swap_add: expected two (..., 2, C) CUDA tensors of equal shape/dtype, got {tuple(x.shape)} {x.dtype}"
+                       f" and {tuple(p.shape)} {p.dtype}")
+    return _SwapAdd.apply(x, p)
 
 
 def token_informativeness(sigma: torch.Tensor, U: torch.Tensor, rtol: float = DEFAULT_RTOL) -> torch.Tensor:

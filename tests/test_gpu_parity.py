@@ -632,3 +632,44 @@ def test_layer_norm_rejects_cpu_and_bad_width(dev):
         ops.layer_norm(torch.randn(4, 128), torch.ones(128), torch.zeros(128))
     with pytest.raises(R3DError):
         ops.layer_norm(torch.randn(4, 30, device=dev), torch.ones(30, device=dev), torch.zeros(30, device=dev))
+
+
+@pytest.mark.parametrize("R,C,dtype", [(5, 128, torch.float32), (300, 512, torch.float32), (2048, 512, torch.bfloat16),
+                                       (17, 264, torch.bfloat16)])
+def test_layer_norm_mean2_and_swap_add_vs_torch(R, C, dtype, dev):
+    """The two fused Block kernels against their torch definitions (fp32 on the rounded inputs), forward and backward:
+    layer_norm_mean2 = F.layer_norm(x).mean(-2) on (R, 2, C); swap_add = x + p.flip(-2)."""
+    from r3d_b200 import ops
+    g = torch.Generator().manual_seed(R * 3 + C)
+    x = (torch.randn(R, 2, C, generator=g) * 1.5 - 0.3).to(dtype)
+    p = torch.randn(R, 2, C, generator=g).to(dtype)
+    w = (1 + 0.1 * torch.randn(C, generator=g)).to(dtype)
+    b = (0.1 * torch.randn(C, generator=g)).to(dtype)
+    gy = torch.randn(R, C, generator=g).to(dtype)
+    gs = torch.randn(R, 2, C, generator=g).to(dtype)
+    tol = 1e-5 if dtype == torch.float32 else 1e-2
+
+    def close(a, ref, t):
+        a = a.float().cpu(); ref = ref.float()
+        return (a - ref).abs().max() <= t * ref.abs().max() + 1e-6
+
+    xr, wr, br = (t.float().clone().requires_grad_(True) for t in (x, w, b))
+    yr = torch.nn.functional.layer_norm(xr, (C,), wr, br, 1e-5).mean(dim=-2)
+    yr.backward(gy.float())
+    xd, wd, bd = (t.detach().clone().to(dev).requires_grad_(True) for t in (x, w, b))
+    y = ops.layer_norm_mean2(xd, wd, bd, 1e-5)
+    y.backward(gy.to(dev))
+    assert y.shape == (R, C)
+    assert close(y, yr, tol) and close(xd.grad, xr.grad, 4 * tol)
+    assert close(wd.grad, wr.grad, 4 * tol) and close(bd.grad, br.grad, 4 * tol)
+
+    x2, p2 = (t.float().clone().requires_grad_(True) for t in (x, p))
+    sr = x2 + p2.flip(-2)
+    sr.backward(gs.float())
+    x3, p3 = (t.detach().clone().to(dev).requires_grad_(True) for t in (x, p))
+    s = ops.swap_add(x3, p3)
+    s.backward(gs.to(dev))
+    if dtype == torch.float32:
+        assert torch.equal(s.cpu(), sr.detach()) and torch.equal(x3.grad.cpu(), x2.grad) and torch.equal(p3.grad.cpu(), p2.grad)
+    else:
+        assert close(s, sr, tol) and torch.equal(x3.grad.float().cpu(), x2.grad) and torch.equal(p3.grad.float().cpu(), p2.grad)
