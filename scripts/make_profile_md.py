@@ -53,7 +53,9 @@ tab = [f"Captured window: {n} launches, {tot / 1e3:.2f} ms of kernel time under 
        "| kernel | launches | total ms | share | avg us |", "|---|---:|---:|---:|---:|"]
 for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     tab.append(f"| `{k[:90]}` | {v[0]} | {v[1] / 1e3:.3f} | {100 * v[1] / tot:.1f}% | {v[1] / v[0]:.1f} |")
-open(P + "r01_launch_table.md", "w").write("\n".join(tab) + "\n")
+summ = open(P + "r01_ncu_summary.md").read()          # splice the table into the hand-written summary
+a, b = summ.index("Captured window:"), summ.index("The window starts")
+open(P + "r01_ncu_summary.md", "w").write(summ[:a] + "\n".join(tab) + "\n\n" + summ[b:])
 d = json.load(open(P + "r01_bench_n1.json"))
 st, t = d["stages"], d["ms_per_step_with_stage_events"]
 print("\n".join(tab))
