@@ -1,4 +1,5 @@
-"""Two-pass solver: first-pass threshold vs accuracy (fp32 gradient error vs float64) -- time comes from bench.py --opt."""
+"""Two-pass solver: first-pass significance floor and second-pass sweep cap vs accuracy (fp32 erank and gradient
+error against the float64 oracle); the matching step times come from `bench.py --opt key=value`."""
 import sys, numpy as np, torch
 sys.path.insert(0, '.')
 from r3d_b200 import _lib, ops
@@ -13,8 +14,8 @@ def spectra(kind, B, T, C, seed):
         return (rng.standard_normal((B, T, r)) @ rng.standard_normal((B, r, C))).astype(np.float32)
     if kind == "decay": return (rng.standard_normal((B, T, C)) * np.exp(-np.arange(C) / (C / 8))).astype(np.float32)
 cases = [("gauss", 1, 512, 512), ("relu", 1, 512, 512), ("gauss", 2, 128, 128), ("decay", 2, 256, 512), ("relu", 2, 256, 512), ("decay", 1, 512, 512), ("rankdef", 1, 512, 512)]
-for tol1, cap in ((0, 6), (8, 6), (64, 6), (512, 6), (4096, 6), (32768, 6)):
-    _lib.set_option("erank_passes", 2); _lib.set_option("jacobi_stop_count_pass1", tol1); _lib.set_option("erank_pass2_sweeps", cap)
+for tol1, cap in ((2048, 6), (2048, 3), (2048, 2), (512, 2), (4096, 2)):
+    _lib.set_option("erank_passes", 2); _lib.set_option("jacobi_nu_pass1", tol1); _lib.set_option("erank_pass2_sweeps", cap)
     out = []
     for kind, B, T, C in cases:
         x = spectra(kind, B, T, C, T * 1000 + C)
@@ -25,4 +26,4 @@ for tol1, cap in ((0, 6), (8, 6), (64, 6), (512, 6), (4096, 6), (32768, 6)):
         e1 = np.abs(er.detach().cpu().numpy() - ref).max() / ref.max()
         e2 = np.abs(xt.grad.cpu().numpy() - gref).max() / np.abs(gref).max()
         out.append(f"{kind}{T}x{C}: er {e1:.1e} grad {e2:.1e} sw {int(sw.max())}")
-    print(f"stop_count={tol1:g} cap={cap} | " + " | ".join(out), flush=True)
+    print(f"nu_pass1={tol1:g} cap={cap} | " + " | ".join(out), flush=True)
