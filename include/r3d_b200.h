@@ -40,14 +40,14 @@ int64_t r3d_launch_count(int reset);
  * default).  r3d_profile_read synchronises the recorded events and returns, per
  * stage, accumulated milliseconds, bracketed calls and kernel launches. */
 /* Thread-local tuning knobs: "jacobi_update_tc" (1 = tcgen05 3xTF32 panel update, default;
- * 0 = SIMT fp32), "jacobi_tol" (relative off-diagonal threshold, default 1e-5),
+ * 0 = SIMT fp32), "jacobi_tol" (relative rotation threshold, default 1e-6),
  * "jacobi_max_sweeps" (default 16, at most 32), "jacobi_overlap_v" (1 = run the eigenvector update on a
  * library-owned side stream overlapped with the next inner solve, default),
  * "erank_passes" (2 default: after the first Jacobi pass a second one runs on G2 = Y Y^T, which is graded and
  * nearly diagonal, and updates U and Y -- relative accuracy for the smallest singular directions, gradients
  * within 1e-4 of float64 on square samples; 1 = single pass, 13 % faster, gradients 2e-4 .. 1e-2),
  * "erank_pass2_sweeps" (sweep cap of that second pass, default 6), "jacobi_tol_pass1" (first-pass threshold when
- * a second pass follows, default 1e-5), "jacobi_nu_pass1" (first-pass absolute significance floor in units of
+ * a second pass follows, default 1e-6), "jacobi_nu_pass1" (first-pass absolute significance floor in units of
  * 2^-23 max|diag|, default 2048: the first pass stops early and the second pass finishes the job),
  * "gemm_tc" (1 = refinement/backward/fp32-Gram GEMMs on tcgen05 through bf16 planes, default; 0 = SIMT),
  * "jacobi_chunks" (default 1; 2 = split a large

@@ -23,11 +23,12 @@ int panel_tc_update_v(PanelTc* h, int qbuf, int round, int sweep, const int* cnt
 
 struct Options {
   int jacobi_update_tc = 1;     // 1: tcgen05 3xTF32 panel update, 0: SIMT fp32 tile update
-  float jacobi_tol = 1e-5f;     // relative off-diagonal threshold
+  float jacobi_tol = 1e-6f;     // relative rotation threshold |s_pq| > tol sqrt(s_pp s_qq) (1e-5 costs 0.3 ms less per step and
+                                // ~10x in gradient accuracy: 8e-5 vs 8e-6 on square samples)
   int jacobi_max_sweeps = 16;
   int jacobi_chunks = 1;        // 2: run two half-batches on two streams (measured slower at the headline shape: 69.8 vs 65.9 ms)
-  float jacobi_tol_pass1 = 1e-5f; // first-pass threshold when a second pass follows (looser values measured slower:
-                                  // 1e-4 -> 70.4 ms, 1e-3 -> 73.7 ms vs 69.2 ms; the second pass then needs more sweeps)
+  float jacobi_tol_pass1 = 1e-6f; // first-pass relative threshold when a second pass follows (looser values are slower:
+                                  // 1e-4 -> 56.7 ms, 1e-3 -> 59.5 ms vs 55.3 ms at 1e-5, measured before the raised floor)
   float jacobi_nu_pass1 = 2048.f; // first pass of the two-pass solver: absolute significance floor in units of 2^-23 max|diag|
                                   // (single-pass solver and second pass: 4).  The second pass removes what the first leaves,
                                   // so the first may stop ~2.5 sweeps earlier: 4 -> 55.1 ms, 1024 -> 50.7, 4096 -> 48.8 with

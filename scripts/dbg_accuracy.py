@@ -11,7 +11,7 @@ def spectra(kind, B, T, C, seed):
     if kind == "decay": return (rng.standard_normal((B, T, C)) * np.exp(-np.arange(C) / (C / 8))).astype(np.float32)
 cases = [("gauss", 1, 512, 512), ("relu", 1, 512, 512), ("gauss", 2, 128, 128), ("relu", 2, 128, 128), ("decay", 2, 256, 512), ("relu", 2, 256, 512)]
 for passes in (1, 2):
-    for tol in (1e-5,):
+    for tol in (1e-6,):        # the library default
         tc = 1
         _lib.set_option("erank_passes", passes); _lib.set_option("jacobi_tol", tol); _lib.set_option("jacobi_max_sweeps", 24)
         out = []
