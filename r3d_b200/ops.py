@@ -605,7 +605,7 @@ class FuserStep:
         check(L.r3d_channel_score_partial(rgb_p, dep_p, rows, C, dt, _p(self.ws_score), st))
         check(L.r3d_score_finalize(_p(self.ws_score), rows, C, _p(self.packed), None, st))
         self.packed[2 * C] = self.er.sum()
-        self.packed[2 * C + 1] = float(rows)
+        self.packed[2 * C + 1:2 * C + 2].fill_(float(rows))      # device-side fill (no host copy: graph-capturable)
         if self.world > 1:
             torch.distributed.all_reduce(self.packed, group=self.group)
         torch.div(self.packed[:2 * C].view(2, C), self.packed[2 * C + 1], out=self.score)

@@ -673,3 +673,40 @@ def test_layer_norm_mean2_and_swap_add_vs_torch(R, C, dtype, dev):
         assert torch.equal(s.cpu(), sr.detach()) and torch.equal(x3.grad.cpu(), x2.grad) and torch.equal(p3.grad.cpu(), p2.grad)
     else:
         assert close(s, sr, tol) and torch.equal(x3.grad.float().cpu(), x2.grad) and torch.equal(p3.grad.float().cpu(), p2.grad)
+
+
+def test_fuser_step_cuda_graph_capture(dev):
+    """The fused step makes ~1000 launches on two streams with device-side convergence control and no host
+    synchronisation, so it must be capturable in a CUDA graph and replay bit-identically."""
+    from r3d_b200 import ops
+    B, T, C = 2, 128, 256
+    rgb, dep = synth(B, T, C, 13, torch.bfloat16)
+    buf = torch.stack([rgb, dep]).to(dev).contiguous()
+    g = torch.randn(B, T, 2, C, generator=torch.Generator().manual_seed(2)).to(torch.bfloat16).to(dev)
+    step = ops.FuserStep(B, T, C, torch.bfloat16, dev)
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for _ in range(2):
+            step(buf, g)
+    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+    ref = (step.out.clone(), step.er.clone(), step.dgrad.clone(), step.idx.clone())
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        step(buf, g)
+    for t in (step.out, step.er, step.dgrad):
+        t.zero_()
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(step.out, ref[0]) and torch.equal(step.er, ref[1]) and torch.equal(step.dgrad, ref[2])
+    assert torch.equal(step.idx, ref[3])
+    # new inputs through the same graph: the static buffers are simply overwritten
+    rgb2, dep2 = synth(B, T, C, 14, torch.bfloat16)
+    buf.copy_(torch.stack([rgb2, dep2]).to(dev))
+    graph.replay()
+    torch.cuda.synchronize()
+    er_graph = step.er.clone()
+    step(buf, g)
+    torch.cuda.synchronize()
+    assert torch.equal(step.er, er_graph)
