@@ -39,19 +39,27 @@ int64_t r3d_launch_count(int reset);
 /* Per-stage timing with CUDA events recorded on the launching stream (off by
  * default).  r3d_profile_read synchronises the recorded events and returns, per
  * stage, accumulated milliseconds, bracketed calls and kernel launches. */
-/* Thread-local tuning knobs: "jacobi_update_tc" (1 = tcgen05 3xTF32 panel update, default;
- * 0 = SIMT fp32), "jacobi_tol" (relative rotation threshold, default 1e-6),
- * "jacobi_max_sweeps" (default 16, at most 32), "jacobi_overlap_v" (1 = run the eigenvector update on a
- * library-owned side stream overlapped with the next inner solve, default),
- * "erank_passes" (2 default: after the first Jacobi pass a second one runs on G2 = Y Y^T, which is graded and
- * nearly diagonal, and updates U and Y -- relative accuracy for the smallest singular directions, gradients
- * within 1e-4 of float64 on square samples; 1 = single pass, 13 % faster, gradients 2e-4 .. 1e-2),
- * "erank_pass2_sweeps" (sweep cap of that second pass, default 6), "jacobi_tol_pass1" (first-pass threshold when
- * a second pass follows, default 1e-6), "jacobi_nu_pass1" (first-pass absolute significance floor in units of
- * 2^-23 max|diag|, default 2048: the first pass stops early and the second pass finishes the job),
- * "gemm_tc" (1 = refinement/backward/fp32-Gram GEMMs on tcgen05 through bf16 planes, default; 0 = SIMT),
- * "jacobi_chunks" (default 1; 2 = split a large
- * batch into two halves on two streams so that one half's inner solve overlaps the other's panel passes). */
+/* Thread-local tuning knobs (unknown keys are an error).  Solver:
+ *   "erank_passes"        2 (default): after the first Jacobi pass a second one runs on G2 = Y Y^T, which is graded
+ *                         and nearly diagonal, and updates U and Y -- gradients within 1e-4 of float64 on square
+ *                         samples; 1 = single pass (erank unchanged, gradients 1e-3 .. 5e-2 on square samples)
+ *   "jacobi_tol"          relative rotation threshold |s_pq| > tol sqrt(s_pp s_qq), default 1e-6
+ *   "jacobi_tol_pass1"    the same for the first pass of the two-pass solver, default 1e-6
+ *   "jacobi_nu_pass1"     first-pass absolute significance floor in units of 2^-23 max|diag|, default 2048 (the first
+ *                         pass stops early, the second finishes; single-pass solver and second pass use 4)
+ *   "jacobi_max_sweeps"   sweep cap, default 16, at most 32; "erank_pass1_sweeps" (12) / "erank_pass2_sweeps" (6)
+ *                         are the caps of the two passes
+ * Kernel selection (defaults are the fast paths; the alternatives exist for A/B measurements and as fallbacks):
+ *   "jacobi_update_tc"    1 = tcgen05 3xTF32 panel update, 0 = SIMT fp32 tile update
+ *   "jacobi_inner_regs"   1 = register-resident inner solver for the cross rounds, 0 = shared-memory solver
+ *   "gemm_tc"             1 = refinement / backward / fp32-Gram GEMMs on tcgen05 through bf16 planes, 0 = SIMT
+ *   "jacobi_overlap_v"    1 = eigenvector update on a library-owned side stream; "jacobi_v_after_g" 0 = it starts
+ *                         right after the inner solve (default), 1 = after the G passes of the round
+ *   "jacobi_chunks"       1 (default); 2 = two half-batches on two streams (measured slower)
+ *   "panel_merged"        0 (default); 1 = both G passes in one launch with H in an L2-resident ring, sized by
+ *                         "panel_group_mb" (8) and "panel_ring" (6) (less DRAM traffic, measured slower)
+ *   "row_chunk_mult"      row chunks per SM of the column-reduction kernels, default 4
+ *   "panel_debug", "panel_grid_cap"   test / timing hooks of the panel kernel */
 int r3d_set_option(const char* key, double value);
 /* Test hook: one tensor-core panel-update round (G <- Q^T G Q via H, V <- V Q) on caller buffers. */
 int r3d_debug_panel_round(float* G, float* H, float* V, const float* Qb, int64_t B, int np, int round,
