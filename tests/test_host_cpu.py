@@ -210,3 +210,27 @@ def test_bench_ours_refuses_without_gpu():
                          capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert out.returncode != 0
     assert "CUDA" in (out.stderr + out.stdout)
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """The drop-in boundary is a C ABI: include/r3d_b200.h must compile as C99 (no C++ or torch types) and a C program
+    must link against the shared library and call it (no compute: there is no GPU here)."""
+    import shutil, subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "abi.c"
+    src.write_text('#include "r3d_b200.h"\n#include <stdio.h>\n'
+                   'int main(void) {\n'
+                   '  if (r3d_abi_version() < 1) return 1;\n'
+                   '  /* a NULL-pointer call must fail cleanly with a message, not crash */\n'
+                   '  if (r3d_bottomk(NULL, 1, 8, 2, NULL, NULL) == 0) return 2;\n'
+                   '  const char* e = r3d_last_error();\n'
+                   '  if (!e || !e[0]) return 3;\n'
+                   '  printf("%s\\n", e);\n  return 0;\n}\n')
+    libdir = os.path.join(ROOT, "r3d_b200", "csrc")
+    exe = tmp_path / "abi"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    str(src), "-o", str(exe), "-L", libdir, "-lr3d_b200", f"-Wl,-rpath,{libdir}"], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
+    assert "null" in out.stdout.lower()
