@@ -64,6 +64,11 @@ int r3d_set_option(const char* key, double value);
 /* Test hook: one tensor-core panel-update round (G <- Q^T G Q via H, V <- V Q) on caller buffers. */
 int r3d_debug_panel_round(float* G, float* H, float* V, const float* Qb, int64_t B, int np, int round,
                           int* scratch, void* stream);
+/* Measurement hook: panel tiles (128 rows x 64 columns: 32 KB read + 32 KB written) the Jacobi panel kernel has
+ * actually processed on the current device since the last reset -- out2[0] G passes, out2[1] V passes.  The
+ * launch sequence is fixed and launches after convergence exit at once, so algorithmic bytes per timed region are
+ * tiles x 65536, not launches x (one full pass).  Synchronises the device. */
+int r3d_panel_tiles(uint64_t* out2, int reset);
 int r3d_profile_enable(int on);
 int r3d_profile_num_stages(void);
 const char* r3d_profile_stage_name(int stage);

@@ -1012,6 +1012,14 @@ extern "C" int r3d_debug_panel_round(float* G, float* H, float* V, const float* 
   return panel_tc_update_g(&ptc, 0, round, 0, cnt, qflag, st);
 }
 
+extern "C" int r3d_panel_tiles(uint64_t* out2, int reset) {
+  R3D_CHECK(out2 != nullptr, "null pointer");
+  unsigned long long v[2];
+  if (int e = panel_tiles_read(v, reset)) return e;
+  out2[0] = v[0]; out2[1] = v[1];
+  return 0;
+}
+
 extern "C" int r3d_set_option(const char* key, double value) {
   R3D_CHECK(key != nullptr, "null option key");
   const std::string k(key);

@@ -133,6 +133,11 @@ __device__ __forceinline__ void rr_pair_tc(int m, int r, int t, int& a, int& b) 
   a = min(x, y); b = max(x, y);
 }
 
+// tiles actually processed (not skipped) since the last reset: [0] G passes, [1] in-place V passes -- lets bench.py
+// divide the ALGORITHMIC bytes of the timed region (tiles x 64 KB) by its time instead of assuming that every launch
+// of the fixed launch sequence did a full pass (launches after convergence exit at once)
+__device__ unsigned long long g_panel_tiles[2];
+
 struct PanelJob {
   // job 0 and job 1 may run in the same launch
   float* out0; float* out1;
@@ -293,6 +298,7 @@ __global__ void __maxnreg__(72) panel_update_tc_kernel(const __grid_constant__ C
         tma_2d(st + 2 * A_RAW + PM * 128, &map_q, &raw_full[s], 32, qrow);
         ++it;
       }
+      if (it > 0) atomicAdd(&g_panel_tiles[pj.skip_on_qflag0 ? 1 : 0], (unsigned long long)it);
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
@@ -518,6 +524,15 @@ int panel_tc_prepare(PanelTc* h, float* G, float* H, float* V, const float* Qb0,
   static bool attr_done[kMaxDevices] = {};
   if (per_device_once(attr_done)) {
     R3D_CUDA(cudaFuncSetAttribute(panel_update_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+  }
+  return 0;
+}
+
+int panel_tiles_read(unsigned long long out[2], int reset) {
+  R3D_CUDA(cudaMemcpyFromSymbol(out, g_panel_tiles, sizeof(unsigned long long) * 2));
+  if (reset) {
+    const unsigned long long z[2] = {0, 0};
+    R3D_CUDA(cudaMemcpyToSymbol(g_panel_tiles, z, sizeof(z)));
   }
   return 0;
 }

@@ -21,6 +21,9 @@ int panel_tc_update_g(PanelTc* h, int qbuf, int round, int sweep, const int* cnt
 // V <- V Q for one round (one launch on `st`); independent of the G update and of the next inner solve.
 int panel_tc_update_v(PanelTc* h, int qbuf, int round, int sweep, const int* cnt, const int* qflag, cudaStream_t st);
 
+// Panel tiles (128 rows x 64 columns, 32 KB in + 32 KB out) processed since the last reset: [0] G passes, [1] V passes.
+int panel_tiles_read(unsigned long long out[2], int reset);
+
 struct Options {
   int jacobi_update_tc = 1;     // 1: tcgen05 3xTF32 panel update, 0: SIMT fp32 tile update
   float jacobi_tol = 1e-6f;     // relative rotation threshold |s_pq| > tol sqrt(s_pp s_qq) (1e-5 costs 0.3 ms less per step and
