@@ -36,10 +36,14 @@ namespace {
 constexpr int PB = 32;                 // Jacobi block width (must equal JB in erank_kernels.cu)
 constexpr int PM = 64;                 // panel width = 2 blocks
 constexpr int TM = 128;                // rows per tile
-constexpr int NSTAGE = 1;             // one stage per CTA, two CTAs per SM (24 warps) overlap each other
-constexpr int A_RAW = TM * PM * 4;     // 32 KB: panel tile, hi part after the split (in place)
-constexpr int Q_RAW = PM * PM * 4;     // 16 KB
-constexpr int STAGE = 2 * A_RAW + 2 * Q_RAW;        // hi + lo of both operands: 96 KB
+// A pipeline stage holds ONE 32-column K slab of a tile (block I or block J of the pair): the tile's two slabs go
+// through a 2-stage ring, so the TMA of the next slab runs while this one is split and multiplied, and a stage is
+// held for half as long as when a stage was a whole tile (same 96 KB per CTA, two CTAs per SM).
+constexpr int NSTAGE = 2;
+constexpr int SLABS = 2;               // K slabs per tile
+constexpr int A_RAW = TM * PB * 4;     // 16 KB: one slab of the panel tile, hi part after the split (in place)
+constexpr int Q_RAW = PM * PB * 4;     // 8 KB: the matching 32 k-columns of Q^T
+constexpr int STAGE = 2 * A_RAW + 2 * Q_RAW;        // hi + lo of both operands: 48 KB
 constexpr int STG_WARP = kStgWarpBytes;              // 2560 B of store staging per epilogue warp (tc_store.cuh)
 constexpr int SMEM_TOTAL = NSTAGE * STAGE + 4 * STG_WARP + 1024 + 256;
 constexpr int TMEM_COLS_P = 128;       // 2 accumulator stages x 64 fp32 columns
@@ -271,14 +275,10 @@ __global__ void __maxnreg__(72) panel_update_tc_kernel(const __grid_constant__ C
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (elect()) {
-      int it = 0;
+      int it = 0, ntiles = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const TileInfo ti = decode_tile(tile, njobs, B, nt, mtiles, sweep, cnt, qflag, pj);
         if (!ti.run) continue;
-        const int s = it % NSTAGE;
-        const uint32_t ph = (it / NSTAGE) & 1;
-        bar_wait(&smem_empty[s], ph ^ 1);
-        uint8_t* st = smem + s * STAGE;
         int I, J;
         rr_pair_tc(nb, round, ti.c, I, J);
         if (pj.merged && ti.job == 1) {
@@ -286,57 +286,64 @@ __global__ void __maxnreg__(72) panel_update_tc_kernel(const __grid_constant__ C
           spin_until(&pj.done1[ti.group], group_target(pj, ti.group, B, nt, mtiles), pj.err);
           asm volatile("fence.proxy.async;" ::: "memory");
         }
-        bar_expect_tx(&raw_full[s], A_RAW + Q_RAW);
         const CUtensorMap* mp = ti.job == 0 ? &map_in0 : &map_in1;
         const int mb = (pj.merged && ti.job == 1) ? ti.hb : ti.b;
-        // panel tile: rows [mt*128, +128), column blocks I and J (32 floats = 128 B each)
-        tma_3d(st, mp, &raw_full[s], 0, ti.mt * TM, mb * nb + I);      // 16 KB contiguous in HBM
-        tma_3d(st + TM * 128, mp, &raw_full[s], 0, ti.mt * TM, mb * nb + J);
-        // Q_c^T: 64 rows (j) x two 32-column halves of k
         const int qrow = (ti.b * nt + ti.c) * PM;
-        tma_2d(st + 2 * A_RAW, &map_q, &raw_full[s], 0, qrow);
-        tma_2d(st + 2 * A_RAW + PM * 128, &map_q, &raw_full[s], 32, qrow);
-        ++it;
+#pragma unroll
+        for (int slab = 0; slab < SLABS; ++slab, ++it) {
+          const int s = it % NSTAGE;
+          const uint32_t ph = (it / NSTAGE) & 1;
+          bar_wait(&smem_empty[s], ph ^ 1);
+          uint8_t* st = smem + s * STAGE;
+          bar_expect_tx(&raw_full[s], A_RAW + Q_RAW);
+          // panel slab: rows [mt*128, +128) of column block I (slab 0) or J (slab 1): 16 KB contiguous in HBM
+          tma_3d(st, mp, &raw_full[s], 0, ti.mt * TM, mb * nb + (slab == 0 ? I : J));
+          // Q_c^T: 64 rows (j) x the 32 k-columns of this slab
+          tma_2d(st + 2 * A_RAW, &map_q, &raw_full[s], slab * PB, qrow);
+        }
+        ++ntiles;
       }
-      if (it > 0) atomicAdd(&g_panel_tiles[pj.skip_on_qflag0 ? 1 : 0], (unsigned long long)it);
+      if (ntiles > 0) atomicAdd(&g_panel_tiles[pj.skip_on_qflag0 ? 1 : 0], (unsigned long long)ntiles);
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (elect()) {
-      int it = 0;
+      int it = 0, tt = 0;                              // stage counter (slabs), tile counter (accumulators)
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const TileInfo ti = decode_tile(tile, njobs, B, nt, mtiles, sweep, cnt, qflag, pj);
         if (!ti.run) continue;
-        const int s = it % NSTAGE;
-        const uint32_t ph = (it / NSTAGE) & 1;
-        const int acc = it & 1;
-        const uint32_t aph = (it >> 1) & 1;
+        const int acc = tt & 1;
+        const uint32_t aph = (tt >> 1) & 1;
         bar_wait(&tmem_empty[acc], aph ^ 1);           // epilogue has drained this accumulator
-        bar_wait(&split_done[s], ph);                  // hi/lo operands are in shared memory
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t a_hi = s_u32(smem + s * STAGE), a_lo = a_hi + A_RAW;
-        const uint32_t q_hi = a_hi + 2 * A_RAW, q_lo = q_hi + Q_RAW;
         const uint32_t d = tmem_base + acc * PM;
         uint32_t first = 0;
 #pragma unroll
-        for (int prod = 0; prod < 3; ++prod) {
-          if ((debug & 1) && prod > 0) break;
-          if (debug & 16) break;                      // timing experiment: no MMAs at all
-          const uint32_t ab = (prod == 2) ? a_lo : a_hi;
-          const uint32_t qb = (prod == 1) ? q_lo : q_hi;
+        for (int slab = 0; slab < SLABS; ++slab, ++it) {
+          const int s = it % NSTAGE;
+          const uint32_t ph = (it / NSTAGE) & 1;
+          bar_wait(&split_done[s], ph);                // hi/lo operands of this K slab are in shared memory
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t a_hi = s_u32(smem + s * STAGE), a_lo = a_hi + A_RAW;
+          const uint32_t q_hi = a_hi + 2 * A_RAW, q_lo = q_hi + Q_RAW;
 #pragma unroll
-          for (int kk = 0; kk < PM / 8; ++kk) {
-            // A: K-major; 32-column half kk/4, 32 B (8 tf32) per step inside the 128 B swizzle row
-            const uint64_t ad = desc_sw128(ab + (kk / 4) * (TM * 128) + (kk % 4) * 32, 16, 1024);
-            // B (Q^T): K-major, rows = j (64), same half/step addressing as A
-            const uint64_t bd = desc_sw128(qb + (kk / 4) * (PM * 128) + (kk % 4) * 32, 16, 1024);
-            umma_tf32(d, ad, bd, first);
-            first = 1;
+          for (int prod = 0; prod < 3; ++prod) {
+            if ((debug & 1) && prod > 0) break;
+            if (debug & 16) break;                    // timing experiment: no MMAs at all
+            const uint32_t ab = (prod == 2) ? a_lo : a_hi;
+            const uint32_t qb = (prod == 1) ? q_lo : q_hi;
+#pragma unroll
+            for (int kk = 0; kk < PB / 8; ++kk) {
+              // both operands K-major: 32 B (8 tf32) per step inside the 128 B swizzle row of the slab
+              const uint64_t ad = desc_sw128(ab + kk * 32, 16, 1024);
+              const uint64_t bd = desc_sw128(qb + kk * 32, 16, 1024);
+              umma_tf32(d, ad, bd, first);
+              first = 1;
+            }
           }
+          umma_commit_to(&smem_empty[s]);
         }
-        umma_commit_to(&smem_empty[s]);
         umma_commit_to(&tmem_full[acc]);
-        ++it;
+        ++tt;
       }
     }
   } else if (warp >= 2 && warp < 6) {
@@ -346,39 +353,41 @@ __global__ void __maxnreg__(72) panel_update_tc_kernel(const __grid_constant__ C
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const TileInfo ti = decode_tile(tile, njobs, B, nt, mtiles, sweep, cnt, qflag, pj);
       if (!ti.run) continue;
-      const int s = it % NSTAGE;
-      const uint32_t ph = (it / NSTAGE) & 1;
-      bar_wait(&raw_full[s], ph);
-      uint8_t* st = smem + s * STAGE;
-      float4* a_hi = reinterpret_cast<float4*>(st);
-      float4* a_lo = reinterpret_cast<float4*>(st + A_RAW);
-      float4* q_hi = reinterpret_cast<float4*>(st + 2 * A_RAW);
-      float4* q_lo = reinterpret_cast<float4*>(st + 2 * A_RAW + Q_RAW);
-      if (!(debug & 4)) {
+#pragma unroll 1
+      for (int slab = 0; slab < SLABS; ++slab, ++it) {
+        const int s = it % NSTAGE;
+        const uint32_t ph = (it / NSTAGE) & 1;
+        bar_wait(&raw_full[s], ph);
+        uint8_t* st = smem + s * STAGE;
+        float4* a_hi = reinterpret_cast<float4*>(st);
+        float4* a_lo = reinterpret_cast<float4*>(st + A_RAW);
+        float4* q_hi = reinterpret_cast<float4*>(st + 2 * A_RAW);
+        float4* q_lo = reinterpret_cast<float4*>(st + 2 * A_RAW + Q_RAW);
+        if (!(debug & 4)) {
 #pragma unroll 4
-      for (int e = t; e < A_RAW / 16; e += 128) {
-        const float4 x = a_hi[e];
-        float4 h, l;
-        h.x = tf32_rn(x.x); l.x = x.x - h.x;
-        h.y = tf32_rn(x.y); l.y = x.y - h.y;
-        h.z = tf32_rn(x.z); l.z = x.z - h.z;
-        h.w = tf32_rn(x.w); l.w = x.w - h.w;
-        a_hi[e] = h; a_lo[e] = l;
-      }
+          for (int e = t; e < A_RAW / 16; e += 128) {
+            const float4 x = a_hi[e];
+            float4 h, l;
+            h.x = tf32_rn(x.x); l.x = x.x - h.x;
+            h.y = tf32_rn(x.y); l.y = x.y - h.y;
+            h.z = tf32_rn(x.z); l.z = x.z - h.z;
+            h.w = tf32_rn(x.w); l.w = x.w - h.w;
+            a_hi[e] = h; a_lo[e] = l;
+          }
 #pragma unroll 4
-      for (int e = t; e < Q_RAW / 16; e += 128) {
-        const float4 x = q_hi[e];
-        float4 h, l;
-        h.x = tf32_rn(x.x); l.x = x.x - h.x;
-        h.y = tf32_rn(x.y); l.y = x.y - h.y;
-        h.z = tf32_rn(x.z); l.z = x.z - h.z;
-        h.w = tf32_rn(x.w); l.w = x.w - h.w;
-        q_hi[e] = h; q_lo[e] = l;
+          for (int e = t; e < Q_RAW / 16; e += 128) {
+            const float4 x = q_hi[e];
+            float4 h, l;
+            h.x = tf32_rn(x.x); l.x = x.x - h.x;
+            h.y = tf32_rn(x.y); l.y = x.y - h.y;
+            h.z = tf32_rn(x.z); l.z = x.z - h.z;
+            h.w = tf32_rn(x.w); l.w = x.w - h.w;
+            q_hi[e] = h; q_lo[e] = l;
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to UMMA
+        bar_arrive(&split_done[s]);
       }
-      }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to UMMA
-      bar_arrive(&split_done[s]);
-      ++it;
     }
   } else if (warp >= 6) {
     // ===================== epilogue: TMEM -> global =====================
@@ -423,8 +432,7 @@ __global__ void __maxnreg__(72) panel_update_tc_kernel(const __grid_constant__ C
         const int cblk = (half == 0 ? I : J);
         if (debug & 2) {
           // dump the staged panel tile as the async proxy left it (after the split): element (row r, k = half*32 + j)
-          const int sidx = it % NSTAGE;
-          const uint8_t* abase = smem + sidx * STAGE + half * (TM * 128);
+          const uint8_t* abase = smem + half * STAGE;      // slab `half` of this tile sits in stage `half` (NSTAGE == SLABS)
           const int r = q * 32 + lane;
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
