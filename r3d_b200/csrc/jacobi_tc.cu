@@ -13,11 +13,13 @@
 // hi = round-to-nearest TF32 of x (exact in TF32), lo = x - hi, and D = A_hi B_hi + A_hi B_lo + A_lo B_hi
 // accumulated in fp32 in TMEM (error ~2^-22 per product).
 //
-// Pipeline per CTA (persistent over a strided tile list):
-//   warp 0      TMA producer: panel tile (two 32-column boxes of 128 rows, K-major
-//               SWIZZLE_128B) + Q^T (two 32-column boxes of 64 rows, K-major SWIZZLE_128B)
+// Pipeline per CTA (persistent over a strided tile list); the unit that travels through the 2-stage shared-memory
+// ring is one 32-column K slab of a tile, not the tile:
+//   warp 0      TMA producer: per slab one 32-column box of 128 panel rows + one 32-column box of the 64 rows of
+//               Q^T (both K-major SWIZZLE_128B)
 //   warps 2-5   splitters: hi/lo split in shared memory (same swizzled addresses)
-//   warp 1      MMA issuer: 24 x tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=64, K=8)
+//   warp 1      MMA issuer: per slab 12 x tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=64, K=8), the two slabs of a
+//               tile accumulate into the same TMEM tile
 //   warps 6-9   epilogue: tcgen05.ld 32x32b.x64 -> (transposed) global stores
 //   (warp 0 also allocates TMEM: 2 accumulator stages x 64 columns)
 // SASS evidence: UTCHMMA/UTCMMA (tcgen05.mma), UTMALDG (TMA), LDTM (tcgen05.ld).
