@@ -47,7 +47,7 @@ int64_t r3d_launch_count(int reset);
  *   "jacobi_tol_pass1"    the same for the first pass of the two-pass solver, default 1e-6
  *   "jacobi_nu_pass1"     first-pass absolute significance floor in units of 2^-23 max|diag|, default 2048 (the first
  *                         pass stops early, the second finishes; single-pass solver and second pass use 4)
- *   "jacobi_max_sweeps"   sweep cap, default 16, at most 32; "erank_pass1_sweeps" (12) / "erank_pass2_sweeps" (6)
+ *   "jacobi_max_sweeps"   sweep cap, default 16, at most 32; "erank_pass1_sweeps" (12) / "erank_pass2_sweeps" (4)
  *                         are the caps of the two passes
  * Kernel selection (defaults are the fast paths; the alternatives exist for A/B measurements and as fallbacks):
  *   "jacobi_update_tc"    1 = tcgen05 3xTF32 panel update, 0 = SIMT fp32 tile update

@@ -39,8 +39,9 @@ struct Options {
                                   // loses its smallest directions (9e-3)
   int erank_pass1_sweeps = 12;  // sweep cap of the first pass of the two-pass solver (it converges in 8-11 with the raised floor;
                                 // whatever a capped matrix still needs, the second pass does); 0 = jacobi_max_sweeps
-  int erank_pass2_sweeps = 6;   // sweep cap of the second pass (0 = jacobi_max_sweeps); it usually converges in 2-3, and the
-                                // sweeps after convergence cost launch latency only (48.8 -> 49.4 ms for 3 -> 6)
+  int erank_pass2_sweeps = 4;   // sweep cap of the second pass (0 = jacobi_max_sweeps); it converges in 2 (one working sweep and one
+                                // that finds nothing significant) on every spectrum tried; each spare sweep costs 60 launches
+                                // that return at once (~0.2 ms per step)
   int erank_passes = 2;         // 2: second refinement pass (G2 = Y Y^T -> Jacobi -> U, Y updated): relative accuracy for the
                                 //    smallest singular directions (gradients <= 1e-4 on square samples), +15 % time;
                                 //    1: single pass (erank itself is already <= 3e-6; gradients 2e-4 .. 1e-2)
