@@ -58,17 +58,26 @@ int64_t r3d_launch_count(int reset);
  *   "jacobi_chunks"       1 (default); 2 = two half-batches on two streams (measured slower)
  *   "panel_merged"        0 (default); 1 = both G passes in one launch with H in an L2-resident ring, sized by
  *                         "panel_group_mb" (8) and "panel_ring" (6) (less DRAM traffic, measured slower)
+ *   "jacobi_schedule"     1 (default) = spread schedule where the block count allows it (a power of two >= 8, i.e.
+ *                         n in (192,256], (448,512], (960,1024], ...): the rounds of a sweep are XOR matchings grouped three
+ *                         at a time into super-rounds confined to 128-column groups, so G and V are streamed once per
+ *                         super-round instead of once per round; 0 = circle-method round robin
  *   "row_chunk_mult"      row chunks per SM of the column-reduction kernels, default 4
  *   "panel_debug", "panel_grid_cap"   test / timing hooks of the panel kernel */
 int r3d_set_option(const char* key, double value);
 /* Test hook: one tensor-core panel-update round (G <- Q^T G Q via H, V <- V Q) on caller buffers. */
 int r3d_debug_panel_round(float* G, float* H, float* V, const float* Qb, int64_t B, int np, int round,
                           int* scratch, void* stream);
-/* Measurement hook: panel tiles (128 rows x 64 columns: 32 KB read + 32 KB written) the Jacobi panel kernel has
- * actually processed on the current device since the last reset -- out2[0] G passes, out2[1] V passes.  The
- * launch sequence is fixed and launches after convergence exit at once, so algorithmic bytes per timed region are
- * tiles x 65536, not launches x (one full pass).  Synchronises the device. */
-int r3d_panel_tiles(uint64_t* out2, int reset);
+/* Measurement hook: panel tiles (128 rows x 64 output columns: 32 KB read + 32 KB written) the Jacobi panel kernel
+ * has actually processed on the current device since the last reset -- out3[0] G passes, out3[1] V passes, out3[2]
+ * tiles of the group-local 128 x 128 problems of the spread schedule (an L2-resident working set, not HBM traffic).
+ * The launch sequence is fixed and launches after convergence exit at once, so the bytes a timed region really
+ * moved are tiles x 65536, not launches x (one full pass).  Synchronises the device. */
+int r3d_panel_tiles(uint64_t* out3, int reset);
+/* Side-stream sets (4 streams + 11 events each) created in this process so far.  They are pooled per device and
+ * lent to host threads, so the count stays flat when short-lived threads (nn.DataParallel replicas,
+ * main_utkinects.py:129) call the effective-rank entry points. */
+int r3d_stream_sets_created(void);
 int r3d_profile_enable(int on);
 int r3d_profile_num_stages(void);
 const char* r3d_profile_stage_name(int stage);

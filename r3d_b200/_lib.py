@@ -52,6 +52,7 @@ SIGNATURES = {
     "r3d_jacobi_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "r3d_token_informativeness": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_float, c_void_p, c_void_p]),
     "r3d_panel_tiles": (c_int, [c_void_p, c_int]),
+    "r3d_stream_sets_created": (c_int, []),
     "r3d_ln_bwd_workspace_floats": (c_size_t, [c_int64, c_int64]),
     "r3d_ln_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_float, c_int, c_void_p, c_void_p,
                            c_void_p, c_void_p]),
@@ -95,10 +96,11 @@ def launch_count(reset: bool = False) -> int:
 
 
 def panel_tiles(reset: bool = True):
-    """(G tiles, V tiles) the Jacobi panel kernel processed on the current device since the last reset."""
-    out = (ctypes.c_uint64 * 2)()
+    """(G tiles, V tiles, group-local tiles) the Jacobi panel kernel processed on the current device since the
+    last reset."""
+    out = (ctypes.c_uint64 * 3)()
     check(lib().r3d_panel_tiles(out, 1 if reset else 0))
-    return int(out[0]), int(out[1])
+    return int(out[0]), int(out[1]), int(out[2])
 
 
 def profile_enable(on: bool = True) -> bool:

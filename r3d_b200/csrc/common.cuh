@@ -34,7 +34,8 @@ void count_launch(int n = 1);
 enum Stage {
   ST_SCORE_PARTIAL = 0, ST_SCORE_FINALIZE, ST_BOTTOMK, ST_EXCHANGE_FWD, ST_EXCHANGE_BWD, ST_COLSUM_FINALIZE,
   ST_BN_STATS, ST_BN_BWD, ST_GRAM, ST_JACOBI_INIT, ST_JACOBI_INNER, ST_JACOBI_UPDATE, ST_JACOBI_EXTRACT,
-  ST_REFINE_Y, ST_SIGMA, ST_ENTROPY, ST_COEF, ST_BWD_GEMM, ST_TOKEN_INFO, ST_BLOCK, ST_JACOBI_VUPDATE, ST_NUM
+  ST_REFINE_Y, ST_SIGMA, ST_ENTROPY, ST_COEF, ST_BWD_GEMM, ST_TOKEN_INFO, ST_BLOCK, ST_JACOBI_VUPDATE,
+  ST_JACOBI_LOCAL, ST_NUM
 };
 bool profiling_enabled();
 void stage_begin(int stage, cudaStream_t st);

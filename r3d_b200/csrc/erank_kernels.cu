@@ -11,6 +11,8 @@
 // X^T X a graded matrix, which two-sided Jacobi resolves to relative accuracy.
 // No transposes are materialised: the GEMMs read X through (row, col) strides.
 #include <algorithm>
+#include <atomic>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -145,6 +147,10 @@ struct JacobiWs {
   float* Gp; float* Vt; float* H; float* Qb[2]; int* cnt; int* qflag[2]; float* nu;   // nact = cnt + B*JMAX_SWEEPS
   int* psync;   // 2 * kPanelSyncGroups + 1 counters of the merged panel schedule (cleared by the inner solver)
   int np, nb, nt;
+  // spread schedule (np % 128 == 0): group-local problems of a super-round, B * np/128 matrices of 128 x 128
+  float* Sg; float* Sh; float* Pv; float* Pt[2];   // local G, its ping-pong scratch, local V (= P), P^T (double-buffered)
+  float* Ql[2];                                    // Q^T of the local rounds (2 tasks of 64 x 64 per group)
+  int* lflag[3]; int* gflag[2];                    // per local task flags of the three rounds; per group flags
 };
 
 static inline int jacobi_np(int64_t n) { return int(((n + JM - 1) / JM) * JM); }
@@ -160,7 +166,11 @@ static size_t jacobi_ws_bytes(int64_t B, int64_t n) {   // includes slack so tha
   const size_t np = jacobi_np(n), nt = np / JM;
   size_t f = size_t(B) * (3 * np * np + 2 * nt * JM * JM + 1);
   size_t i = size_t(B) * (JMAX_SWEEPS + 2 * nt) + JMAX_SWEEPS + 2 * (2 * kPanelSyncGroups + 8);
-  return f * 4 + i * 4 + 2048;
+  if (np % 128 == 0) {                                  // spread schedule: Sg, Sh, Pv, Pt[2] + flags
+    f += size_t(B) * 6 * np * 128;
+    i += size_t(B) * 5 * nt;
+  }
+  return f * 4 + i * 4 + 4096;
 }
 
 static JacobiWs jacobi_carve(void* ws, int64_t B, int64_t n) {
@@ -178,7 +188,21 @@ static JacobiWs jacobi_carve(void* ws, int64_t B, int64_t n) {
   w.cnt = (int*)p; p += (size_t(B) * JMAX_SWEEPS + JMAX_SWEEPS) * 4;   // per-matrix counts, then nact[JMAX_SWEEPS]
   w.qflag[0] = (int*)p; p += size_t(B) * w.nt * 4;
   w.qflag[1] = (int*)p; p += size_t(B) * w.nt * 4;
-  w.psync = (int*)p;
+  w.psync = (int*)p; p += size_t(2 * kPanelSyncGroups + 8) * 4;
+  w.Sg = w.Sh = w.Pv = w.Pt[0] = w.Pt[1] = nullptr;
+  if (w.np % 128 == 0) {
+    p = (char*)((uintptr_t(p) + 255) & ~uintptr_t(255));
+    const size_t gsz = size_t(B) * w.np * 128 * 4;     // B * (np/128) groups x 128 x 128 floats
+    w.Sg = (float*)p; p += gsz;
+    w.Sh = (float*)p; p += gsz;
+    w.Pv = (float*)p; p += gsz;
+    w.Pt[0] = (float*)p; p += gsz;
+    w.Pt[1] = (float*)p; p += gsz;
+    w.Ql[0] = (float*)p; p += gsz / 2;
+    w.Ql[1] = (float*)p; p += gsz / 2;
+    for (int k = 0; k < 3; ++k) { w.lflag[k] = (int*)p; p += size_t(B) * w.nt * 4; }   // B * ng * 2 local tasks = B * nt
+    for (int k = 0; k < 2; ++k) { w.gflag[k] = (int*)p; p += size_t(B) * (w.nt / 2) * 4; }
+  }
   return w;
 }
 
@@ -227,8 +251,15 @@ __global__ void jacobi_active_kernel(int* __restrict__ cnt, int B, int sweep) {
   if (threadIdx.x == 0) cnt[B * JMAX_SWEEPS + sweep] = total;
 }
 
-// circle-method round robin over m (even) players: pair t of round r
+// pair t of round r over m (even) blocks: r >= 0 circle-method round robin; r < 0 the XOR matching with mask -r
+// (block i is paired with i ^ mask; i = t with a zero bit inserted at the mask's top bit)
 __device__ __forceinline__ void rr_pair(int m, int r, int t, int& a, int& b) {
+  if (r < 0) {
+    const int mask = -r, hb = 31 - __clz(mask);
+    a = ((t >> hb) << (hb + 1)) | (t & ((1 << hb) - 1));
+    b = a ^ mask;
+    return;
+  }
   if (m == 2) { a = 0; b = 1; return; }
   int x, y;
   if (t == 0) { x = r; y = m - 1; }
@@ -286,12 +317,15 @@ __global__ void __launch_bounds__(256, 5) jacobi_inner_kernel(float* __restrict_
                                                               int sweep, int* __restrict__ cnt,
                                                               int* __restrict__ qflag, float* __restrict__ Qb,
                                                               float tol, const float* __restrict__ nu,
-                                                              int max_inner, int* __restrict__ psync) {
-  const int b = blockIdx.y, t = blockIdx.x;
-  if (sweep > 0 && cnt[gridDim.y * JMAX_SWEEPS + sweep] == 0) return;   // every matrix converged
+                                                              int max_inner, int* __restrict__ psync, int bdiv,
+                                                              int generic) {
+  // bdiv > 1: the batch is the set of group-local problems of the spread schedule, bdiv per matrix; the convergence
+  // bookkeeping (cnt, nact, nu) stays per matrix
+  const int b = blockIdx.y, t = blockIdx.x, bm = b / bdiv;
+  if (sweep > 0 && cnt[(gridDim.y / bdiv) * JMAX_SWEEPS + sweep] == 0) return;   // every matrix converged
   if (psync != nullptr && b == 0 && t == 0)                             // counters of this round's merged panel launch
     for (int i = threadIdx.x; i < 2 * kPanelSyncGroups + 1; i += 256) psync[i] = 0;
-  if (sweep > 0 && cnt[b * JMAX_SWEEPS + sweep - 1] == 0) return;   // this matrix converged
+  if (sweep > 0 && cnt[bm * JMAX_SWEEPS + sweep - 1] == 0) return;   // this matrix converged
   __shared__ __align__(16) float S[JM][SP];          // S~
   __shared__ __align__(16) float Qt[JM][SP];         // Q~^T: Qt[i][k] = Q[k][i] / d_i
   __shared__ __align__(16) float4 rot[JB];           // generic rounds: {tau_pq, tau_qp, bits(p), bits(q)}
@@ -318,12 +352,12 @@ __global__ void __launch_bounds__(256, 5) jacobi_inner_kernel(float* __restrict_
       S[i][j] = v; S[j][i] = v;
     }
   }
-  const float nu_abs = nu[b];
+  const float nu_abs = nu[bm];
   __syncthreads();
 
   int sig_total = 0;
   for (int it = 0; it < max_inner; ++it) {
-    if (round == 0) {
+    if (generic) {
       // ---------------- generic schedule: all pairs of the 64 columns ----------------
       for (int s = 0; s < JM - 1; ++s) {
         if (tid < JB) {
@@ -436,7 +470,7 @@ __global__ void __launch_bounds__(256, 5) jacobi_inner_kernel(float* __restrict_
     if (sig_now == sig_total) break;  // nothing significant in this inner sweep
     sig_total = sig_now;
   }
-  if (tid == 0 && sig_total > 0) atomicAdd(&cnt[b * JMAX_SWEEPS + sweep], sig_total);
+  if (tid == 0 && sig_total > 0) atomicAdd(&cnt[bm * JMAX_SWEEPS + sweep], sig_total);
   float* qo = Qb + (int64_t(b) * nt + t) * JM * JM;
   for (int e = tid; e < JM * JM; e += 256) qo[e] = dsc[e / JM] * Qt[e / JM][e % JM];   // Q^T = D Q~^T, row-major
   if (tid == 0) qflag[b * nt + t] = (s_tot > 0);
@@ -488,12 +522,12 @@ __global__ void __launch_bounds__(256, 4) jacobi_inner_cross_kernel(float* __res
                                                                     int round, int sweep, int* __restrict__ cnt,
                                                                     int* __restrict__ qflag, float* __restrict__ Qb,
                                                                     float tol, const float* __restrict__ nu,
-                                                                    int* __restrict__ psync) {
-  const int b = blockIdx.y, t = blockIdx.x;
-  if (sweep > 0 && cnt[gridDim.y * JMAX_SWEEPS + sweep] == 0) return;   // every matrix converged
+                                                                    int* __restrict__ psync, int bdiv) {
+  const int b = blockIdx.y, t = blockIdx.x, bm = b / bdiv;              // bdiv: see jacobi_inner_kernel
+  if (sweep > 0 && cnt[(gridDim.y / bdiv) * JMAX_SWEEPS + sweep] == 0) return;   // every matrix converged
   if (psync != nullptr && b == 0 && t == 0)                             // counters of this round's merged panel launch
     for (int i = threadIdx.x; i < 2 * kPanelSyncGroups + 1; i += 256) psync[i] = 0;
-  if (sweep > 0 && cnt[b * JMAX_SWEEPS + sweep - 1] == 0) return;       // this matrix converged
+  if (sweep > 0 && cnt[bm * JMAX_SWEEPS + sweep - 1] == 0) return;      // this matrix converged
   // ONE 17 KB staging buffer (initial tile, the three cross-warp transitions, final Q^T): small enough that a CTA
   // of this kernel fits next to two resident CTAs of the panel update (V on the side stream)
   __shared__ __align__(16) float S[JM][SP];
@@ -549,7 +583,7 @@ __global__ void __launch_bounds__(256, 4) jacobi_inner_cross_kernel(float* __res
       QB[ra][c] = (u == 4 * Bc + c) ? 1.f : 0.f;
     }
   }
-  const float nu_abs = nu[b], tol2 = tol * tol;
+  const float nu_abs = nu[bm], tol2 = tol * tol;
   const bool rot_warp = (warp & 3) == 0;            // warps 0 and 4 hold the diagonal pair blocks (D == 0) ...
   const bool rot_lane = rot_warp && (lane & 8) == 0; // ... in lanes with D1 == 0; lane bit 2 (D0) picks the rotation
   const int rsel = (lane >> 2) & 1;
@@ -676,7 +710,7 @@ __global__ void __launch_bounds__(256, 4) jacobi_inner_cross_kernel(float* __res
     *reinterpret_cast<float4*>(&S[u][4 * Bc]) = make_float4(QB[ra][0], QB[ra][1], QB[ra][2], QB[ra][3]);
   }
   __syncthreads();
-  if (tid == 0 && s_sig > 0) atomicAdd(&cnt[b * JMAX_SWEEPS + sweep], s_sig);
+  if (tid == 0 && s_sig > 0) atomicAdd(&cnt[bm * JMAX_SWEEPS + sweep], s_sig);
   float4* qo = reinterpret_cast<float4*>(Qb + (int64_t(b) * nt + t) * JM * JM);
 #pragma unroll
   for (int u = 0; u < JM * JM / 4 / 256; ++u) {
@@ -774,6 +808,120 @@ __global__ void __launch_bounds__(256) jacobi_update_kernel(float* __restrict__ 
     const int gj = two_sided ? blk_row(Ic, Jc, j0) : slab * JM + j0;   // 4 consecutive j stay inside one block
     *reinterpret_cast<float4*>(&base[boff(np, blk_row(Ia, Ja, i), gj)]) =
         make_float4(acc[u][0], acc[u][1], acc[u][2], acc[u][3]);
+  }
+}
+
+// ------------------------------------------------------------------------------
+// Spread schedule.  With nb = 2^k blocks, the rounds of a sweep are the XOR matchings i <-> i ^ mask, mask = 1..nb-1.
+// Three masks {a, b, a^b} (a two-dimensional subspace of GF(2)^k minus zero) only ever pair blocks inside the cosets
+// {i0, i0^a, i0^b, i0^a^b}: 4-block groups of 128 columns.  A super-round gathers the 128 x 128 diagonal group blocks
+// of G into a batch of small matrices (Sg), runs the three rounds on them with the same kernels (inner solve, panel
+// update with V accumulation: the local "V" is the product P of the three rounds' rotations), and then streams G and
+// V ONCE with the 128 x 128 products P (K = N = 128) instead of three times with 64 x 64 rotations.  The subspaces
+// of a sweep partition the masks (a spread of PG(k-1, 2), built from GF(2^k) over GF(4) when k is even; for odd k a
+// greedy partial spread and the left-over masks as ordinary single rounds), so every block pair still meets exactly
+// once per sweep.  The group-local working set (B * np/128 matrices of 64 KB) stays in L2.
+// ------------------------------------------------------------------------------
+struct SuperRound { int a, b; };             // b == 0: single round with mask a; else the triple {a, b, a^b}
+
+static std::vector<SuperRound> spread_plan(int nb) {
+  std::vector<SuperRound> plan;
+  int k = 0;
+  while ((1 << k) < nb) ++k;
+  if ((1 << k) != nb || k < 3) return plan;                 // needs a power of two >= 8 blocks
+  std::vector<char> used(nb, 0);
+  if (k % 2 == 0) {
+    static const int prim[9] = {0, 0, 0x7, 0, 0x13, 0, 0x43, 0, 0x11d};   // primitive polynomials of degree 2, 4, 6, 8
+    if (k <= 8) {
+      std::vector<int> e(nb - 1);
+      e[0] = 1;
+      for (int i = 1; i < nb - 1; ++i) { int v = e[i - 1] << 1; if (v & nb) v ^= prim[k]; e[i] = v; }
+      const int third = (nb - 1) / 3;
+      for (int i = 0; i < third; ++i) {                       // g^i GF(4)^* = {g^i, g^(i + N/3), g^(i + 2N/3)}
+        plan.push_back({e[i], e[i + third]});
+        used[e[i]] = used[e[i + third]] = used[e[i] ^ e[i + third]] = 1;
+      }
+    }
+  }
+  // whatever is left (odd k, or k > 8): greedy triples, then single rounds
+  for (int a = 1; a < nb; ++a) {
+    if (used[a]) continue;
+    int found = 0;
+    for (int b = a + 1; b < nb && !found; ++b)
+      if (!used[b] && !used[a ^ b] && (a ^ b) > a) { found = b; }
+    used[a] = 1;
+    if (found) { used[found] = used[a ^ found] = 1; plan.push_back({a, found}); }
+    else plan.push_back({a, 0});
+  }
+  // the first round of a sweep rotates the pairs inside each block too (generic schedule): it must be a round that
+  // exists in every plan -- the first mask of the first super-round, whatever that is
+  return plan;
+}
+
+static PanelGroups groups_of(const SuperRound& sr) {
+  auto top = [](int v) { int h = 0; while ((v >> (h + 1)) != 0) ++h; return h; };
+  const int p1 = top(sr.a);
+  const int b2 = ((sr.b >> p1) & 1) ? (sr.b ^ sr.a) : sr.b;
+  const int p2 = top(b2);
+  PanelGroups g;
+  g.ga = sr.a; g.gb = sr.b; g.plo = std::min(p1, p2); g.phi = std::max(p1, p2);
+  return g;
+}
+
+// Sg[b*ng + g] <- the 128 x 128 diagonal block of group g (16 sub-blocks of 32 x 32 = contiguous 4 KB runs in the
+// blocked layout of both matrices); Pv <- I.  One CTA per (group, matrix).
+__global__ void __launch_bounds__(256) group_gather_kernel(const float* __restrict__ Gp, int np, int nb, int ng,
+                                                           PanelGroups grp, int sweep, const int* __restrict__ cnt,
+                                                           float* __restrict__ Sg, float* __restrict__ Pv) {
+  const int g = blockIdx.x, b = blockIdx.y;
+  if (sweep > 0 && cnt[gridDim.y * JMAX_SWEEPS + sweep] == 0) return;
+  if (sweep > 0 && cnt[b * JMAX_SWEEPS + sweep - 1] == 0) return;
+  int x = g;
+  x = ((x >> grp.plo) << (grp.plo + 1)) | (x & ((1 << grp.plo) - 1));
+  x = ((x >> grp.phi) << (grp.phi + 1)) | (x & ((1 << grp.phi) - 1));
+  int blk[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) blk[j] = x ^ ((j & 1) ? grp.ga : 0) ^ ((j & 2) ? grp.gb : 0);
+  const float4* src = reinterpret_cast<const float4*>(Gp + int64_t(b) * np * np);
+  float4* dst = reinterpret_cast<float4*>(Sg + (int64_t(b) * ng + g) * 128 * 128);
+  float4* pv = reinterpret_cast<float4*>(Pv + (int64_t(b) * ng + g) * 128 * 128);
+  // local element (r, c) sits at ((c >> 5) * 128 + r) * 32 + (c & 31); as float4 index e = (cb * 128 + r) * 8 + j4
+  for (int e = threadIdx.x; e < 128 * 128 / 4; e += 256) {
+    const int j4 = e & 7, r = (e >> 3) & 127, cb = e >> 10;
+    const int64_t s = (int64_t(blk[cb]) * np + blk[r >> 5] * JB + (r & 31)) * 8 + j4;
+    dst[e] = src[s];
+    const int d = r - cb * 32 - j4 * 4;                 // diagonal position inside this float4, if 0..3
+    pv[e] = make_float4(d == 0 ? 1.f : 0.f, d == 1 ? 1.f : 0.f, d == 2 ? 1.f : 0.f, d == 3 ? 1.f : 0.f);
+  }
+}
+
+// Pt[b*ng + g][n][k] = P[k][n] (P = the local V, blocked layout) -- the K-major B operand of the K = 128 panel update;
+// gflag = OR of the six local task flags of the super-round.  One CTA per (group, matrix).
+__global__ void __launch_bounds__(256) group_transpose_kernel(const float* __restrict__ Pv, int ng, int sweep,
+                                                              const int* __restrict__ cnt,
+                                                              const int* __restrict__ f0, const int* __restrict__ f1,
+                                                              const int* __restrict__ f2, float* __restrict__ Pt,
+                                                              int* __restrict__ gflag) {
+  const int g = blockIdx.x, b = blockIdx.y;
+  if (sweep > 0 && cnt[gridDim.y * JMAX_SWEEPS + sweep] == 0) return;
+  if (sweep > 0 && cnt[b * JMAX_SWEEPS + sweep - 1] == 0) return;
+  __shared__ float tile[32][33];
+  const int64_t gi = int64_t(b) * ng + g;
+  const float* pv = Pv + gi * 128 * 128;
+  float* pt = Pt + gi * 128 * 128;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int t = 0; t < 16; ++t) {                       // 32 x 32 tile (k block kb, column block cb)
+    const int cb = t >> 2, kb = t & 3;
+#pragma unroll
+    for (int r = warp; r < 32; r += 8) tile[r][lane] = pv[(cb * 128 + kb * 32 + r) * 32 + lane];   // [k][n]
+    __syncthreads();
+#pragma unroll
+    for (int r = warp; r < 32; r += 8) pt[(cb * 32 + r) * 128 + kb * 32 + lane] = tile[lane][r];     // [n][k]
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const int i = int(gi) * 2;
+    gflag[gi] = f0[i] | f0[i + 1] | f1[i] | f1[i + 1] | f2[i] | f2[i + 1];
   }
 }
 
@@ -1009,16 +1157,23 @@ extern "C" int r3d_debug_panel_round(float* G, float* H, float* V, const float* 
   PanelTc ptc;
   if (int e = panel_tc_prepare(&ptc, G, H, V, Qb, Qb, B, np)) return e;
   if (int e = panel_tc_update_v(&ptc, 0, round, 0, cnt, qflag, st)) return e;
+  if (options().panel_sym != 0 && panel_sym_supported(np)) {       // one in-place pass; H is not touched
+    if (int e = panel_sym_prepare(&ptc)) return e;
+    return panel_sym_update_g(&ptc, 0, round, 0, cnt, qflag, st);
+  }
   return panel_tc_update_g(&ptc, 0, round, 0, cnt, qflag, st);
 }
 
-extern "C" int r3d_panel_tiles(uint64_t* out2, int reset) {
-  R3D_CHECK(out2 != nullptr, "null pointer");
-  unsigned long long v[2];
+extern "C" int r3d_panel_tiles(uint64_t* out3, int reset) {
+  R3D_CHECK(out3 != nullptr, "null pointer");
+  unsigned long long v[3];
   if (int e = panel_tiles_read(v, reset)) return e;
-  out2[0] = v[0]; out2[1] = v[1];
+  unsigned long long units = 0;                     // the one-pass symmetric G update counts in the same 64 KB units
+  if (int e = panel_sym_units_read(&units, reset)) return e;
+  out3[0] = v[0] + units; out3[1] = v[1]; out3[2] = v[2];
   return 0;
 }
+
 
 extern "C" int r3d_set_option(const char* key, double value) {
   R3D_CHECK(key != nullptr, "null option key");
@@ -1040,6 +1195,8 @@ extern "C" int r3d_set_option(const char* key, double value) {
   else if (k == "panel_group_mb") options().panel_group_mb = std::max(1, (int)value);
   else if (k == "panel_ring") options().panel_ring = (int)value;
   else if (k == "jacobi_v_after_g") options().jacobi_v_after_g = value != 0.0;
+  else if (k == "jacobi_schedule") options().jacobi_schedule = (int)value;
+  else if (k == "panel_sym") options().panel_sym = (int)value;
   else if (k == "panel_debug") g_panel_debug = (int)value;
   else if (k == "panel_grid_cap") g_panel_grid_cap = (int)value;
   else R3D_CHECK(false, "unknown option '%s'", key);
@@ -1230,8 +1387,7 @@ struct StreamSet {
   cudaStream_t chunk[kMaxChunks] = {nullptr, nullptr};     // chunk 0 uses the caller's stream
   cudaStream_t vst[kMaxChunks] = {nullptr, nullptr};
   cudaEvent_t ev_inner[kMaxChunks][2], ev_v[kMaxChunks][2], ev_fork, ev_join[kMaxChunks];
-  int ensure() {
-    if (ready) return 0;
+  int create() {
     for (int c = 0; c < kMaxChunks; ++c) {
       R3D_CUDA(cudaStreamCreateWithFlags(&chunk[c], cudaStreamNonBlocking));
       R3D_CUDA(cudaStreamCreateWithFlags(&vst[c], cudaStreamNonBlocking));
@@ -1246,8 +1402,44 @@ struct StreamSet {
     return 0;
   }
 };
-static thread_local StreamSet g_streams_dev[kMaxDevices];   // per host thread AND per device
-#define g_streams (g_streams_dev[current_device_index()])
+// Stream sets are pooled per device for the whole process: a host thread borrows one on first use and hands it back
+// when it exits (nn.DataParallel starts fresh threads for every forward, so thread-owned sets would be re-created
+// -- or, without a destructor, leaked -- on every step).  A set is never shared by two live threads: events recorded
+// by one thread must not be overwritten by another.
+static std::mutex g_pool_mu;
+static std::vector<StreamSet*> g_pool_free[kMaxDevices];
+static std::atomic<int> g_sets_created{0};
+struct StreamLease {
+  StreamSet* set[kMaxDevices] = {};
+  ~StreamLease() {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    for (int d = 0; d < kMaxDevices; ++d)
+      if (set[d]) g_pool_free[d].push_back(set[d]);
+  }
+  int get(StreamSet** out) {
+    const int d = current_device_index();
+    if (!set[d]) {
+      {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        if (!g_pool_free[d].empty()) { set[d] = g_pool_free[d].back(); g_pool_free[d].pop_back(); }
+      }
+      if (!set[d]) {
+        StreamSet* s = new StreamSet();
+        if (int e = s->create()) { delete s; return e; }
+        g_sets_created.fetch_add(1);
+        set[d] = s;
+      }
+    }
+    *out = set[d];
+    return 0;
+  }
+};
+static thread_local StreamLease g_lease;
+struct StreamRef {                         // keeps the old `g_streams.x` / `g_streams.ensure()` spelling
+  StreamSet* s = nullptr;
+  int ensure() { return s ? 0 : g_lease.get(&s); }
+  StreamSet* operator->() { return s; }
+};
 
 static int jacobi_run(const float* G, int64_t B, int64_t n, void* workspace, float* lambda_out, float* U_out,
                       int32_t* sweeps_out, int max_sweeps, cudaStream_t st, int chunk = 0, float tol_override = 0.f) {
@@ -1258,8 +1450,14 @@ static int jacobi_run(const float* G, int64_t B, int64_t n, void* workspace, flo
   const bool tc = options().jacobi_update_tc != 0 && panel_tc_supported(w.np);
   PanelTc ptc;
   const bool overlap = tc && options().jacobi_overlap_v != 0;
+  StreamRef g_streams;
+  std::vector<SuperRound> plan;
+  if (tc && options().jacobi_schedule == 1 && w.Sg != nullptr) plan = spread_plan(w.nb);
+  const bool spread = !plan.empty();
+  const bool sym = tc && options().panel_sym != 0 && panel_sym_supported(w.np);
   if (tc) {
     if (int e = panel_tc_prepare(&ptc, w.Gp, w.H, w.Vt, w.Qb[0], w.Qb[1], B, w.np)) return e;
+    if (sym) { if (int e = panel_sym_prepare(&ptc)) return e; }
     if (overlap) { if (int e = g_streams.ensure()) return e; }
   }
   {
@@ -1275,59 +1473,112 @@ static int jacobi_run(const float* G, int64_t B, int64_t n, void* workspace, flo
   const int upd_tiles = w.nt * w.nt + w.nt * (w.np / JM);
   int iter = 0;
   bool v_pending[2] = {false, false};
+  // V(big) of an iteration on the side stream: `launch_v(vs)` issues it
+  auto fork_v = [&](int qb, auto&& launch_v) -> int {
+    cudaStream_t vs = g_streams->vst[chunk];
+    R3D_CUDA(cudaEventRecord(g_streams->ev_inner[chunk][qb], st));
+    R3D_CUDA(cudaStreamWaitEvent(vs, g_streams->ev_inner[chunk][qb], 0));
+    if (int e = launch_v(vs)) return e;
+    R3D_CUDA(cudaEventRecord(g_streams->ev_v[chunk][qb], vs));
+    v_pending[qb] = true;
+    return 0;
+  };
+  // one ordinary round (pairing code r: >= 0 circle method, < 0 XOR mask) on the full matrices
+  auto plain_round = [&](int r, bool generic, int sweep, int qb) -> int {
+    {
+      R3D_STAGE(ST_JACOBI_INNER, st);
+      if (!generic && options().jacobi_inner_regs != 0)
+        jacobi_inner_cross_kernel<<<dim3(w.nt, (unsigned)B), 256, 0, st>>>(w.Gp, w.np, w.nb, w.nt, r, sweep, w.cnt,
+                                                                          w.qflag[qb], w.Qb[qb], tol, w.nu, w.psync, 1);
+      else
+        jacobi_inner_kernel<<<dim3(w.nt, (unsigned)B), 256, 0, st>>>(w.Gp, w.np, w.nb, w.nt, r, sweep, w.cnt,
+                                                                    w.qflag[qb], w.Qb[qb], tol, w.nu, 1, w.psync, 1,
+                                                                    generic ? 1 : 0);
+      R3D_LAUNCH_CHECK();
+    }
+    if (tc) {
+      auto vlaunch = [&](cudaStream_t vs) { return panel_tc_update_v(&ptc, qb, r, sweep, w.cnt, w.qflag[qb], vs); };
+      if (overlap && options().jacobi_v_after_g == 0) { if (int e = fork_v(qb, vlaunch)) return e; }
+      else if (!overlap) { if (int e = vlaunch(st)) return e; }
+      if (sym) { if (int e = panel_sym_update_g(&ptc, qb, r, sweep, w.cnt, w.qflag[qb], st)) return e; }
+      else if (int e = panel_tc_update_g(&ptc, qb, r, sweep, w.cnt, w.qflag[qb], st, spread ? nullptr : w.psync)) return e;
+      // jacobi_v_after_g: start V(r) only when the G passes of round r are done, so that it overlaps inner(r+1)
+      // instead of competing with the G passes for HBM bandwidth
+      if (overlap && options().jacobi_v_after_g != 0) { if (int e = fork_v(qb, vlaunch)) return e; }
+    } else {
+      R3D_STAGE(ST_JACOBI_UPDATE, st);
+      jacobi_update_kernel<<<dim3(upd_tiles, (unsigned)B), 256, upd_smem, st>>>(w.Gp, w.Vt, w.np, w.nb, w.nt, r,
+                                                                               sweep, w.cnt, w.qflag[qb], w.Qb[qb]);
+      R3D_LAUNCH_CHECK();
+    }
+    return 0;
+  };
+  PanelTc loc;
+  const int ng = w.np / 128;
+  if (spread) {
+    if (int e = panel_tc_prepare(&loc, w.Sg, w.Sh, w.Pv, w.Ql[0], w.Ql[1], B * ng, 128)) return e;
+    loc.bdiv = ng; loc.local = 1;
+    if (sym) { if (int e = panel_sym_prepare(&loc)) return e; }
+    if (int e = panel_tc_prepare_groups(&ptc, w.Pt[0], w.Pt[1])) return e;
+  }
+  // one super-round of the spread schedule: three XOR rounds inside the 4-block groups, then ONE pass over G and V
+  auto super_round = [&](const SuperRound& sr, bool first_of_sweep, int sweep, int pb) -> int {
+    const PanelGroups grp = groups_of(sr);
+    const dim3 ggrid((unsigned)ng, (unsigned)B);
+    {
+      R3D_STAGE(ST_JACOBI_LOCAL, st);
+      group_gather_kernel<<<ggrid, 256, 0, st>>>(w.Gp, w.np, w.nb, ng, grp, sweep, w.cnt, w.Sg, w.Pv);
+      R3D_LAUNCH_CHECK();
+    }
+    for (int k = 0; k < 3; ++k) {
+      const int ql = k & 1, code = -(k + 1);
+      const bool generic = first_of_sweep && k == 0;      // once per sweep the pairs inside each block rotate too
+      {
+        R3D_STAGE(ST_JACOBI_INNER, st);
+        if (!generic && options().jacobi_inner_regs != 0)
+          jacobi_inner_cross_kernel<<<dim3(2, (unsigned)(B * ng)), 256, 0, st>>>(w.Sg, 128, 4, 2, code, sweep, w.cnt, w.lflag[k],
+                                                                                w.Ql[ql], tol, w.nu, nullptr, ng);
+        else
+          jacobi_inner_kernel<<<dim3(2, (unsigned)(B * ng)), 256, 0, st>>>(w.Sg, 128, 4, 2, code, sweep, w.cnt, w.lflag[k],
+                                                                          w.Ql[ql], tol, w.nu, 1, nullptr, ng, generic ? 1 : 0);
+        R3D_LAUNCH_CHECK();
+      }
+      if (int e = panel_tc_update_v(&loc, ql, code, sweep, w.cnt, w.lflag[k], st)) return e;          // P <- P Q_k
+      if (k < 2) {
+        if (sym) { if (int e = panel_sym_update_g(&loc, ql, code, sweep, w.cnt, w.lflag[k], st)) return e; }
+        else if (int e = panel_tc_update_g(&loc, ql, code, sweep, w.cnt, w.lflag[k], st, nullptr)) return e;
+      }
+    }
+    {
+      R3D_STAGE(ST_JACOBI_LOCAL, st);
+      group_transpose_kernel<<<ggrid, 256, 0, st>>>(w.Pv, ng, sweep, w.cnt, w.lflag[0], w.lflag[1], w.lflag[2], w.Pt[pb],
+                                                    w.gflag[pb]);
+      R3D_LAUNCH_CHECK();
+    }
+    auto vlaunch = [&](cudaStream_t vs) { return panel_tc_update_v_groups(&ptc, pb, grp, sweep, w.cnt, w.gflag[pb], vs); };
+    if (overlap) { if (int e = fork_v(pb, vlaunch)) return e; }
+    else { if (int e = vlaunch(st)) return e; }
+    return panel_tc_update_g_groups(&ptc, pb, grp, sweep, w.cnt, w.gflag[pb], st);
+  };
   for (int sweep = 0; sweep < max_sweeps; ++sweep) {
     if (sweep > 0) {
       jacobi_active_kernel<<<1, 256, 0, st>>>(w.cnt, (int)B, sweep);
       R3D_LAUNCH_CHECK();
     }
-    for (int r = 0; r < rounds; ++r, ++iter) {
+    const int steps = spread ? (int)plan.size() : rounds;
+    for (int r = 0; r < steps; ++r, ++iter) {
       const int qb = tc ? (iter & 1) : 0;
-      if (overlap && v_pending[qb]) {        // the V update that last read this Q buffer must be done
-        R3D_CUDA(cudaStreamWaitEvent(st, g_streams.ev_v[chunk][qb], 0));
+      if (overlap && v_pending[qb]) {        // the V update that last read this Q / P^T buffer must be done
+        R3D_CUDA(cudaStreamWaitEvent(st, g_streams->ev_v[chunk][qb], 0));
         v_pending[qb] = false;
       }
-      {
-        R3D_STAGE(ST_JACOBI_INNER, st);
-        if (r > 0 && options().jacobi_inner_regs != 0)
-          jacobi_inner_cross_kernel<<<dim3(w.nt, (unsigned)B), 256, 0, st>>>(w.Gp, w.np, w.nb, w.nt, r, sweep, w.cnt,
-                                                                            w.qflag[qb], w.Qb[qb], tol, w.nu, w.psync);
-        else
-          jacobi_inner_kernel<<<dim3(w.nt, (unsigned)B), 256, 0, st>>>(w.Gp, w.np, w.nb, w.nt, r, sweep, w.cnt,
-                                                                      w.qflag[qb], w.Qb[qb], tol, w.nu, 1, w.psync);
-        R3D_LAUNCH_CHECK();
-      }
-      if (tc) {
-        if (overlap && options().jacobi_v_after_g == 0) {
-          cudaStream_t vs = g_streams.vst[chunk];
-          R3D_CUDA(cudaEventRecord(g_streams.ev_inner[chunk][qb], st));
-          R3D_CUDA(cudaStreamWaitEvent(vs, g_streams.ev_inner[chunk][qb], 0));
-          if (int e = panel_tc_update_v(&ptc, qb, r, sweep, w.cnt, w.qflag[qb], vs)) return e;
-          R3D_CUDA(cudaEventRecord(g_streams.ev_v[chunk][qb], vs));
-          v_pending[qb] = true;
-        } else if (!overlap) {
-          if (int e = panel_tc_update_v(&ptc, qb, r, sweep, w.cnt, w.qflag[qb], st)) return e;
-        }
-        if (int e = panel_tc_update_g(&ptc, qb, r, sweep, w.cnt, w.qflag[qb], st, w.psync)) return e;
-        if (overlap && options().jacobi_v_after_g != 0) {
-          // start V(r) only when the G passes of round r are done, so that it overlaps inner(r+1) instead of
-          // competing with the G passes for HBM bandwidth
-          cudaStream_t vs = g_streams.vst[chunk];
-          R3D_CUDA(cudaEventRecord(g_streams.ev_inner[chunk][qb], st));
-          R3D_CUDA(cudaStreamWaitEvent(vs, g_streams.ev_inner[chunk][qb], 0));
-          if (int e = panel_tc_update_v(&ptc, qb, r, sweep, w.cnt, w.qflag[qb], vs)) return e;
-          R3D_CUDA(cudaEventRecord(g_streams.ev_v[chunk][qb], vs));
-          v_pending[qb] = true;
-        }
-      } else {
-        R3D_STAGE(ST_JACOBI_UPDATE, st);
-        jacobi_update_kernel<<<dim3(upd_tiles, (unsigned)B), 256, upd_smem, st>>>(w.Gp, w.Vt, w.np, w.nb, w.nt, r,
-                                                                                 sweep, w.cnt, w.qflag[qb], w.Qb[qb]);
-        R3D_LAUNCH_CHECK();
-      }
+      if (!spread) { if (int e = plain_round(r, r == 0, sweep, qb)) return e; }
+      else if (plan[r].b == 0) { if (int e = plain_round(-plan[r].a, false, sweep, qb)) return e; }
+      else { if (int e = super_round(plan[r], r == 0, sweep, qb)) return e; }
     }
   }
   for (int i = 0; i < 2; ++i)
-    if (overlap && v_pending[i]) R3D_CUDA(cudaStreamWaitEvent(st, g_streams.ev_v[chunk][i], 0));
+    if (overlap && v_pending[i]) R3D_CUDA(cudaStreamWaitEvent(st, g_streams->ev_v[chunk][i], 0));
   {
     dim3 grid((unsigned)std::min<int64_t>((n + 7) / 8, 64), (unsigned)B);
     R3D_STAGE(ST_JACOBI_EXTRACT, st);
@@ -1342,6 +1593,9 @@ static int jacobi_run(const float* G, int64_t B, int64_t n, void* workspace, flo
   return 0;
 }
 
+// number of side-stream sets created so far in this process (they are pooled: stays flat across short-lived threads)
+extern "C" int r3d_stream_sets_created(void) { return g_sets_created.load(); }
+
 // Split the batch into two chunks on two streams when it is large enough to fill the GPU twice over.
 static int jacobi_run_chunked(const float* G, int64_t B, int64_t n, void* workspace, float* lambda_out, float* U_out,
                               int32_t* sweeps_out, int max_sweeps, cudaStream_t st, float tol_override) {
@@ -1349,18 +1603,19 @@ static int jacobi_run_chunked(const float* G, int64_t B, int64_t n, void* worksp
   const bool split = options().jacobi_chunks >= 2 && B >= 2 && panel_tc_supported(np) &&
                      options().jacobi_update_tc != 0 && (B / 2) * (np / JM) >= 2 * kNumSMs;
   if (!split) return jacobi_run(G, B, n, workspace, lambda_out, U_out, sweeps_out, max_sweeps, st, 0, tol_override);
+  StreamRef g_streams;
   if (int e = g_streams.ensure()) return e;
   const int64_t B0 = (B + 1) / 2, B1 = B - B0;
   char* ws1 = (char*)workspace + ((jacobi_ws_bytes(B0, n) + 255) & ~size_t(255));
-  cudaStream_t s1 = g_streams.chunk[1];
-  R3D_CUDA(cudaEventRecord(g_streams.ev_fork, st));
-  R3D_CUDA(cudaStreamWaitEvent(s1, g_streams.ev_fork, 0));
+  cudaStream_t s1 = g_streams->chunk[1];
+  R3D_CUDA(cudaEventRecord(g_streams->ev_fork, st));
+  R3D_CUDA(cudaStreamWaitEvent(s1, g_streams->ev_fork, 0));
   if (int e = jacobi_run(G, B0, n, workspace, lambda_out, U_out, sweeps_out, max_sweeps, st, 0, tol_override)) return e;
   if (int e = jacobi_run(G + B0 * n * n, B1, n, ws1, lambda_out ? lambda_out + B0 * n : nullptr,
                          U_out ? U_out + B0 * n * n : nullptr, sweeps_out ? sweeps_out + B0 : nullptr, max_sweeps,
                          s1, 1, tol_override)) return e;
-  R3D_CUDA(cudaEventRecord(g_streams.ev_join[1], s1));
-  R3D_CUDA(cudaStreamWaitEvent(st, g_streams.ev_join[1], 0));
+  R3D_CUDA(cudaEventRecord(g_streams->ev_join[1], s1));
+  R3D_CUDA(cudaStreamWaitEvent(st, g_streams->ev_join[1], 0));
   return 0;
 }
 

@@ -621,7 +621,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T* __restrict__
 using namespace r3d;
 
 extern "C" const char* r3d_last_error(void) { return g_err; }
-extern "C" int r3d_abi_version(void) { return 1; }
+extern "C" int r3d_abi_version(void) { return 2; }
 extern "C" int r3d_profile_enable(int on) {
   const int prev = g_prof ? 1 : 0;
   g_prof = on != 0;
@@ -632,7 +632,7 @@ extern "C" const char* r3d_profile_stage_name(int stage) {
   static const char* names[ST_NUM] = {"score_partial", "score_finalize", "bottomk", "exchange_fwd", "exchange_bwd",
                                       "colsum_finalize", "bn_stats", "bn_bwd", "gram", "jacobi_init", "jacobi_inner",
                                       "jacobi_update", "jacobi_extract", "refine_y", "sigma", "entropy", "coef",
-                                      "bwd_gemm", "token_info", "block", "jacobi_vupdate"};
+                                      "bwd_gemm", "token_info", "block", "jacobi_vupdate", "jacobi_local"};
   return (stage >= 0 && stage < ST_NUM) ? names[stage] : "?";
 }
 extern "C" int r3d_profile_read(double* ms_out, int64_t* calls_out, int64_t* launches_out, int reset) {

@@ -42,7 +42,6 @@ constexpr int TM = 128;                // rows per tile
 // through a 2-stage ring, so the TMA of the next slab runs while this one is split and multiplied, and a stage is
 // held for half as long as when a stage was a whole tile (same 96 KB per CTA, two CTAs per SM).
 constexpr int NSTAGE = 2;
-constexpr int SLABS = 2;               // K slabs per tile
 constexpr int A_RAW = TM * PB * 4;     // 16 KB: one slab of the panel tile, hi part after the split (in place)
 constexpr int Q_RAW = PM * PB * 4;     // 8 KB: the matching 32 k-columns of Q^T
 constexpr int STAGE = 2 * A_RAW + 2 * Q_RAW;        // hi + lo of both operands: 48 KB
@@ -130,8 +129,16 @@ __device__ __forceinline__ float tf32_rn(float x) {
   return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
 }
 
-// circle-method round robin (same function as erank_kernels.cu)
+// pairing of round r (same function as erank_kernels.cu): r >= 0 circle-method round robin over m blocks,
+// r < 0 the XOR matching with mask -r (task t pairs block i with i ^ mask, i = t with a zero inserted at the
+// mask's top bit)
 __device__ __forceinline__ void rr_pair_tc(int m, int r, int t, int& a, int& b) {
+  if (r < 0) {
+    const int mask = -r, hb = 31 - __clz(mask);
+    a = ((t >> hb) << (hb + 1)) | (t & ((1 << hb) - 1));
+    b = a ^ mask;
+    return;
+  }
   if (m == 2) { a = 0; b = 1; return; }
   int x, y;
   if (t == 0) { x = r; y = m - 1; }
@@ -142,7 +149,8 @@ __device__ __forceinline__ void rr_pair_tc(int m, int r, int t, int& a, int& b) 
 // tiles actually processed (not skipped) since the last reset: [0] G passes, [1] in-place V passes -- lets bench.py
 // divide the ALGORITHMIC bytes of the timed region (tiles x 64 KB) by its time instead of assuming that every launch
 // of the fixed launch sequence did a full pass (launches after convergence exit at once)
-__device__ unsigned long long g_panel_tiles[2];
+// [2] tiles of the group-local 128x128 problems of the spread schedule (L2-resident working set, not HBM traffic)
+__device__ unsigned long long g_panel_tiles[3];
 
 struct PanelJob {
   // job 0 and job 1 may run in the same launch
@@ -154,17 +162,45 @@ struct PanelJob {
   int merged;
   int gs, ng, ring, lag;                // matrices per group, groups, ring slots (in groups), pass-2 lag (in groups)
   int* done1; int* done2; int* err;     // per-group completion counters (4 per tile), error flag
+  // batch entries per matrix of the convergence bookkeeping (cnt / nact are indexed by b / bdiv): 1, or the number
+  // of 128-column groups when the batch is the set of group-local problems of the spread schedule
+  int bdiv;
+  int counter;                          // which g_panel_tiles slot this launch adds to
+  // group mode (SL == 4): a task is (group g, output half h) of the 4-block groups {i0, i0^ga, i0^gb, i0^ga^gb},
+  // i0 = g with zero bits inserted at the pivot positions plo < phi
+  int ga, gb, plo, phi;
 };
+
+// blocks of task c: SL == 2 -> the pair of the round; SL == 4 -> the four blocks of group c >> 1.  o0/o1: the two
+// column blocks the task writes.
+template <int SL>
+__device__ __forceinline__ void task_blocks(const PanelJob& pj, int nb, int round, int c, int (&blk)[SL], int& o0,
+                                            int& o1) {
+  if constexpr (SL == 2) {
+    rr_pair_tc(nb, round, c, blk[0], blk[1]);
+    o0 = blk[0]; o1 = blk[1];
+  } else {
+    int x = c >> 1;
+    x = ((x >> pj.plo) << (pj.plo + 1)) | (x & ((1 << pj.plo) - 1));
+    x = ((x >> pj.phi) << (pj.phi + 1)) | (x & ((1 << pj.phi) - 1));
+#pragma unroll
+    for (int j = 0; j < 4; ++j) blk[j] = x ^ ((j & 1) ? pj.ga : 0) ^ ((j & 2) ? pj.gb : 0);
+    const int h = c & 1;
+    o0 = h ? blk[2] : blk[0];
+    o1 = h ? blk[3] : blk[1];
+  }
+}
 
 // tile index -> (job, matrix b, task c, row tile mt); returns false when the tile must be skipped
 struct TileInfo { int job, b, c, mt, hb, group; bool run, valid; };
 
+template <int SL>
 __device__ __forceinline__ TileInfo decode_tile(int tile, int njobs, int B, int nt, int mtiles, int sweep,
                                                 const int* __restrict__ cnt, const int* __restrict__ qflag,
                                                 const PanelJob& pj) {
   TileInfo ti;
   ti.valid = true; ti.group = 0;
-  if (pj.merged) {
+  if (SL == 2 && pj.merged) {
     // Merged schedule.  The batch is cut into groups of gs matrices; block s of the tile list interleaves the
     // pass-1 tiles of group s with the pass-2 tiles of group s - lag.  A pass-2 tile waits (done1) until every
     // pass-1 tile of its group has stored H; H lives in a ring of `ring` groups that stays in L2, so it never
@@ -202,14 +238,16 @@ __device__ __forceinline__ TileInfo decode_tile(int tile, int njobs, int B, int 
   ti.c = r / mtiles;
   ti.mt = r % mtiles;
   ti.run = true;
-  if (sweep > 0 && cnt[ti.b * JMAXS + sweep - 1] == 0) ti.run = false;            // matrix converged
+  // flags: one per task (SL == 2) or one per group = two tasks (SL == 4)
+  const int nfl = SL == 4 ? (nt >> 1) : nt, fc = SL == 4 ? (ti.c >> 1) : ti.c;
+  if (sweep > 0 && cnt[(ti.b / pj.bdiv) * JMAXS + sweep - 1] == 0) ti.run = false;   // matrix converged
   else if ((ti.job == 0 ? pj.skip_on_qflag0 : pj.skip_on_qflag1)) {
-    if (qflag[ti.b * nt + ti.c] == 0) ti.run = false;                               // in-place job: identity task
+    if (qflag[ti.b * nfl + fc] == 0) ti.run = false;                                 // in-place job: identity task
   } else {
     // ping-pong G passes: an identity task still has to be copied through, but if NO task of this matrix rotated
     // in this round, G is unchanged and both passes can be skipped for the whole matrix
     int any = 0;
-    for (int c = 0; c < nt; ++c) any |= qflag[ti.b * nt + c];
+    for (int c = 0; c < nfl; ++c) any |= qflag[ti.b * nfl + c];
     if (!any) ti.run = false;
   }
   (void)njobs;
@@ -233,6 +271,7 @@ __device__ __forceinline__ void spin_until(const int* p, int target, int* err) {
   }
 }
 
+template <int SL>
 __global__ void __maxnreg__(72) panel_update_tc_kernel(const __grid_constant__ CUtensorMap map_in0,
                                                                  const __grid_constant__ CUtensorMap map_in1,
                                                                  const __grid_constant__ CUtensorMap map_q,
@@ -249,10 +288,11 @@ __global__ void __maxnreg__(72) panel_update_tc_kernel(const __grid_constant__ C
   uint64_t* tmem_empty = tmem_full + 2;                          // epilogue -> MMA (count 128)
   uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 2);
 
-  if (sweep > 0 && cnt[B * JMAXS + sweep] == 0) return;          // every matrix converged: nothing to do
+  constexpr int SLABS = SL;                                      // K slabs per tile: the pair (2) or the group (4)
+  if (sweep > 0 && cnt[(B / pj.bdiv) * JMAXS + sweep] == 0) return;   // every matrix converged: nothing to do
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int mtiles = np / TM;
-  const int total_tiles = pj.merged ? (pj.ng + pj.lag) * 2 * pj.gs * nt * mtiles : njobs * B * nt * mtiles;
+  const int total_tiles = (SL == 2 && pj.merged) ? (pj.ng + pj.lag) * 2 * pj.gs * nt * mtiles : njobs * B * nt * mtiles;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_in0) : "memory");
@@ -279,17 +319,17 @@ __global__ void __maxnreg__(72) panel_update_tc_kernel(const __grid_constant__ C
     if (elect()) {
       int it = 0, ntiles = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const TileInfo ti = decode_tile(tile, njobs, B, nt, mtiles, sweep, cnt, qflag, pj);
+        const TileInfo ti = decode_tile<SL>(tile, njobs, B, nt, mtiles, sweep, cnt, qflag, pj);
         if (!ti.run) continue;
-        int I, J;
-        rr_pair_tc(nb, round, ti.c, I, J);
-        if (pj.merged && ti.job == 1) {
+        int blk[SL], o0, o1;
+        task_blocks<SL>(pj, nb, round, ti.c, blk, o0, o1);
+        if (SL == 2 && pj.merged && ti.job == 1) {
           // pass 2 reads what pass 1 of this group stored (generic proxy, other CTAs) through the async proxy
           spin_until(&pj.done1[ti.group], group_target(pj, ti.group, B, nt, mtiles), pj.err);
           asm volatile("fence.proxy.async;" ::: "memory");
         }
         const CUtensorMap* mp = ti.job == 0 ? &map_in0 : &map_in1;
-        const int mb = (pj.merged && ti.job == 1) ? ti.hb : ti.b;
+        const int mb = (SL == 2 && pj.merged && ti.job == 1) ? ti.hb : ti.b;
         const int qrow = (ti.b * nt + ti.c) * PM;
 #pragma unroll
         for (int slab = 0; slab < SLABS; ++slab, ++it) {
@@ -299,20 +339,21 @@ __global__ void __maxnreg__(72) panel_update_tc_kernel(const __grid_constant__ C
           uint8_t* st = smem + s * STAGE;
           bar_expect_tx(&raw_full[s], A_RAW + Q_RAW);
           // panel slab: rows [mt*128, +128) of column block I (slab 0) or J (slab 1): 16 KB contiguous in HBM
-          tma_3d(st, mp, &raw_full[s], 0, ti.mt * TM, mb * nb + (slab == 0 ? I : J));
-          // Q_c^T: 64 rows (j) x the 32 k-columns of this slab
+          tma_3d(st, mp, &raw_full[s], 0, ti.mt * TM, mb * nb + blk[slab]);
+          // Q_c^T: 64 rows (j) x the 32 k-columns of this slab (group mode: rows [64 h, 64 h + 64) of the group's
+          // 128 x 128 P^T, so qrow = (b * nt + c) * 64 holds there too)
           tma_2d(st + 2 * A_RAW, &map_q, &raw_full[s], slab * PB, qrow);
         }
         ++ntiles;
       }
-      if (ntiles > 0) atomicAdd(&g_panel_tiles[pj.skip_on_qflag0 ? 1 : 0], (unsigned long long)ntiles);
+      if (ntiles > 0) atomicAdd(&g_panel_tiles[pj.counter], (unsigned long long)ntiles);
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (elect()) {
       int it = 0, tt = 0;                              // stage counter (slabs), tile counter (accumulators)
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const TileInfo ti = decode_tile(tile, njobs, B, nt, mtiles, sweep, cnt, qflag, pj);
+        const TileInfo ti = decode_tile<SL>(tile, njobs, B, nt, mtiles, sweep, cnt, qflag, pj);
         if (!ti.run) continue;
         const int acc = tt & 1;
         const uint32_t aph = (tt >> 1) & 1;
@@ -353,7 +394,7 @@ __global__ void __maxnreg__(72) panel_update_tc_kernel(const __grid_constant__ C
     const int t = threadIdx.x - 64;
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const TileInfo ti = decode_tile(tile, njobs, B, nt, mtiles, sweep, cnt, qflag, pj);
+      const TileInfo ti = decode_tile<SL>(tile, njobs, B, nt, mtiles, sweep, cnt, qflag, pj);
       if (!ti.run) continue;
 #pragma unroll 1
       for (int slab = 0; slab < SLABS; ++slab, ++it) {
@@ -396,25 +437,25 @@ __global__ void __maxnreg__(72) panel_update_tc_kernel(const __grid_constant__ C
     const int q = warp & 3;                      // TMEM lanes [32q, 32q+32)
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const TileInfo ti = decode_tile(tile, njobs, B, nt, mtiles, sweep, cnt, qflag, pj);
+      const TileInfo ti = decode_tile<SL>(tile, njobs, B, nt, mtiles, sweep, cnt, qflag, pj);
       if (!ti.run) {
         // merged mode: a skipped tile still counts as done for the waiters of its group
-        if (pj.merged && ti.valid && lane == 0) atomicAdd(ti.job == 0 ? &pj.done1[ti.group] : &pj.done2[ti.group], 1);
+        if (SL == 2 && pj.merged && ti.valid && lane == 0) atomicAdd(ti.job == 0 ? &pj.done1[ti.group] : &pj.done2[ti.group], 1);
         continue;
       }
       const int acc = it & 1;
       const uint32_t aph = (it >> 1) & 1;
       bar_wait(&tmem_full[acc], aph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      int I, J;
-      rr_pair_tc(nb, round, ti.c, I, J);
-      if (pj.merged && ti.job == 0 && ti.group >= pj.ring) {
+      int blk[SL], I, J;
+      task_blocks<SL>(pj, nb, round, ti.c, blk, I, J);
+      if (SL == 2 && pj.merged && ti.job == 0 && ti.group >= pj.ring) {
         // the ring slot is reused: pass 2 of group - ring must have read it
         if (lane == 0) spin_until(&pj.done2[ti.group - pj.ring], group_target(pj, ti.group - pj.ring, B, nt, mtiles), pj.err);
         __syncwarp();
       }
       float* out = (ti.job == 0 ? pj.out0 : pj.out1) +
-                   int64_t((pj.merged && ti.job == 0) ? ti.hb : ti.b) * np * np;
+                   int64_t((SL == 2 && pj.merged && ti.job == 0) ? ti.hb : ti.b) * np * np;
       const bool tr = (ti.job == 0 ? pj.transposed0 : pj.transposed1) != 0;
       const int row = ti.mt * TM + q * 32 + lane;
 #pragma unroll
@@ -432,7 +473,7 @@ __global__ void __maxnreg__(72) panel_update_tc_kernel(const __grid_constant__ C
             : "r"(taddr));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         const int cblk = (half == 0 ? I : J);
-        if (debug & 2) {
+        if (SL == 2 && (debug & 2)) {
           // dump the staged panel tile as the async proxy left it (after the split): element (row r, k = half*32 + j)
           const uint8_t* abase = smem + half * STAGE;      // slab `half` of this tile sits in stage `half` (NSTAGE == SLABS)
           const int r = q * 32 + lane;
@@ -458,7 +499,7 @@ __global__ void __maxnreg__(72) panel_update_tc_kernel(const __grid_constant__ C
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       bar_arrive(&tmem_empty[acc]);
-      if (pj.merged) {
+      if (SL == 2 && pj.merged) {
         // publish this warp's stores (pass 1) / its tile's completed reads (pass 2) at device scope
         asm volatile("fence.proxy.async;" ::: "memory");
         __threadfence();
@@ -505,11 +546,12 @@ int make_map_panel(CUtensorMap* m, const float* base, int64_t B, int np) {
   R3D_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(panel) failed with %d", (int)r);
   return 0;
 }
-int make_map_q(CUtensorMap* m, const float* base, int64_t rows) {
+// rows of `pitch` floats (64: the Q^T of a block pair; 128: the P^T of a 4-block group); a box is 64 rows x 32 k-columns
+int make_map_q(CUtensorMap* m, const float* base, int64_t rows, int pitch = PM) {
   EncodeTiledFn2 enc = get_encode2();
   R3D_CHECK(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
-  const cuuint64_t gdim[2] = {(cuuint64_t)PM, (cuuint64_t)rows};
-  const cuuint64_t gstr[1] = {(cuuint64_t)PM * 4};
+  const cuuint64_t gdim[2] = {(cuuint64_t)pitch, (cuuint64_t)rows};
+  const cuuint64_t gstr[1] = {(cuuint64_t)pitch * 4};
   const cuuint32_t box[2] = {32, PM};
   const cuuint32_t es[2] = {1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, es,
@@ -526,22 +568,31 @@ bool panel_tc_supported(int np) { return np % TM == 0; }
 int panel_tc_prepare(PanelTc* h, float* G, float* H, float* V, const float* Qb0, const float* Qb1, int64_t B,
                      int np) {
   h->G = G; h->H = H; h->V = V; h->B = B; h->np = np; h->nb = np / PB; h->nt = np / PM;
+  h->bdiv = 1; h->local = 0;
   if (int e = make_map_panel(&h->map_g, G, B, np)) return e;
-  if (int e = make_map_panel(&h->map_h, H, B, np)) return e;
+  if (H != nullptr) { if (int e = make_map_panel(&h->map_h, H, B, np)) return e; }
   if (int e = make_map_panel(&h->map_v, V, B, np)) return e;
   if (int e = make_map_q(&h->map_q[0], Qb0, B * h->nt * PM)) return e;
   if (int e = make_map_q(&h->map_q[1], Qb1, B * h->nt * PM)) return e;
   static bool attr_done[kMaxDevices] = {};
   if (per_device_once(attr_done)) {
-    R3D_CUDA(cudaFuncSetAttribute(panel_update_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    R3D_CUDA(cudaFuncSetAttribute(panel_update_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    R3D_CUDA(cudaFuncSetAttribute(panel_update_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
   }
   return 0;
 }
 
-int panel_tiles_read(unsigned long long out[2], int reset) {
-  R3D_CUDA(cudaMemcpyFromSymbol(out, g_panel_tiles, sizeof(unsigned long long) * 2));
+// P^T of the 4-block groups of the spread schedule: (B * np/128 groups, 128, 128) fp32 row-major, double-buffered
+int panel_tc_prepare_groups(PanelTc* h, const float* Pt0, const float* Pt1) {
+  const int64_t rows = h->B * (h->np / 128) * 128;
+  if (int e = make_map_q(&h->map_p[0], Pt0, rows, 128)) return e;
+  return make_map_q(&h->map_p[1], Pt1, rows, 128);
+}
+
+int panel_tiles_read(unsigned long long out[3], int reset) {
+  R3D_CUDA(cudaMemcpyFromSymbol(out, g_panel_tiles, sizeof(unsigned long long) * 3));
   if (reset) {
-    const unsigned long long z[2] = {0, 0};
+    const unsigned long long z[3] = {0, 0, 0};
     R3D_CUDA(cudaMemcpyToSymbol(g_panel_tiles, z, sizeof(z)));
   }
   return 0;
@@ -552,17 +603,25 @@ int g_panel_grid_cap = 0;
 
 static int panel_launch(PanelTc* h, const CUtensorMap& in, const CUtensorMap& q, float* out, int transposed,
                         int skip_on_qflag, int round, int sweep, const int* cnt, const int* qflag, int stage_id,
-                        cudaStream_t st) {
+                        cudaStream_t st, const PanelGroups* grp = nullptr) {
   const int mtiles = h->np / TM;
   const int64_t tiles = h->B * h->nt * mtiles;
   PanelJob pj{};
   pj.out0 = out; pj.transposed0 = transposed; pj.skip_on_qflag0 = skip_on_qflag;
   pj.out1 = nullptr; pj.transposed1 = 0; pj.skip_on_qflag1 = 0;
+  pj.bdiv = h->bdiv;
+  pj.counter = h->local ? 2 : (skip_on_qflag ? 1 : 0);
   int grid = (int)std::min<int64_t>(tiles, 2 * kNumSMs);
   if (g_panel_grid_cap > 0) grid = std::min(grid, g_panel_grid_cap);
   StageScope scope(stage_id, st);
-  panel_update_tc_kernel<<<grid, kPanelThreads, SMEM_TOTAL, st>>>(in, in, q, pj, 1, (int)h->B, h->np, h->nb, h->nt, round, sweep,
-                                                        cnt, qflag, g_panel_debug);
+  if (grp != nullptr) {
+    pj.ga = grp->ga; pj.gb = grp->gb; pj.plo = grp->plo; pj.phi = grp->phi;
+    panel_update_tc_kernel<4><<<grid, kPanelThreads, SMEM_TOTAL, st>>>(in, in, q, pj, 1, (int)h->B, h->np, h->nb, h->nt, 0,
+                                                                       sweep, cnt, qflag, g_panel_debug);
+  } else {
+    panel_update_tc_kernel<2><<<grid, kPanelThreads, SMEM_TOTAL, st>>>(in, in, q, pj, 1, (int)h->B, h->np, h->nb, h->nt,
+                                                                       round, sweep, cnt, qflag, g_panel_debug);
+  }
   R3D_LAUNCH_CHECK();
   return 0;
 }
@@ -584,18 +643,19 @@ static int panel_launch_merged(PanelTc* h, const CUtensorMap& q, int round, int 
   pj.lag = 2;
   if (pj.ring <= pj.lag) pj.ring = pj.ng;             // tiny batches: no slot reuse at all
   pj.done1 = sync; pj.done2 = sync + kPanelSyncGroups; pj.err = sync + 2 * kPanelSyncGroups;
+  pj.bdiv = 1; pj.counter = 0;
   const int64_t tiles = int64_t(pj.ng + pj.lag) * 2 * pj.gs * per_mat;
   int grid = (int)std::min<int64_t>(tiles, 2 * kNumSMs);
   if (g_panel_grid_cap > 0) grid = std::min(grid, g_panel_grid_cap);
   StageScope scope(ST_JACOBI_UPDATE, st);
-  panel_update_tc_kernel<<<grid, kPanelThreads, SMEM_TOTAL, st>>>(h->map_g, h->map_h, q, pj, 2, (int)h->B, h->np, h->nb, h->nt,
+  panel_update_tc_kernel<2><<<grid, kPanelThreads, SMEM_TOTAL, st>>>(h->map_g, h->map_h, q, pj, 2, (int)h->B, h->np, h->nb, h->nt,
                                                         round, sweep, cnt, qflag, g_panel_debug);
   R3D_LAUNCH_CHECK();
   return 0;
 }
 
 bool panel_tc_merged_ok(const PanelTc* h) {
-  if (options().panel_merged == 0) return false;
+  if (options().panel_merged == 0 || h->bdiv != 1) return false;
   const int64_t mat_bytes = int64_t(h->np) * h->np * 4;
   const int64_t gs = std::max<int64_t>(1, std::min<int64_t>(h->B, (int64_t(options().panel_group_mb) << 20) / mat_bytes));
   return (h->B + gs - 1) / gs <= kPanelSyncGroups;
@@ -606,14 +666,29 @@ int panel_tc_update_g(PanelTc* h, int qbuf, int round, int sweep, const int* cnt
   if (sync != nullptr && panel_tc_merged_ok(h))
     return panel_launch_merged(h, h->map_q[qbuf], round, sweep, cnt, qflag, sync, st);
   // pass 1: H^T = (G Q)^T (transposed store);  pass 2: G = H^T Q.  Identity tasks cannot be skipped (ping-pong).
-  if (int e = panel_launch(h, h->map_g, h->map_q[qbuf], h->H, 1, 0, round, sweep, cnt, qflag, ST_JACOBI_UPDATE, st))
+  const int sid = h->local ? ST_JACOBI_LOCAL : ST_JACOBI_UPDATE;
+  if (int e = panel_launch(h, h->map_g, h->map_q[qbuf], h->H, 1, 0, round, sweep, cnt, qflag, sid, st))
     return e;
   // G' is symmetric, so pass 2 may also use the transposed store (one full 128-byte line per store instruction)
-  return panel_launch(h, h->map_h, h->map_q[qbuf], h->G, 1, 0, round, sweep, cnt, qflag, ST_JACOBI_UPDATE, st);
+  return panel_launch(h, h->map_h, h->map_q[qbuf], h->G, 1, 0, round, sweep, cnt, qflag, sid, st);
 }
 
 int panel_tc_update_v(PanelTc* h, int qbuf, int round, int sweep, const int* cnt, const int* qflag, cudaStream_t st) {
-  return panel_launch(h, h->map_v, h->map_q[qbuf], h->V, 0, 1, round, sweep, cnt, qflag, ST_JACOBI_VUPDATE, st);
+  return panel_launch(h, h->map_v, h->map_q[qbuf], h->V, 0, 1, round, sweep, cnt, qflag,
+                      h->local ? ST_JACOBI_LOCAL : ST_JACOBI_VUPDATE, st);
+}
+
+// The same two updates with the 128 x 128 group products P of a super-round (K = N = 128): `gflag` holds one flag per
+// (matrix, group).
+int panel_tc_update_g_groups(PanelTc* h, int pbuf, const PanelGroups& grp, int sweep, const int* cnt, const int* gflag,
+                             cudaStream_t st) {
+  if (int e = panel_launch(h, h->map_g, h->map_p[pbuf], h->H, 1, 0, 0, sweep, cnt, gflag, ST_JACOBI_UPDATE, st, &grp))
+    return e;
+  return panel_launch(h, h->map_h, h->map_p[pbuf], h->G, 1, 0, 0, sweep, cnt, gflag, ST_JACOBI_UPDATE, st, &grp);
+}
+int panel_tc_update_v_groups(PanelTc* h, int pbuf, const PanelGroups& grp, int sweep, const int* cnt, const int* gflag,
+                             cudaStream_t st) {
+  return panel_launch(h, h->map_v, h->map_p[pbuf], h->V, 0, 1, 0, sweep, cnt, gflag, ST_JACOBI_VUPDATE, st, &grp);
 }
 
 }  // namespace r3d

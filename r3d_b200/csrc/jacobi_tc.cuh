@@ -7,10 +7,17 @@
 namespace r3d {
 struct PanelTc {
   CUtensorMap map_g, map_h, map_v, map_q[2];   // Q^T is double-buffered (round parity)
+  CUtensorMap map_p[2];                        // spread schedule: P^T of the 4-block groups, double-buffered
+  CUtensorMap map_g32;                         // one-pass symmetric update: 32-row boxes of G (jacobi_sym.cu)
   float *G, *H, *V;
   int64_t B;
   int np, nb, nt;
+  int bdiv;     // batch entries per matrix of the convergence bookkeeping (> 1: the batch is the group-local problems)
+  int local;    // 1: group-local problem (stage / tile counters are booked separately)
 };
+// One super-round of the spread schedule: the block index set is partitioned into the cosets {i0, i0^ga, i0^gb,
+// i0^ga^gb} of a two-dimensional subspace of GF(2)^k; plo < phi are the pivot bit positions of the subspace.
+struct PanelGroups { int ga, gb, plo, phi; };
 bool panel_tc_supported(int np);
 int panel_tc_prepare(PanelTc* h, float* G, float* H, float* V, const float* Qb0, const float* Qb1, int64_t B, int np);
 // G <- Q^T G Q for one round (two launches on `st`): pass 1 writes (G Q)^T into H, pass 2 H Q back into G.
@@ -21,8 +28,21 @@ int panel_tc_update_g(PanelTc* h, int qbuf, int round, int sweep, const int* cnt
 // V <- V Q for one round (one launch on `st`); independent of the G update and of the next inner solve.
 int panel_tc_update_v(PanelTc* h, int qbuf, int round, int sweep, const int* cnt, const int* qflag, cudaStream_t st);
 
-// Panel tiles (128 rows x 64 columns, 32 KB in + 32 KB out) processed since the last reset: [0] G passes, [1] V passes.
-int panel_tiles_read(unsigned long long out[2], int reset);
+// One-pass symmetric update (jacobi_sym.cu): G <- Q^T G Q in place, upper block triangle + mirrored store, one launch.
+bool panel_sym_supported(int np);
+int panel_sym_prepare(PanelTc* h);
+int panel_sym_update_g(PanelTc* h, int qbuf, int round, int sweep, const int* cnt, const int* qflag, cudaStream_t st);
+int panel_sym_units_read(unsigned long long* out, int reset);   // 64 KB units of HBM traffic processed
+
+int panel_tc_prepare_groups(PanelTc* h, const float* Pt0, const float* Pt1);
+int panel_tc_update_g_groups(PanelTc* h, int pbuf, const PanelGroups& grp, int sweep, const int* cnt, const int* gflag,
+                             cudaStream_t st);
+int panel_tc_update_v_groups(PanelTc* h, int pbuf, const PanelGroups& grp, int sweep, const int* cnt, const int* gflag,
+                             cudaStream_t st);
+
+// Panel tiles (128 rows x 64 output columns, 32 KB in + 32 KB out of HBM traffic) processed since the last reset:
+// [0] G passes, [1] V passes, [2] tiles of the group-local (L2-resident) problems of the spread schedule.
+int panel_tiles_read(unsigned long long out[3], int reset);
 
 struct Options {
   int jacobi_update_tc = 1;     // 1: tcgen05 3xTF32 panel update, 0: SIMT fp32 tile update
@@ -55,6 +75,13 @@ struct Options {
   int jacobi_v_after_g = 0;     // 0: V(r) starts right after inner(r) and runs beside the G passes (58.9 ms); 1: V(r) starts after the
                                 //    G passes of round r and runs beside inner(r+1) (60.1 ms with the register-resident inner solver)
   int jacobi_overlap_v = 1;     // run V <- V Q on a side stream, overlapped with the next inner solve
+  int panel_sym = 1;            // 1: G <- Q^T G Q as ONE in-place pass over the upper block triangle with mirrored stores
+                                //    (jacobi_sym.cu: 0.56 n^2 read + n^2 written per round); 0: two passes through the scratch
+                                //    matrix H (jacobi_tc.cu: 2 n^2 read + 2 n^2 written)
+  int jacobi_schedule = 0;      // 1: spread schedule where the block count allows it (power of two >= 8): the rounds of a sweep
+                                //    are the XOR matchings, grouped three at a time into super-rounds that stay inside 4-block
+                                //    (128-column) groups, so G and V are streamed once per super-round instead of once per round;
+                                //    0: circle-method round robin, one panel update per round
 };
 Options& options();
 }  // namespace r3d

@@ -10,6 +10,7 @@ def rr_pair(m, r, t):
     return min(x, y), max(x, y)
 def run(B, npad, rnd, seed=0, simpleQ=False, debug=0, pattern=False):
     _lib.set_option("panel_debug", debug)
+    _lib.set_option("panel_sym", SYM)
     rng = np.random.default_rng(seed)
     nb, nt = npad // 32, npad // 64
     if pattern:
@@ -51,7 +52,13 @@ def run(B, npad, rnd, seed=0, simpleQ=False, debug=0, pattern=False):
     if pattern:
         print("  V out [0,:4,:6]:\n", Vd.cpu().numpy()[0, :4, :6])
         print("  V out [0,64:66,32:38]:\n", Vd.cpu().numpy()[0, 64:66, 32:38])
+SYM = 1
 which = sys.argv[1] if len(sys.argv) > 1 else "a"
+if which == "sym":      # one-pass symmetric G update (jacobi_sym.cu): H is not written, G and V are
+    for (B, npad, rnd) in ((1, 128, 0), (1, 256, 1), (2, 256, 2), (3, 512, 4), (5, 384, 3)):
+        run(B, npad, rnd)
+    sys.exit(0)
+SYM = 0
 if which == "a":
     run(1, 128, 0, simpleQ=True, debug=1 | 4, pattern=True)  # MMA hi*hi only on raw data
     run(1, 128, 0, simpleQ=False, debug=1)

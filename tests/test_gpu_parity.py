@@ -712,14 +712,17 @@ def test_fuser_step_cuda_graph_capture(dev):
     assert torch.equal(step.er, er_graph)
 
 
-@pytest.mark.parametrize("opts", [{"panel_merged": 1}, {"jacobi_inner_regs": 0}, {"jacobi_update_tc": 0},
-                                  {"gemm_tc": 0}, {"jacobi_overlap_v": 0}, {"jacobi_chunks": 2}])
+@pytest.mark.parametrize("opts", [{"panel_merged": 1, "panel_sym": 0}, {"jacobi_inner_regs": 0},
+                                  {"jacobi_update_tc": 0}, {"gemm_tc": 0}, {"jacobi_overlap_v": 0},
+                                  {"jacobi_chunks": 2}, {"panel_sym": 0}, {"jacobi_schedule": 1},
+                                  {"jacobi_schedule": 1, "panel_sym": 0},
+                                  {"jacobi_schedule": 1, "jacobi_inner_regs": 0}])
 def test_alternative_kernel_paths_agree(opts, dev):
     """Every selectable kernel path (merged panel schedule, shared-memory inner solver, SIMT panel update, SIMT GEMMs,
-    no side stream, two chunks) must reproduce the default path's effective rank and gradient."""
+    no side stream, two chunks, two-pass panel update through H, spread schedule) must reproduce the default path's effective rank and gradient."""
     from r3d_b200 import ops, _lib
     defaults = {"panel_merged": 0, "jacobi_inner_regs": 1, "jacobi_update_tc": 1, "gemm_tc": 1, "jacobi_overlap_v": 1,
-                "jacobi_chunks": 1}
+                "jacobi_chunks": 1, "jacobi_schedule": 0, "panel_sym": 1}
     x = _spectra("relu", 6, 256, 256, 77)
     ref = EO.erank(x)
     gref = EO.erank_bwd(x, np.ones(6, np.float32))

@@ -31,7 +31,7 @@ def test_library_exports_every_header_symbol():
     # and the ctypes binding covers the same set (no drift between header and host side)
     assert set(_lib.SIGNATURES) == set(syms), set(_lib.SIGNATURES) ^ set(syms)
     L = _lib.lib()
-    assert L.r3d_abi_version() == 1
+    assert L.r3d_abi_version() == 2
     assert L.r3d_score_workspace_floats(2048, 512) > 0          # size queries need no GPU
     assert L.r3d_erank_workspace_bytes(2, 64, 128, 0) > 0
     assert L.r3d_profile_num_stages() > 10
