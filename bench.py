@@ -501,7 +501,8 @@ def main_ours(args):
     tiles = _lib.panel_tiles(reset=True)
     _lib.profile_enable(False)
     _lib.launch_count(reset=True)
-    sweeps = step.sweeps.float().mean().item()
+    sweeps = step.sweeps.abs().float().mean().item()
+    not_converged = int((step.sweeps < 0).sum().item())
     er_mean = step.er.mean().item()
     # ---- end to end
     e2e_state["steps"] = 2
@@ -537,7 +538,7 @@ def main_ours(args):
                                "erank(rgb,depth) + score/bottom-k/exchange fwd + exchange/erank bwd",
                    "B_per_gpu": B, "T": T, "C": C, "global_batch": B * world, "parallelism": f"dp{world}",
                    "l2": f"{NSETS} rotating input+grad sets ({NSETS * 2 * 2 * B * T * C * 2 / 1e6:.0f} MB) > 126 MB L2",
-                   "jacobi_sweeps_mean": sweeps, "erank_mean": er_mean, "gram": args.gram},
+                   "jacobi_sweeps_mean": sweeps, "jacobi_not_converged": not_converged, "erank_mean": er_mean, "gram": args.gram},
         "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": int(2 * B * T * C * 2), "d2h_bytes_per_step": int(2 * B * 4)},
         "gpu_launches": int(launches),

@@ -97,6 +97,11 @@ int r3d_channel_score_partial(const void* rgb, const void* depth, int64_t rows, 
  * all-reduced across ranks in global-score mode; score_out (2, C) = sums / rows. */
 int r3d_score_finalize(const float* partial, int64_t rows, int64_t C, float* sums_out, float* score_out,
                        void* stream);
+/* The packed statistic of the batch-sharded path in one launch, no host involvement:
+ * packed_out (2C + 2) = [sum|rgb| (C) | sum|depth| (C) | sum of er[0..n_er) | rows].  `er` may be NULL (the sum is
+ * then 0).  This buffer is what global-score mode all-reduces; r3d_bottomk_scaled consumes it. */
+int r3d_score_finalize_packed(const float* partial, int64_t rows, int64_t C, const float* er, int64_t n_er,
+                              float* packed_out, void* stream);
 
 /* ---- a4: bottom-k -----------------------------------------------------------
  * Replaces  torch.topk(score, k, dim=-1, largest=False)[1]  for `nvec` score
@@ -104,6 +109,11 @@ int r3d_score_finalize(const float* partial, int64_t rows, int64_t C, float* sum
  * ..._batchnormalization.py:58-60.  score: (nvec, C) float; idx_out: (nvec, k)
  * int64, ascending by score, ties -> lower index, NaN last.  C <= 8192. */
 int r3d_bottomk(const float* score, int nvec, int64_t C, int64_t k, int64_t* idx_out, void* stream);
+/* Same selection on  sums[i] / *denom  (IEEE fp32 division of the column sums by the -- possibly all-reduced -- row
+ * count, i.e. exactly the mean of tokenfusion.py:49-50) without a separate elementwise kernel.  score_out: optional
+ * (nvec, C) quotient. */
+int r3d_bottomk_scaled(const float* sums, int nvec, int64_t C, int64_t k, const float* denom, int64_t* idx_out,
+                       float* score_out, void* stream);
 
 /* ---- a3: BatchNorm1d front end of the BN variant ------------------------------
  * Replaces  bn(x.permute(0,2,1)).permute(0,2,1)  batch statistics:
@@ -156,8 +166,11 @@ size_t r3d_erank_workspace_bytes(int64_t B, int64_t T, int64_t C, int dtype);
 /* Forward: erank_out (B) float, sigma_out (B, n) float (solver order, not sorted),
  * U_out (B, n, n) float eigenvectors of the Gram (column j <-> sigma j),
  * Y_out (B, n, m) float = U^T A with A the (n, m) short-side-major view of x.
- * sweeps_out: optional (B) int32 Jacobi sweeps used.  gram_impl: 0 = tcgen05
- * tensor-core path, 1 = SIMT fp32 path (kept for A/B accuracy checks). */
+ * sweeps_out: optional (B) int32 Jacobi sweeps used, both passes of the two-pass solver added up; NEGATIVE when the
+ * final pass ran into its sweep cap while still rotating (not converged: sigma / the gradient are less accurate than
+ * the bounds DESIGN.md states; raise "erank_pass2_sweeps" / "jacobi_max_sweeps").  The same holds for the sweeps
+ * r3d_jacobi_eigh reports.  gram_impl: 0 = tcgen05 tensor-core path, 1 = SIMT fp32 path (kept for A/B accuracy
+ * checks). */
 int r3d_erank_fwd(const void* x, int64_t B, int64_t T, int64_t C, int dtype, float rtol, int gram_impl,
                   void* workspace, float* erank_out, float* sigma_out, float* U_out, float* Y_out,
                   int32_t* sweeps_out, void* stream);
@@ -175,6 +188,27 @@ size_t r3d_jacobi_workspace_bytes(int64_t B, int64_t n);
 /* a13: per-token (short-side) informativeness  s_t = sum_j p_j U[t,j]^2. */
 int r3d_token_informativeness(const float* sigma, const float* U, int64_t B, int64_t n, float rtol,
                               float* score_out, void* stream);
+
+/* ---- N1: token-axis selection (north_star kernels 3-6) -----------------------------------------------------
+ * No reference symbol: the reference ships only the channel exchange (model/futr_safuser_tokenfusion.py:33-66,
+ * SURVEY.md F2) and describes the token form in prose (README.md:13).  PARITY UNPINNED; oracle:
+ * oracle/fuser_oracle.py:token_fusion_tokens.
+ * r3d_token_scores: score_out (B, T) = sum_j p_j u_{tj}^2 over the LEFT singular vectors of every (T, C) sample, from
+ * the sigma / U / Y that r3d_erank_fwd saved (U when T < C, the rows of Y when T >= C), kept singular values only.
+ * r3d_token_mask: per-sample index lists idx_r, idx_d (B, k) int64 (from r3d_bottomk on the scores) -> mask_out (B, T)
+ * bytes, bit 0 = token in S_rgb(b), bit 1 = token in S_depth(b).  T <= 8192.
+ * r3d_token_exchange_fwd: out (rows, 2, C): out[r, 0] = bit0 ? depth[r] : rgb[r], out[r, 1] = bit1 ? rgb[r] : depth[r]
+ * (rows = B*T; the token analogue of tokenfusion.py:56-62).  2 N s read + 2 N s written.
+ * r3d_token_exchange_bwd: g (rows, 2, C) -> d_rgb, d_depth (rows, C): masked select per token; the index sets hold no
+ * duplicates, so no atomics / scatter-add are needed. */
+int r3d_token_scores(const float* sigma, const float* U, const float* Y, int64_t B, int64_t T, int64_t C, float rtol,
+                     float* score_out, void* stream);
+int r3d_token_mask(const int64_t* idx_r, const int64_t* idx_d, int64_t B, int64_t T, int64_t k, uint8_t* mask_out,
+                   void* stream);
+int r3d_token_exchange_fwd(const void* rgb, const void* depth, const uint8_t* mask, void* out, int64_t rows, int64_t C,
+                           int dtype, void* stream);
+int r3d_token_exchange_bwd(const void* g, const uint8_t* mask, void* d_rgb, void* d_depth, int64_t rows, int64_t C,
+                           int dtype, void* stream);
 
 /* ---- f1 (next row, first step): row LayerNorm of the fuser Block ------------------
  * Replaces the three nn.LayerNorm of a fuser call and their autograd backward:

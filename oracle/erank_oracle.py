@@ -95,3 +95,13 @@ def token_informativeness(x: np.ndarray, rtol: float = DEFAULT_RTOL) -> np.ndarr
     if T <= C:
         return np.einsum("btj,bj->bt", U ** 2, p)
     return np.einsum("bjc,bj->bc", Vt ** 2, p)
+
+
+def token_scores(x: np.ndarray, rtol: float = DEFAULT_RTOL) -> np.ndarray:
+    """(B, T): informativeness of every TOKEN, whichever side is shorter -- s_t = sum_j p_j u_{tj}^2 with u_j the left
+    singular vectors of the (T, C) sample (north_star kernel 3; no reference symbol, unpinned).  Sums to 1 over t."""
+    x = np.asarray(x, dtype=np.float64)
+    U, s, Vt = np.linalg.svd(x, full_matrices=False)
+    er, H, S, keep = erank_from_sigma(s, rtol)
+    p = np.where(keep, s, 0.0) / np.where(S > 0, S, 1.0)[:, None]
+    return np.einsum("btj,bj->bt", U ** 2, p)

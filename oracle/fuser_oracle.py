@@ -316,3 +316,38 @@ def fuser_forward(variant, rgb, depth, mode, params, num_heads, depth_blocks=1, 
         # torch.stack(attn_weights).transpose(0, 1): (B, depth, T, heads, 2, 2)
         return y, np.stack(attns).transpose(1, 0, 2, 3, 4, 5).astype(np.float32)
     return y
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Token-axis selection (north_star kernels 3-6).  NO reference symbol: the reference ships the channel exchange only
+#  and describes the token form in prose (README.md:13).  PARITY UNPINNED -- this restates the
+# definition r3d_b200 fixes: per sample, the k = T // 4 tokens with the lowest spectral informativeness
+# (oracle/erank_oracle.py:token_scores; ties -> lower token index) of a modality are replaced by the other modality's
+# tokens at the same positions; output stacked (B, T, 2, C) like tokenfusion.py:62.
+# ---------------------------------------------------------------------------------------------------------
+def token_fusion_tokens(rgb, depth, k=None, rtol=1e-4, scores=None, return_indices=False):
+    from . import erank_oracle as EO
+    rgb, depth = np.asarray(rgb), np.asarray(depth)
+    B, T, C = rgb.shape
+    k = T // 4 if k is None else k
+    s_r, s_d = scores if scores is not None else (EO.token_scores(rgb, rtol), EO.token_scores(depth, rtol))
+    idx_r = np.stack([bottomk(np.asarray(s_r[b], np.float32), k) for b in range(B)]) if B else np.zeros((0, k), np.int64)
+    idx_d = np.stack([bottomk(np.asarray(s_d[b], np.float32), k) for b in range(B)]) if B else np.zeros((0, k), np.int64)
+    ex_r, ex_d = rgb.copy(), depth.copy()
+    for b in range(B):
+        ex_r[b, idx_r[b]] = depth[b, idx_r[b]]
+        ex_d[b, idx_d[b]] = rgb[b, idx_d[b]]
+    out = np.stack([ex_r, ex_d], axis=2)
+    return (out, idx_r, idx_d) if return_indices else out
+
+
+def token_exchange_bwd(g, idx_r, idx_d):
+    """g (B, T, 2, C) -> (d_rgb, d_depth): masked select per sample (no duplicates inside an index set)."""
+    g = np.asarray(g)
+    B, T, _, C = g.shape
+    g_r, g_d = g[:, :, 0], g[:, :, 1]
+    m_r = np.zeros((B, T, 1), g.dtype); m_d = np.zeros((B, T, 1), g.dtype)
+    for b in range(B):
+        m_r[b, idx_r[b]] = 1
+        m_d[b, idx_d[b]] = 1
+    return g_r * (1 - m_r) + g_d * m_d, g_d * (1 - m_d) + g_r * m_r

@@ -31,6 +31,8 @@ SIGNATURES = {
     "r3d_channel_score_partial": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p]),
     "r3d_score_finalize": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
     "r3d_bottomk": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p]),
+    "r3d_score_finalize_packed": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p]),
+    "r3d_bottomk_scaled": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "r3d_bn_workspace_floats": (c_size_t, [c_int64, c_int64]),
     "r3d_bn_stats": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     "r3d_exchange_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int,
@@ -51,6 +53,10 @@ SIGNATURES = {
                                 c_void_p]),
     "r3d_jacobi_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "r3d_token_informativeness": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_float, c_void_p, c_void_p]),
+    "r3d_token_scores": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_float, c_void_p, c_void_p]),
+    "r3d_token_mask": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p]),
+    "r3d_token_exchange_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p]),
+    "r3d_token_exchange_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p]),
     "r3d_panel_tiles": (c_int, [c_void_p, c_int]),
     "r3d_stream_sets_created": (c_int, []),
     "r3d_ln_bwd_workspace_floats": (c_size_t, [c_int64, c_int64]),

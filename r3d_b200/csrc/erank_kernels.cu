@@ -354,6 +354,25 @@ __global__ void __launch_bounds__(256, 5) jacobi_inner_kernel(float* __restrict_
   }
   const float nu_abs = nu[bm];
   __syncthreads();
+  {
+    // Early out: when no pair of this visit passes the rotation test on the initial block, the first step rotates
+    // nothing, the block stays as it is, and so does every later step -- the visit is the identity.  Typical for the
+    // last sweep of a pass and for the null space of rank-deficient samples.
+    int any = 0;
+    for (int e = tid; e < JM * JM; e += 256) {
+      const int i = e / JM, j = e % JM;
+      if (i < j && (generic || (i < JB && j >= JB))) {
+        const float v = S[i][j];
+        any |= (v != 0.f) && (fabsf(v) > tol * sqrtf(fabsf(S[i][i] * S[j][j])));
+      }
+    }
+    if (!__syncthreads_or(any)) {
+      float* qo = Qb + (int64_t(b) * nt + t) * JM * JM;
+      for (int e = tid; e < JM * JM; e += 256) qo[e] = (e / JM == e % JM) ? 1.f : 0.f;
+      if (tid == 0) qflag[b * nt + t] = 0;
+      return;
+    }
+  }
 
   int sig_total = 0;
   for (int it = 0; it < max_inner; ++it) {
@@ -584,6 +603,29 @@ __global__ void __launch_bounds__(256, 4) jacobi_inner_cross_kernel(float* __res
     }
   }
   const float nu_abs = nu[bm], tol2 = tol * tol;
+  {
+    // Early out (see jacobi_inner_kernel): the thread's four TR entries are cross pairs (a, 32 + c), and the 256
+    // threads together hold all 1024 of them; if none passes the rotation test, the whole visit is the identity.
+    int any = 0;
+#pragma unroll
+    for (int ra = 0; ra < 2; ++ra)
+#pragma unroll
+      for (int rb = 0; rb < 2; ++rb) {
+        const int a = 2 * A + ra, v = JB + 2 * Bc + rb;
+        const float x = TR[ra][rb];
+        any |= x * x > tol2 * fabsf(S[a][a] * S[v][v]);
+      }
+    if (!__syncthreads_or(any)) {
+      float4* qo = reinterpret_cast<float4*>(Qb + (int64_t(b) * nt + t) * JM * JM);
+#pragma unroll
+      for (int u = 0; u < JM * JM / 4 / 256; ++u) {
+        const int e = tid + u * 256, i = e / (JM / 4), j4 = (e % (JM / 4)) * 4;
+        qo[e] = make_float4(i == j4 ? 1.f : 0.f, i == j4 + 1 ? 1.f : 0.f, i == j4 + 2 ? 1.f : 0.f, i == j4 + 3 ? 1.f : 0.f);
+      }
+      if (tid == 0) qflag[b * nt + t] = 0;
+      return;
+    }
+  }
   const bool rot_warp = (warp & 3) == 0;            // warps 0 and 4 hold the diagonal pair blocks (D == 0) ...
   const bool rot_lane = rot_warp && (lane & 8) == 0; // ... in lanes with D1 == 0; lane bit 2 (D0) picks the rotation
   const int rsel = (lane >> 2) & 1;
@@ -956,7 +998,7 @@ __global__ void __launch_bounds__(256) jacobi_extract_kernel(const float* __rest
   if (blockIdx.x == 0 && threadIdx.x == 0 && sweeps) {
     int s = 0;
     while (s < max_sweeps && cnt[b * JMAX_SWEEPS + s] != 0) ++s;
-    sweeps[b] = s + (s < max_sweeps ? 1 : 0);
+    sweeps[b] = s < max_sweeps ? s + 1 : -max_sweeps;    // negative: every sweep up to the cap still rotated (not converged)
   }
 }
 
@@ -1008,7 +1050,7 @@ __global__ void __launch_bounds__(256) jacobi_extract_cols_kernel(const float* _
   if (ib == 0 && threadIdx.x == 0 && sweeps) {
     int s = 0;
     while (s < max_sweeps && cnt[b * JMAX_SWEEPS + s] != 0) ++s;
-    sweeps[b] = s + (s < max_sweeps ? 1 : 0);
+    sweeps[b] = s < max_sweeps ? s + 1 : -max_sweeps;    // negative: every sweep up to the cap still rotated (not converged)
   }
 }
 
@@ -1032,6 +1074,15 @@ __global__ void __launch_bounds__(256) row_sigma_kernel(const float* __restrict_
     su += __shfl_xor_sync(0xffffffffu, su, o);
   }
   if (lane == 0) sigma[row] = (su > 0.f) ? sqrtf(sy / su) : 0.f;
+}
+
+// two-pass solver: total sweeps of both passes; negative when the FINAL pass hit its cap (the first pass may hit its
+// cap by design -- whatever it leaves, the second pass removes)
+__global__ void sweeps_merge_kernel(int32_t* __restrict__ sweeps, const int32_t* __restrict__ sweeps2, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int s1 = abs(sweeps[b]), s2 = sweeps2[b];
+  sweeps[b] = s2 < 0 ? -(s1 - s2) : (s1 + s2);
 }
 
 // block-wide reductions for the per-sample spectrum kernels (blockDim = 256)
@@ -1189,6 +1240,7 @@ extern "C" int r3d_set_option(const char* key, double value) {
   else if (k == "erank_pass1_sweeps") options().erank_pass1_sweeps = (int)value;
   else if (k == "jacobi_tol_pass1") options().jacobi_tol_pass1 = (float)value;
   else if (k == "jacobi_nu_pass1") options().jacobi_nu_pass1 = (float)value;
+  else if (k == "jacobi_nu_pass2") options().jacobi_nu_pass2 = (float)value;
   else if (k == "jacobi_inner_regs") options().jacobi_inner_regs = (int)value;
   else if (k == "panel_merged") options().panel_merged = (int)value;
   else if (k == "row_chunk_mult") g_row_chunk_mult = std::max(1, std::min(16, (int)value));
@@ -1290,7 +1342,8 @@ static int jacobi_run_chunked(const float* G, int64_t B, int64_t n, void* worksp
 // absolute error of an fp32 Gram (eps * lambda_max), which is large relative to the smallest singular directions.
 // G2 = Y Y^T is nearly diagonal and GRADED (its small entries are represented to fp32 relative accuracy), which
 // two-sided Jacobi resolves to relative accuracy (Demmel-Veselic): G2 = V2^T diag V2, then U <- V2 U, Y <- V2 Y.
-static int second_pass_tc(const ErankWs& w, int64_t B, int64_t n, int64_t m, float* U, float* Y, cudaStream_t st) {
+static int second_pass_tc(const ErankWs& w, int64_t B, int64_t n, int64_t m, float* U, float* Y, int32_t* sweeps2,
+                          cudaStream_t st) {
   if (int e = split_planes(Y, R3D_F32, w.Ypl, B * n * m, 3, m, nullptr, st)) return e;
   {
     R3D_STAGE(ST_GRAM, st);
@@ -1301,7 +1354,7 @@ static int second_pass_tc(const ErankWs& w, int64_t B, int64_t n, int64_t m, flo
     g.out_mode = 0; g.C = w.G; g.ldc = n; g.strideC = n * n;
     if (int e = pgemm_launch(g, st)) return e;
   }
-  if (int e = jacobi_run_chunked(w.G, B, n, w.jws, nullptr, w.U2, nullptr, options().erank_pass2_sweeps, st)) return e;
+  if (int e = jacobi_run_chunked(w.G, B, n, w.jws, nullptr, w.U2, sweeps2, options().erank_pass2_sweeps, st, -1.f)) return e;
   R3D_STAGE(ST_REFINE_Y, st);
   if (int e = split_planes(w.U2, R3D_F32, w.U2pl, B * n * n, 3, n, nullptr, st)) return e;
   if (int e = split_planes(U, R3D_F32, w.Upl, B * n * n, 3, n, nullptr, st)) return e;
@@ -1318,13 +1371,14 @@ static int second_pass_tc(const ErankWs& w, int64_t B, int64_t n, int64_t m, flo
 
 // The same pass with the SIMT GEMMs (shapes the tensor-core path does not take: T or C not a multiple of 8,
 // unaligned x).  The plane buffers are free at this point and serve as the fp32 temporaries.
-static int second_pass_simt(const ErankWs& w, int64_t B, int64_t n, int64_t m, float* U, float* Y, cudaStream_t st) {
+static int second_pass_simt(const ErankWs& w, int64_t B, int64_t n, int64_t m, float* U, float* Y, int32_t* sweeps2,
+                            cudaStream_t st) {
   {
     R3D_STAGE(ST_GRAM, st);
     if (int e = sgemm_launch<float, float, float>(false, true, Y, Y, w.G, int(n), int(n), int(m), m, m, n, n * m, n * m,
                                                   n * n, nullptr, 0, 0, int(B), st)) return e;
   }
-  if (int e = jacobi_run_chunked(w.G, B, n, w.jws, nullptr, w.U2, nullptr, options().erank_pass2_sweeps, st)) return e;
+  if (int e = jacobi_run_chunked(w.G, B, n, w.jws, nullptr, w.U2, sweeps2, options().erank_pass2_sweeps, st, -1.f)) return e;
   R3D_STAGE(ST_REFINE_Y, st);
   float* Un = reinterpret_cast<float*>(w.Upl);
   float* Yn = reinterpret_cast<float*>(w.Ypl);
@@ -1446,6 +1500,8 @@ static int jacobi_run(const float* G, int64_t B, int64_t n, void* workspace, flo
   if (max_sweeps <= 0 || max_sweeps > JMAX_SWEEPS) max_sweeps = options().jacobi_max_sweeps;
   if (max_sweeps <= 0 || max_sweeps > JMAX_SWEEPS) max_sweeps = 16;
   JacobiWs w = jacobi_carve(workspace, B, n);
+  // tol_override > 0: first pass of the two-pass solver (its own threshold and raised significance floor);
+  // tol_override < 0: second pass (default threshold, floor jacobi_nu_pass2); 0: single-pass solver
   const float tol = tol_override > 0.f ? tol_override : options().jacobi_tol;
   const bool tc = options().jacobi_update_tc != 0 && panel_tc_supported(w.np);
   PanelTc ptc;
@@ -1464,7 +1520,8 @@ static int jacobi_run(const float* G, int64_t B, int64_t n, void* workspace, flo
     dim3 grid(std::min<int64_t>((int64_t(w.np) * w.np + 255) / 256, 64), (unsigned)B);
     R3D_STAGE(ST_JACOBI_INIT, st);
     jacobi_init_kernel<<<grid, 256, 0, st>>>(G, int(n), w.np, w.Gp, w.Vt, w.cnt, w.nu,
-                                             tol_override > 0.f ? options().jacobi_nu_pass1 : 4.f);
+                                             tol_override > 0.f ? options().jacobi_nu_pass1
+                                                                : (tol_override < 0.f ? options().jacobi_nu_pass2 : 4.f));
     R3D_LAUNCH_CHECK();
   }
   const size_t upd_smem = size_t(3) * JM * (JM + 4) * sizeof(float);
@@ -1650,20 +1707,25 @@ extern "C" int r3d_erank_fwd(const void* x, int64_t B, int64_t T, int64_t C, int
   const ErankWs w = erank_carve(workspace, B, T, C, dtype);
   if (int e = r3d_gram(x, B, T, C, dtype, gram_impl, workspace, w.G, st)) return e;
   const bool two_pass = options().erank_passes >= 2;
+  int32_t* sweeps2 = sweeps_out ? reinterpret_cast<int32_t*>(w.coef) : nullptr;   // coef is free until the backward
   if (int e = jacobi_run_chunked(w.G, B, n, w.jws, nullptr, U_out, sweeps_out,
                                  two_pass ? options().erank_pass1_sweeps : 0, st,
                                  two_pass ? options().jacobi_tol_pass1 : 0.f)) return e;
   if (tc_gemm_ok(T, C) && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
     if (int e = refine_Y_tc(x, dtype, U_out, w, B, T, C, Y_out, st)) return e;
     if (two_pass) {
-      if (int e = second_pass_tc(w, B, n, m, U_out, Y_out, st)) return e;
+      if (int e = second_pass_tc(w, B, n, m, U_out, Y_out, sweeps2, st)) return e;
     }
   } else {
     if (int e = (dtype == R3D_F32 ? refine_Y<float>(x, U_out, B, T, C, Y_out, st)
                                   : refine_Y<__nv_bfloat16>(x, U_out, B, T, C, Y_out, st))) return e;
     if (two_pass) {
-      if (int e = second_pass_simt(w, B, n, m, U_out, Y_out, st)) return e;
+      if (int e = second_pass_simt(w, B, n, m, U_out, Y_out, sweeps2, st)) return e;
     }
+  }
+  if (two_pass && sweeps_out) {
+    sweeps_merge_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(sweeps_out, sweeps2, (int)B);
+    R3D_LAUNCH_CHECK();
   }
   {
     R3D_STAGE(ST_SIGMA, st);

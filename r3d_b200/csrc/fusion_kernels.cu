@@ -168,11 +168,27 @@ __global__ void __launch_bounds__(256) score_partial_kernel(const T* __restrict_
 
 // Stage 2: 32 channels x 8 partial-sum lanes per CTA; every lane adds its slice of the row chunks in index
 // order, then lane 0 adds the 8 lane sums in order -- a fixed summation tree, so results are bit-reproducible.
+// Optional tail (the packed statistic of the multi-GPU path): tail[0] = sum of er[0..n_er) in a fixed
+// order, tail[1] = rows -- written on the device so that the step needs no ATen reduction / fill kernels.
 __global__ void __launch_bounds__(256) score_finalize_kernel(const float* __restrict__ partial, int row_chunks,
                                                              int64_t rows, int64_t C, float* __restrict__ sums_out,
-                                                             float* __restrict__ score_out) {
+                                                             float* __restrict__ score_out,
+                                                             const float* __restrict__ er, int n_er,
+                                                             float* __restrict__ tail) {
   __shared__ float red[8][33];
   const int cl = threadIdx.x & 31, g = threadIdx.x >> 5;
+  if (tail != nullptr && blockIdx.x == 0 && blockIdx.y == 0) {
+    __shared__ float ered[256];
+    float a = 0.f;
+    for (int i = threadIdx.x; i < n_er; i += 256) a += er[i];
+    ered[threadIdx.x] = a;
+    __syncthreads();
+    for (int st = 128; st > 0; st >>= 1) {
+      if (threadIdx.x < st) ered[threadIdx.x] += ered[threadIdx.x + st];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) { tail[0] = er ? ered[0] : 0.f; tail[1] = float(rows); }
+  }
   const int64_t c = int64_t(blockIdx.x) * 32 + cl;
   float s = 0.f;
   if (c < C) {
@@ -205,10 +221,21 @@ __device__ __forceinline__ unsigned long long make_key(float s, uint32_t idx) {
   return (static_cast<unsigned long long>(b) << 32) | idx;
 }
 
+// denom != nullptr: the keys are score[i] / *denom (IEEE division, as torch.div would produce) -- the score sums of
+// the packed statistic divided by the global row count, without a separate elementwise kernel.
 __global__ void __launch_bounds__(1024) bottomk_kernel(const float* __restrict__ score, int64_t C, int64_t k, int n2,
-                                                       int64_t* __restrict__ idx_out) {
+                                                       int64_t* __restrict__ idx_out, const float* __restrict__ denom,
+                                                       float* __restrict__ score_out) {
   extern __shared__ unsigned long long keys[];
-  const float* s = score + int64_t(blockIdx.x) * C;
+  const float* sraw = score + int64_t(blockIdx.x) * C;
+  const float dn = denom ? *denom : 1.f;
+  struct Scaled {
+    const float* p; float d; bool on;
+    __device__ float operator[](int i) const { return on ? __fdiv_rn(p[i], d) : p[i]; }
+  } s{sraw, dn, denom != nullptr};
+  if (score_out) {
+    for (int i = threadIdx.x; i < C; i += blockDim.x) score_out[int64_t(blockIdx.x) * C + i] = s[i];
+  }
   int64_t* out = idx_out + int64_t(blockIdx.x) * k;
   const int tid = threadIdx.x;
   if (n2 <= 1024) {
@@ -696,12 +723,35 @@ extern "C" int r3d_score_finalize(const float* partial, int64_t rows, int64_t C,
   dim3 grid((unsigned)((C + 31) / 32), 2);
   R3D_STAGE(ST_SCORE_FINALIZE, (cudaStream_t)stream);
   score_finalize_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(partial, fixed_row_chunks(rows), rows, C, sums_out,
-                                                               score_out);
+                                                               score_out, nullptr, 0, nullptr);
   R3D_LAUNCH_CHECK();
   return 0;
 }
 
+extern "C" int r3d_score_finalize_packed(const float* partial, int64_t rows, int64_t C, const float* er, int64_t n_er,
+                                         float* packed_out, void* stream) {
+  R3D_CHECK(partial != nullptr && packed_out != nullptr, "null pointer");
+  R3D_CHECK(rows >= 1 && C >= 1 && n_er >= 0, "bad shape");
+  dim3 grid((unsigned)((C + 31) / 32), 2);
+  R3D_STAGE(ST_SCORE_FINALIZE, (cudaStream_t)stream);
+  score_finalize_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(partial, fixed_row_chunks(rows), rows, C, packed_out,
+                                                               nullptr, er, (int)n_er, packed_out + 2 * C);
+  R3D_LAUNCH_CHECK();
+  return 0;
+}
+
+static int bottomk_impl(const float* score, int nvec, int64_t C, int64_t k, int64_t* idx_out, const float* denom,
+                        float* score_out, void* stream);
 extern "C" int r3d_bottomk(const float* score, int nvec, int64_t C, int64_t k, int64_t* idx_out, void* stream) {
+  return bottomk_impl(score, nvec, C, k, idx_out, nullptr, nullptr, stream);
+}
+extern "C" int r3d_bottomk_scaled(const float* sums, int nvec, int64_t C, int64_t k, const float* denom,
+                                  int64_t* idx_out, float* score_out, void* stream) {
+  R3D_CHECK(denom != nullptr, "null denominator");
+  return bottomk_impl(sums, nvec, C, k, idx_out, denom, score_out, stream);
+}
+static int bottomk_impl(const float* score, int nvec, int64_t C, int64_t k, int64_t* idx_out, const float* denom,
+                        float* score_out, void* stream) {
   R3D_CHECK(score != nullptr, "null score");
   R3D_CHECK(C >= 1 && C <= 8192, "bottomk supports 1 <= C <= 8192, got %lld", (long long)C);
   R3D_CHECK(k >= 0 && k <= C, "k=%lld out of range for C=%lld", (long long)k, (long long)C);
@@ -714,7 +764,7 @@ extern "C" int r3d_bottomk(const float* score, int nvec, int64_t C, int64_t k, i
   if (smem > 48 * 1024)
     R3D_CUDA(cudaFuncSetAttribute(bottomk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   R3D_STAGE(ST_BOTTOMK, (cudaStream_t)stream);
-  bottomk_kernel<<<nvec, threads, smem, (cudaStream_t)stream>>>(score, C, k, n2, idx_out);
+  bottomk_kernel<<<nvec, threads, smem, (cudaStream_t)stream>>>(score, C, k, n2, idx_out, denom, score_out);
   R3D_LAUNCH_CHECK();
   return 0;
 }

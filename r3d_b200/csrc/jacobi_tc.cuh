@@ -57,6 +57,7 @@ struct Options {
                                   // so the first may stop ~2.5 sweeps earlier: 4 -> 55.1 ms, 1024 -> 50.7, 4096 -> 48.8 with
                                   // unchanged gradients (<= 8e-5); from 16384 on the hardest spectrum (channel decay 512x512)
                                   // loses its smallest directions (9e-3)
+  float jacobi_nu_pass2 = 4.f;    // second pass: absolute significance floor in the same units
   int erank_pass1_sweeps = 12;  // sweep cap of the first pass of the two-pass solver (it converges in 8-11 with the raised floor;
                                 // whatever a capped matrix still needs, the second pass does); 0 = jacobi_max_sweeps
   int erank_pass2_sweeps = 4;   // sweep cap of the second pass (0 = jacobi_max_sweeps); it converges in 2 (one working sweep and one

@@ -97,24 +97,41 @@ class CMFuser(nn.Module):
     """Rank-enhancing token fuser (SA-Fuser with channel exchange).
 
     Reference-compatible positional arguments; ``variant`` picks which of the four
-    reference files is reproduced.  ``score_scope='global'`` all-reduces the
-    (2, C) score sums over ``process_group`` when torch.distributed is initialised
-    (the single-process oracle on the concatenated batch); ``'local'`` reproduces
-    ``nn.DataParallel`` (each replica scores its own shard).
+    reference files is reproduced.
+
+    ``score_scope='local'`` (default) is the reference's behaviour under
+    ``nn.DataParallel`` (main_utkinects.py:129): every replica / rank scores its own
+    shard and ``forward`` issues NO collective, so ranks may call it independently
+    (rank-0-only validation, uneven last batches).  ``score_scope='global'`` is opt-in:
+    it all-reduces the (2, C) score sums over ``process_group`` so that the selection
+    equals the single-process result on the concatenated batch -- EVERY rank of the
+    group must then call ``forward`` the same number of times, or the collective hangs.
+
+    ``select_axis='channel'`` (default) is what the reference ships (tokenfusion.py:33-66 exchanges CHANNELS chosen by a
+    batch-global score).  ``select_axis='token'`` is the form the paper prose describes (README.md:13; no
+    reference code, parity unpinned): per sample, the T // 4 tokens with the lowest spectral informativeness
+    (``ops.token_scores``, a by-product of the effective-rank chain) are replaced by the other modality's tokens;
+    ``last_erank`` then holds the per-sample effective ranks (rgb, depth) of the call.
     """
 
     def __init__(self, dim, depth=1, num_heads=4, mlp_ratio=4.0, qkv_bias=False, *, variant: str = "tokenfusion",
-                 score_scope: str = "global", process_group=None):
+                 score_scope: str = "local", process_group=None, select_axis: str = "channel"):
         super().__init__()
         if variant not in VARIANTS:
             raise ValueError(f"variant must be one of {VARIANTS}")
         if score_scope not in ("global", "local"):
             raise ValueError("score_scope must be 'global' or 'local'")
+        if select_axis not in ("channel", "token"):
+            raise ValueError("select_axis must be 'channel' or 'token'")
+        if select_axis == "token" and variant != "tokenfusion":
+            raise ValueError("select_axis='token' is defined for the swap variant ('tokenfusion') only")
         self.dim = dim
         self.num_heads = num_heads
         self.variant = variant
         self.score_scope = score_scope
         self.process_group = process_group
+        self.select_axis = select_axis
+        self.last_erank = None
         self.blocks = nn.ModuleList([Block(dim, num_heads, mlp_ratio, qkv_bias) for _ in range(depth)])
         self.norm = nn.LayerNorm(dim)
         self.embd_drop = nn.Dropout(0.1)
@@ -140,15 +157,14 @@ class CMFuser(nn.Module):
     def k_for(self, C: int) -> int:
         return max(0, int(C * 0.1)) if self.variant == "batchnorm" else C // 4
 
-    def _global_sums(self, sums: torch.Tensor, rows: int):
-        """All-reduce the packed [sum|rgb| (C) || sum|depth| (C) || rows] buffer."""
+    def _maybe_allreduce(self, packed: torch.Tensor) -> torch.Tensor:
+        """Global scope: all-reduce the packed [sum|rgb| (C) || sum|depth| (C) || sum erank || rows] buffer (written
+        on the device by one kernel -- no pageable host copy, no sync)."""
         import torch.distributed as dist
         if self.score_scope == "global" and dist.is_available() and dist.is_initialized() \
                 and dist.get_world_size(self.process_group) > 1:
-            packed = torch.cat([sums.reshape(-1), sums.new_tensor([float(rows)])])
             dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=self.process_group)
-            return packed[:-1].reshape(2, -1), packed[-1]
-        return sums, None
+        return packed
 
     def select_channels(self, rgb: torch.Tensor, depth: torch.Tensor, mode: str):
         """score -> bottom-k.  Returns (idx_r, idx_d) int64 (k,) each."""
@@ -163,9 +179,9 @@ class CMFuser(nn.Module):
             idx = torch.arange(k, device=rgb.device, dtype=torch.int64)
             return idx, idx.clone()
         else:
-            sums = ops.channel_score_sums(rgb.detach(), depth.detach())
-            sums, total_rows = self._global_sums(sums, B * T)
-            score = sums / (float(B * T) if total_rows is None else total_rows)
+            packed = self._maybe_allreduce(ops.channel_score_packed(rgb.detach(), depth.detach()))
+            idx = ops.bottomk_packed(packed, k)        # the mean = sums / rows is formed inside the kernel
+            return idx[0], idx[1]
         idx = ops.bottomk(score, k)
         return idx[0], idx[1]
 
@@ -175,6 +191,13 @@ class CMFuser(nn.Module):
             raise R3DError("the safuser variant has no token_fusion (futr_safuser_depth.py has none)")
         if not rgb_feats.is_cuda:
             raise R3DError("r3d_b200.CMFuser runs on CUDA tensors only (no CPU fallback)")
+        if self.select_axis == "token":
+            T = rgb_feats.shape[1]
+            s_r, er_r = ops.token_scores(rgb_feats, return_erank=True)
+            s_d, er_d = ops.token_scores(depth_feats, return_erank=True)
+            idx_r, idx_d = ops.bottomk(s_r, T // 4), ops.bottomk(s_d, T // 4)          # (B, k) each, ties -> lower index
+            self.last_indices, self.last_erank = (idx_r, idx_d), (er_r, er_d)
+            return ops.token_exchange(rgb_feats, depth_feats, idx_r, idx_d)
         idx_r, idx_d = self.select_channels(rgb_feats, depth_feats, mode)
         self.last_indices = (idx_r, idx_d)
         if self.variant == "tokenfusion":

@@ -10,6 +10,7 @@ Public surface (also registered as ``torch.ops.r3d.*``):
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -121,6 +122,36 @@ def channel_score(rgb: torch.Tensor, depth: torch.Tensor) -> torch.Tensor:
     return score
 
 
+def channel_score_packed(rgb: torch.Tensor, depth: torch.Tensor, er: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """(2C + 2,) float32 packed statistic [sum|rgb| (C) | sum|depth| (C) | sum er | rows], written by one finalize
+    launch -- the buffer global-score mode all-reduces; `bottomk_packed` consumes it."""
+    _need_cuda(rgb, depth, er)
+    rgb, depth = _btc(rgb, depth)
+    B, T, C = rgb.shape
+    rows = B * T
+    L = _lib.lib()
+    with _on(rgb.device):
+        ws = torch.empty(L.r3d_score_workspace_floats(rows, C), dtype=torch.float32, device=rgb.device)
+        packed = torch.empty(2 * C + 2, dtype=torch.float32, device=rgb.device)
+        check(L.r3d_channel_score_partial(_p(rgb), _p(depth), rows, C, _dt(rgb), _p(ws), _stream()))
+        e = None if er is None else er.reshape(-1).float().contiguous()
+        check(L.r3d_score_finalize_packed(_p(ws), max(rows, 1), C, _p(e), 0 if e is None else e.numel(), _p(packed),
+                                          _stream()))
+    return packed
+
+
+def bottomk_packed(packed: torch.Tensor, k: int, return_score: bool = False):
+    """Bottom-k of  sums / rows  straight from the packed statistic: (2, k) int64 (+ the (2, C) score)."""
+    _need_cuda(packed)
+    C = (packed.numel() - 2) // 2
+    idx = torch.empty(2, k, dtype=torch.int64, device=packed.device)
+    score = torch.empty(2, C, dtype=torch.float32, device=packed.device) if return_score else None
+    with _on(packed.device):
+        check(_lib.lib().r3d_bottomk_scaled(_p(packed), 2, C, k, packed.data_ptr() + (2 * C + 1) * 4, _p(idx),
+                                            _p(score), _stream()))
+    return (idx, score) if return_score else idx
+
+
 # ---------------------------------------------------------------------------------
 # a4: bottom-k                 (reference: model/futr_safuser_tokenfusion.py:52-54)
 # ---------------------------------------------------------------------------------
@@ -144,6 +175,8 @@ def _exchange_fwd_raw(rgb, depth, idx_r, idx_d, alpha, affine, blend):
     B, T, C = rgb.shape
     out = torch.empty(B, T, 2, C, dtype=rgb.dtype, device=rgb.device)
     k = idx_r.numel()
+    if B * T == 0:
+        return out                                   # empty batch: nothing to launch (zero-size tensors have no pointer)
     with _on(rgb.device):
         check(_lib.lib().r3d_exchange_fwd(_p(rgb), _p(depth), _p(idx_r), _p(idx_d), k, _p(alpha), _p(affine), blend,
                                           _p(out), B * T, C, _dt(rgb), _stream()))
@@ -157,6 +190,8 @@ def _exchange_bwd_raw(g, rgb, depth, idx_r, idx_d, alpha, affine, bn_norm, blend
     d_rgb = torch.empty(B, T, C, dtype=g.dtype, device=g.device)
     d_dep = torch.empty(B, T, C, dtype=g.dtype, device=g.device)
     colsums = None
+    if rows == 0:                                    # empty batch: zero parameter gradients, nothing to launch
+        return d_rgb, d_dep, (None if blend == BLEND_SWAP else torch.zeros(5, C, dtype=torch.float32, device=g.device))
     with _on(g.device):
         ws = None
         if blend != BLEND_SWAP:
@@ -323,16 +358,27 @@ class _ERank(torch.autograd.Function):
         return dx, None, None
 
 
-def erank(x: torch.Tensor, rtol: float = DEFAULT_RTOL, gram_impl: int = GRAM_TCGEN05, return_aux: bool = False):
+def erank(x: torch.Tensor, rtol: float = DEFAULT_RTOL, gram_impl: int = GRAM_TCGEN05, return_aux: bool = False,
+          strict: Optional[bool] = None):
     """Per-sample effective rank of x (B, T, C) -> (B,) float32, differentiable in x.
 
     exp(-sum p ln p), p = sigma / sum sigma over the singular values of each (T, C)
-    sample; sigma <= rtol * sigma_max are treated as zero."""
+    sample; sigma <= rtol * sigma_max are treated as zero.
+
+    ``return_aux`` adds (sigma, sweeps); sweeps < 0 marks a sample whose eigensolver ran into its sweep cap.
+    ``strict=True`` (or environment R3D_STRICT=1) synchronises and raises R3DError in that case instead of returning a
+    less accurate value silently; the default stays asynchronous."""
     _need_cuda(x)
     if x.dim() != 3:
         raise R3DError(f"expected (B, T, C), got {tuple(x.shape)}")
     _dt(x)
     er, sigma, sweeps = _ERank.apply(x.contiguous(), float(rtol), int(gram_impl))
+    if strict is None:
+        strict = os.environ.get("R3D_STRICT", "0") not in ("", "0")
+    if strict and bool((sweeps < 0).any()):
+        bad = torch.nonzero(sweeps < 0).flatten().tolist()
+        raise R3DError(f"erank: the Jacobi eigensolver hit its sweep cap without converging for samples {bad[:8]} "
+                       "(raise erank_pass2_sweeps / jacobi_max_sweeps via r3d_b200._lib.set_option)")
     if return_aux:
         return er, sigma, sweeps
     return er
@@ -379,7 +425,8 @@ def layer_norm_supported(x: torch.Tensor, C: int) -> bool:
     if not x.is_cuda or x.dtype not in _DT:
         return False
     v = 4 if x.dtype == torch.float32 else 8
-    return C % v == 0 and C <= 32 * v * 8
+    # 128-bit row accesses: an offset (unaligned) view takes the caller's torch path instead of raising
+    return C % v == 0 and C <= 32 * v * 8 and x.data_ptr() % 16 == 0 and x.is_contiguous()
 
 
 class _LayerNorm(torch.autograd.Function):
@@ -468,7 +515,7 @@ class _SwapAdd(torch.autograd.Function):
 
 def swap_add_supported(x: torch.Tensor) -> bool:
     return x.is_cuda and x.dtype in _DT and x.dim() >= 2 and x.shape[-2] == 2 and \
-        x.shape[-1] % (4 if x.dtype == torch.float32 else 8) == 0
+        x.shape[-1] % (4 if x.dtype == torch.float32 else 8) == 0 and x.data_ptr() % 16 == 0
 
 
 def swap_add(x: torch.Tensor, p: torch.Tensor) -> torch.Tensor:
@@ -490,6 +537,72 @@ def token_informativeness(sigma: torch.Tensor, U: torch.Tensor, rtol: float = DE
         check(_lib.lib().r3d_token_informativeness(_p(sigma.contiguous()), _p(U.contiguous()), B, n, rtol, _p(out),
                                                    _stream()))
     return out
+
+
+# ---------------------------------------------------------------------------------
+# N1: token-axis selection (north_star kernels 3-6; no reference symbol -- the reference ships the channel exchange
+# only; oracle: oracle/fuser_oracle.py:token_fusion_tokens, parity unpinned)
+# ---------------------------------------------------------------------------------
+def token_scores(x: torch.Tensor, rtol: float = DEFAULT_RTOL, gram_impl: int = GRAM_TCGEN05, return_erank: bool = False):
+    """(B, T, C) -> (B, T) float32: informativeness of every token, s_t = sum_j p_j u_{tj}^2 over the left singular
+    vectors of each sample (p = sigma / sum sigma).  Runs the effective-rank chain and reuses what it saved."""
+    _need_cuda(x)
+    x = x.detach().contiguous()
+    B, T, C = x.shape
+    er, sigma, U, Y, _ = _erank_fwd_raw(x, rtol, gram_impl)
+    out = torch.empty(B, T, dtype=torch.float32, device=x.device)
+    with _on(x.device):
+        check(_lib.lib().r3d_token_scores(_p(sigma), _p(U), _p(Y), B, T, C, rtol, _p(out), _stream()))
+    return (out, er) if return_erank else out
+
+
+def token_mask(idx_r: torch.Tensor, idx_d: torch.Tensor, T: int) -> torch.Tensor:
+    """Per-sample index lists (B, k) int64 -> (B, T) uint8, bit 0 = token in S_rgb(b), bit 1 = token in S_depth(b)."""
+    _need_cuda(idx_r, idx_d)
+    B, k = idx_r.shape
+    mask = torch.empty(B, T, dtype=torch.uint8, device=idx_r.device)
+    with _on(idx_r.device):
+        check(_lib.lib().r3d_token_mask(_p(idx_r.contiguous()), _p(idx_d.contiguous()), B, T, k, _p(mask), _stream()))
+    return mask
+
+
+class _TokenExchange(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, rgb, depth, mask):
+        B, T, C = rgb.shape
+        out = torch.empty(B, T, 2, C, dtype=rgb.dtype, device=rgb.device)
+        if B * T:
+            with _on(rgb.device):
+                check(_lib.lib().r3d_token_exchange_fwd(_p(rgb), _p(depth), _p(mask), _p(out), B * T, C, _dt(rgb),
+                                                        _stream()))
+        ctx.save_for_backward(mask)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (mask,) = ctx.saved_tensors
+        g = g.contiguous()
+        B, T, _, C = g.shape
+        d_rgb = torch.empty(B, T, C, dtype=g.dtype, device=g.device)
+        d_dep = torch.empty(B, T, C, dtype=g.dtype, device=g.device)
+        if B * T:
+            with _on(g.device):
+                check(_lib.lib().r3d_token_exchange_bwd(_p(g), _p(mask), _p(d_rgb), _p(d_dep), B * T, C, _dt(g),
+                                                        _stream()))
+        return d_rgb, d_dep, None
+
+
+def token_exchange(rgb, depth, idx_r, idx_d) -> torch.Tensor:
+    """(B,T,C) x2 + per-sample token index sets (B, k) -> stacked (B,T,2,C): tokens in S_rgb(b) of the rgb stream are
+    replaced by the depth tokens at the same positions and vice versa; differentiable in rgb and depth."""
+    _need_cuda(rgb, depth, idx_r, idx_d)
+    rgb, depth = _btc(rgb, depth)
+    _dt(rgb)
+    B, T, C = rgb.shape
+    if idx_r.shape != idx_d.shape or idx_r.dim() != 2 or idx_r.shape[0] != B:
+        raise R3DError(f"token index sets must both be (B, k), got {tuple(idx_r.shape)} and {tuple(idx_d.shape)}")
+    mask = token_mask(idx_r.to(torch.int64), idx_d.to(torch.int64), T)
+    return _TokenExchange.apply(rgb, depth, mask)
 
 
 def token_fusion_host(rgb: torch.Tensor, depth: torch.Tensor, k: int):
@@ -603,13 +716,13 @@ class FuserStep:
                               _p(self.sigma), _p(self.U), _p(self.Y), _p(self.sweeps), st))
         # ---- forward: score sums -> (all-reduce with the erank statistic) -> bottom-k -> exchange
         check(L.r3d_channel_score_partial(rgb_p, dep_p, rows, C, dt, _p(self.ws_score), st))
-        check(L.r3d_score_finalize(_p(self.ws_score), rows, C, _p(self.packed), None, st))
-        self.packed[2 * C] = self.er.sum()
-        self.packed[2 * C + 1:2 * C + 2].fill_(float(rows))      # device-side fill (no host copy: graph-capturable)
+        # packed = [sum|rgb| | sum|depth| | sum erank | rows], all written by the finalize kernel (no ATen kernels, no
+        # host copy: graph-capturable); the quotient sums / rows is formed inside the bottom-k kernel
+        check(L.r3d_score_finalize_packed(_p(self.ws_score), rows, C, _p(self.er), 2 * B, _p(self.packed), st))
         if self.world > 1:
             torch.distributed.all_reduce(self.packed, group=self.group)
-        torch.div(self.packed[:2 * C].view(2, C), self.packed[2 * C + 1], out=self.score)
-        check(L.r3d_bottomk(_p(self.score), 2, C, self.k, _p(self.idx), st))
+        check(L.r3d_bottomk_scaled(_p(self.packed), 2, C, self.k, self.packed.data_ptr() + (2 * C + 1) * 4,
+                                   _p(self.idx), _p(self.score), st))
         ir, idd = self.idx[0].data_ptr(), self.idx[1].data_ptr()
         check(L.r3d_exchange_fwd(rgb_p, dep_p, ir, idd, self.k, None, None, BLEND_SWAP, _p(self.out), rows, C, dt, st))
         # ---- backward: exchange backward into dgrad, then accumulate d(mean erank)/dX

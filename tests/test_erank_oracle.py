@@ -162,3 +162,31 @@ def test_cutoff_across_threshold():
         assert rel.max() < 3e-4
         if str(z["kind"]) in ("relu", "gauss") and int(z["T"]) < int(z["C"]):
             assert rel.max() < 1e-13
+
+
+def test_token_axis_oracle_against_torch_autograd():
+    """oracle/fuser_oracle.py:token_fusion_tokens / token_exchange_bwd (unpinned restatement) against the same
+    operation written with torch index assignment + autograd; scores sum to one and pick the weakest tokens."""
+    from oracle import fuser_oracle as O
+    rng = np.random.default_rng(3)
+    B, T, C = 3, 12, 7
+    rgb = np.maximum(rng.standard_normal((B, T, C)), 0).astype(np.float32)
+    dep = np.maximum(rng.standard_normal((B, T, C)), 0).astype(np.float32)
+    rgb[:, 5] *= 1e-3                      # an uninformative token must be selected
+    s = EO.token_scores(rgb)
+    np.testing.assert_allclose(s.sum(1), 1.0, rtol=1e-12)
+    out, ir, idd = O.token_fusion_tokens(rgb, dep, return_indices=True)
+    assert all(5 in ir[b] for b in range(B)) and ir.shape == (B, T // 4)
+    r = torch.from_numpy(rgb).requires_grad_(True)
+    d = torch.from_numpy(dep).requires_grad_(True)
+    ex_r, ex_d = r.clone(), d.clone()
+    for b in range(B):
+        ex_r[b, torch.from_numpy(ir[b])] = d[b, torch.from_numpy(ir[b])]
+        ex_d[b, torch.from_numpy(idd[b])] = r[b, torch.from_numpy(idd[b])]
+    st = torch.stack([ex_r, ex_d], dim=2)
+    np.testing.assert_array_equal(st.detach().numpy(), out)
+    g = torch.from_numpy(rng.standard_normal((B, T, 2, C)).astype(np.float32))
+    st.backward(g)
+    gr, gd = O.token_exchange_bwd(g.numpy(), ir, idd)
+    np.testing.assert_array_equal(r.grad.numpy(), gr)
+    np.testing.assert_array_equal(d.grad.numpy(), gd)

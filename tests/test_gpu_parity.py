@@ -738,3 +738,182 @@ def test_alternative_kernel_paths_agree(opts, dev):
     finally:
         for k, v in defaults.items():
             _lib.set_option(k, v)
+
+
+# ------------------------------------------------------------------ round 2 additions
+def test_packed_statistic_and_scaled_bottomk(dev):
+    """r3d_score_finalize_packed + r3d_bottomk_scaled (no ATen kernels in the step): the packed statistic
+    [sum|rgb| | sum|depth| | sum er | rows] and the selection on sums / rows against the oracle, bit-exact indices."""
+    from r3d_b200 import ops
+    for (B, T, C, dt) in ((3, 17, 64, torch.float32), (8, 256, 512, torch.float32), (4, 64, 200, torch.bfloat16)):
+        rgb, dep = synth(B, T, C, 5 + B, dt)
+        er = torch.linspace(1.0, 2.0, 2 * B)
+        packed = ops.channel_score_packed(rgb.to(dev), dep.to(dev), er.to(dev))
+        p = packed.cpu().numpy()
+        rn, dn = rgb.float().numpy(), dep.float().numpy()
+        ref = np.stack([O.channel_score(rn), O.channel_score(dn)])
+        np.testing.assert_allclose(p[:2 * C].reshape(2, C) / (B * T), ref, rtol=1e-5)
+        assert p[2 * C + 1] == B * T
+        np.testing.assert_allclose(p[2 * C], er.sum().item(), rtol=1e-6)
+        k = C // 4
+        idx, score = ops.bottomk_packed(packed, k, return_score=True)
+        sc = score.cpu().numpy()
+        np.testing.assert_array_equal(sc, (p[:2 * C] / p[2 * C + 1]).astype(np.float32).reshape(2, C))   # IEEE division
+        for m in range(2):
+            np.testing.assert_array_equal(idx[m].cpu().numpy(), O.bottomk(sc[m], k))
+            np.testing.assert_array_equal(idx[m].cpu().numpy(), O.bottomk(ref[m], k))   # tie-free synthetic scores
+
+
+def _erank_fixtures():
+    import glob
+    from conftest import GOLDEN
+    return sorted(glob.glob(os.path.join(GOLDEN, "erank_*.npz")))
+
+
+@pytest.mark.parametrize("path", _erank_fixtures(), ids=os.path.basename)
+def test_erank_golden_fixtures(path, dev):
+    """The CUDA chain against tests/golden/erank_*.npz: torch float64 svdvals + autograd, an implementation independent
+    of the numpy oracle (tests/golden/make_erank_golden.py).  north_star bars: 1e-4 relative in fp32."""
+    import sys
+    from conftest import GOLDEN
+    sys.path.insert(0, GOLDEN)
+    from make_erank_golden import make_input
+    from r3d_b200 import ops
+    z = np.load(path)
+    B, T, C = int(z["B"]), int(z["T"]), int(z["C"])
+    x = make_input(str(z["kind"]), B, T, C, int(z["seed"]))
+    xt = torch.from_numpy(x).to(dev).requires_grad_(True)
+    er, sigma, sweeps = ops.erank(xt, return_aux=True)
+    if str(z["kind"]) != "rankdef":
+        # (in the noise null space of an exactly rank-deficient sample rotations never die out; the refinement makes
+        # the result independent of them, which the value checks below show)
+        assert (sweeps > 0).all(), f"eigensolver hit its sweep cap: {sweeps.cpu().numpy()}"
+    np.testing.assert_allclose(er.detach().cpu().numpy(), z["erank"], rtol=1e-4)
+    sg = np.sort(sigma.cpu().numpy(), axis=1)[:, ::-1]
+    assert np.abs(sg - z["sigma"]).max() <= 1e-4 * z["sigma"].max()
+    er.sum().backward()
+    g = xt.grad.cpu().numpy()
+    assert np.abs(g - z["grad"]).max() <= 1e-4 * np.abs(z["grad"]).max()
+    # rtol = 0 (appendix B verbatim, no cut-off) is supported too; it agrees with the float64 value wherever the
+    # spectrum stays above what an fp32 chain resolves (every fixture but the exactly rank-deficient ones, whose null
+    # space comes out as noise of ~1e-6 sigma_max instead of 1e-16)
+    if str(z["kind"]) != "rankdef":
+        er0 = ops.erank(xt.detach(), rtol=0.0)
+        np.testing.assert_allclose(er0.cpu().numpy(), z["erank_rtol0"], rtol=2e-4)
+
+
+def test_erank_from_short_lived_threads_keeps_stream_sets_flat(dev):
+    """nn.DataParallel starts fresh Python threads for every forward (main_utkinects.py:129); the library's side
+    streams / events are pooled per device and lent to threads, so their number must not grow with the thread count."""
+    import threading
+    from r3d_b200 import ops, _lib
+    x = torch.from_numpy(_spectra("relu", 2, 128, 128, 11)).to(dev)
+    ref = ops.erank(x).cpu()
+    torch.cuda.synchronize()
+    before = _lib.lib().r3d_stream_sets_created()
+    outs = []
+
+    def work():
+        with torch.cuda.device(dev):
+            outs.append(ops.erank(x).cpu())
+
+    for _ in range(12):
+        t = threading.Thread(target=work)
+        t.start()
+        t.join()
+    after = _lib.lib().r3d_stream_sets_created()
+    assert after - before <= 1, (before, after)
+    for o in outs:
+        assert torch.equal(o, ref)
+
+
+def test_erank_strict_mode_reports_sweep_cap(dev):
+    """A capped eigensolver is reported (negative sweeps) and strict mode raises instead of returning silently."""
+    from r3d_b200 import ops, _lib
+    from r3d_b200._lib import R3DError
+    x = torch.from_numpy(_spectra("relu", 2, 256, 256, 3)).to(dev)
+    try:
+        _lib.set_option("erank_passes", 1)
+        _lib.set_option("jacobi_max_sweeps", 2)
+        er, sigma, sweeps = ops.erank(x, return_aux=True)
+        assert (sweeps < 0).all()
+        with pytest.raises(R3DError):
+            ops.erank(x, strict=True)
+    finally:
+        _lib.set_option("erank_passes", 2)
+        _lib.set_option("jacobi_max_sweeps", 16)
+    er, sigma, sweeps = ops.erank(x, return_aux=True, strict=True)
+    assert (sweeps > 0).all()
+
+
+def test_empty_batch_blend_backward_is_zero(dev):
+    """rows == 0: no partial sums are written; d_alpha must be zeros, not workspace garbage."""
+    from r3d_b200 import ops
+    C = 64
+    rgb = torch.zeros(0, 5, C, device=dev, requires_grad=True)
+    dep = torch.zeros(0, 5, C, device=dev, requires_grad=True)
+    alpha = torch.ones(1, 1, C, device=dev, requires_grad=True)
+    idx = torch.arange(16, device=dev)
+    out = ops.exchange(rgb, dep, idx, idx, alpha, ops.BLEND_SCALE)
+    out.sum().backward()
+    assert torch.count_nonzero(alpha.grad) == 0
+
+
+# ------------------------------------------------------------------ N1: token-axis selection (unpinned; oracle = restatement)
+@pytest.mark.parametrize("B,T,C,dt", [(3, 64, 128, torch.float32), (2, 128, 64, torch.float32), (2, 96, 96, torch.float32),
+                                      (2, 256, 512, torch.bfloat16), (1, 37, 20, torch.float32)])
+def test_token_axis_scores_selection_exchange(B, T, C, dt, dev):
+    from r3d_b200 import ops
+    rgb, dep = synth(B, T, C, 31 + T, dt)
+    # give the tokens distinct weights so that the scores are tie-free and well separated
+    w = (1.0 + torch.arange(T, dtype=torch.float32) / T).view(1, T, 1)
+    rgb, dep = (rgb.float() * w).to(dt), (dep.float() * w.flip(1)).to(dt)
+    rn, dn = rgb.float().numpy(), dep.float().numpy()
+    s_r = ops.token_scores(rgb.to(dev)).cpu().numpy()
+    s_d = ops.token_scores(dep.to(dev)).cpu().numpy()
+    ref_r, ref_d = EO.token_scores(rn), EO.token_scores(dn)
+    tol = 2e-3 if dt == torch.bfloat16 else 2e-4
+    np.testing.assert_allclose(s_r, ref_r, rtol=tol, atol=tol * ref_r.max())
+    np.testing.assert_allclose(s_d, ref_d, rtol=tol, atol=tol * ref_d.max())
+    np.testing.assert_allclose(s_r.sum(1), 1.0, rtol=1e-3)
+    k = T // 4
+    idx_r = ops.bottomk(torch.from_numpy(s_r).to(dev), k)
+    idx_d = ops.bottomk(torch.from_numpy(s_d).to(dev), k)
+    # selection on the device scores is exactly the oracle rule (ascending score, ties -> lower index) ...
+    st_ref, ir, idd = O.token_fusion_tokens(rn, dn, k, scores=(s_r, s_d), return_indices=True)
+    np.testing.assert_array_equal(idx_r.cpu().numpy(), ir)
+    np.testing.assert_array_equal(idx_d.cpu().numpy(), idd)
+    # ... and the SET equals the float64 oracle's wherever the k-th and (k+1)-th scores are separated by more than the
+    # score error
+    for got, ref in ((ir, ref_r), (idd, ref_d)):
+        for b in range(B):
+            srt = np.sort(ref[b])
+            if srt[k] - srt[k - 1] > 4 * tol * ref.max():
+                assert set(got[b].tolist()) == set(np.argsort(ref[b], kind="stable")[:k].tolist())
+    r = rgb.to(dev).requires_grad_(True)
+    d = dep.to(dev).requires_grad_(True)
+    st = ops.token_exchange(r, d, idx_r, idx_d)
+    np.testing.assert_array_equal(st.detach().float().cpu().numpy(), st_ref)            # pure copies: bit-exact
+    g = torch.randn(B, T, 2, C, generator=torch.Generator().manual_seed(5)).to(dt)
+    st.backward(g.to(dev))
+    gr, gd = O.token_exchange_bwd(g.float().numpy(), ir, idd)
+    np.testing.assert_array_equal(r.grad.float().cpu().numpy(), gr)
+    np.testing.assert_array_equal(d.grad.float().cpu().numpy(), gd)
+
+
+def test_token_axis_fuser_module(dev):
+    import r3d_b200
+    B, T, C = 2, 32, 64
+    rgb, dep = synth(B, T, C, 3)
+    w = (1.0 + torch.arange(T, dtype=torch.float32) / T).view(1, T, 1)
+    rgb, dep = rgb * w, dep * w.flip(1)
+    f = r3d_b200.CMFuser(C, depth=1, num_heads=4, select_axis="token").to(dev).eval()
+    r = rgb.to(dev).requires_grad_(True)
+    d = dep.to(dev).requires_grad_(True)
+    y = f({"rgb": r, "depth": d}, "test")
+    assert y.shape == (B, T, C) and f.last_indices[0].shape == (B, T // 4)
+    np.testing.assert_allclose(f.last_erank[0].cpu().numpy(), EO.erank(rgb.numpy()), rtol=1e-4)
+    y.sum().backward()
+    assert torch.isfinite(r.grad).all() and torch.isfinite(d.grad).all()
+    with pytest.raises(ValueError):
+        r3d_b200.CMFuser(C, variant="vary", select_axis="token")
