@@ -233,7 +233,10 @@ __global__ void jacobi_init_kernel(const float* __restrict__ G, int n, int np, f
       if (threadIdx.x < s) smax[threadIdx.x] = fmaxf(smax[threadIdx.x], smax[threadIdx.x + s]);
       __syncthreads();
     }
-    if (threadIdx.x == 0) nu[b] = smax[0] * nu_ulps * 1.1920929e-7f;   // nu_ulps * 2^-23 (default 4)
+    // nu_ulps > 0: absolute floor nu_ulps * 2^-23 * max|diag| (default 4);  nu_ulps < 0: scale-free mode, stored negative:
+    // a rotation counts as significant when it passes the relative test and at least one of its two diagonal entries
+    // exceeds |nu_ulps| * max|diag| (see jacobi_rotation)
+    if (threadIdx.x == 0) nu[b] = nu_ulps > 0.f ? smax[0] * nu_ulps * 1.1920929e-7f : smax[0] * nu_ulps;
     for (int i = threadIdx.x; i < JMAX_SWEEPS; i += blockDim.x) cnt[b * JMAX_SWEEPS + i] = 0;
   }
 }
@@ -295,7 +298,10 @@ constexpr int SP = JM + 4;   // row pitch of S and Qt: 16-byte aligned rows
 __device__ __forceinline__ bool jacobi_rotation(float spp, float sqq, float spq, float dp, float dq, float tol,
                                                 float nu_abs, float& tau_pq, float& tau_qp, float& c, bool& sig) {
   const bool rt = (spq != 0.f) && (fabsf(spq) > tol * sqrtf(fabsf(spp * sqq)));
-  sig = rt && (fabsf(spq) * dp * dq > nu_abs);
+  // significance (what keeps the sweeps going): an absolute floor on the true off-diagonal entry (nu_abs > 0), or --
+  // for a graded matrix, whose entries are accurate relative to their own rows (the second pass) -- the relative test
+  // itself unless both directions lie below the numerical-rank cut-off (-nu_abs), where only noise is left
+  sig = rt && (nu_abs >= 0.f ? fabsf(spq) * dp * dq > nu_abs : fmaxf(fabsf(spp) * dp * dp, fabsf(sqq) * dq * dq) > -nu_abs);
   tau_pq = 0.f; tau_qp = 0.f; c = 1.f;
   if (rt) {
     const float r = __fdividef(dq, dp);                                  // d_q / d_p
@@ -521,7 +527,7 @@ __device__ __forceinline__ bool jacobi_rotation_fast(float spp, float sqq, float
                                                      float nu_abs, float& tau_pq, float& tau_qp, float& c, bool& sig) {
   const float dpq = dp * dq;
   const bool rt = spq * spq > tol2 * fabsf(spp * sqq);
-  sig = rt && (fabsf(spq) * dpq > nu_abs);
+  sig = rt && (nu_abs >= 0.f ? fabsf(spq) * dpq > nu_abs : fmaxf(fabsf(spp) * dp * dp, fabsf(sqq) * dq * dq) > -nu_abs);
   tau_pq = 0.f; tau_qp = 0.f; c = 1.f;
   if (rt) {
     const float rp = __frcp_rn(dpq);                 // dp, dq in [2^-32, 1]: dpq >= 2^-64, no overflow
