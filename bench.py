@@ -5,18 +5,23 @@
 
 Workload (BASELINE.json configs[1], the config the metric is quoted on): per GPU,
 B=64 clips of RGB+depth features, T=512 tokens, C=512 channels, bf16.  One "step" is
-one pass of the hot path over that batch, forward and backward:
+one TRAINING pass of the fuser path over that batch (r3d_b200.ops.FuserTrainStep):
     erank(rgb), erank(depth)  [Gram -> block Jacobi -> refinement -> entropy/exp]
-    channel score -> [all-reduce] -> bottom-k -> exchange/stack           (forward)
-    exchange backward of an upstream gradient + d(mean erank)/dX accumulated (backward)
-N > 1: one process per GPU (torchrun), batch-sharded (weak scaling); the only
-collective is one all-reduce of the packed (2C + 2)-float score/erank statistic.
+    CMFuser.forward: channel score -> [all-reduce] -> bottom-k -> exchange/stack -> Block (LayerNorm, V / proj /
+                     MLP GEMMs on tcgen05) -> LayerNorm -> mean over the two modality tokens            (forward)
+    backward of an upstream gradient through CMFuser (input + parameter gradients), d(mean erank)/dX
+    accumulated, and with N > 1 the all-reduce of the fuser's parameter gradients                    (backward)
+N > 1: one process per GPU (torchrun), batch-sharded: weak scaling by default (B=64 per GPU), strong scaling with
+--global-batch G (configs[2]: G=512).  Collectives: one all-reduce of the packed (2C + 2)-float score / erank
+statistic in the forward, one all-reduce of the flat fp32 parameter gradients (13.7 MB at C=512) in the backward,
+issued on a side stream beside the effective-rank backward.
 
 `value`  : clips/s with inputs resident in HBM (CUDA events, max over ranks).
 `e2e`    : same metric with each step's inputs copied from pinned host memory and the
            step's erank statistic read back, inside the timed region.
-`--impl reference`: the reference's CPU path (torch-CPU port of the reference fuser in
-           oracle/torch_port.py + the svdvals erank restatement) on the host cores.
+`--impl reference`: the reference's CPU path on the host cores: the reference's own CMFuser (staged under oracle/_ref by
+           oracle/build_ref.py; the torch-CPU port of oracle/torch_port.py when that directory is absent) forward +
+           backward, plus the svdvals erank restatement (the reference has no effective-rank code) forward + backward.
 """
 import argparse
 import json
@@ -46,6 +51,8 @@ def parse():
     ap.add_argument("--gram", default="auto", choices=["auto", "tcgen05", "simt"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--opt", action="append", default=[], help="library tuning knob key=value (r3d_set_option)")
+    ap.add_argument("--global-batch", type=int, default=0, help="strong scaling: total clips per step, split over the ranks")
+    ap.add_argument("--no-yardstick", action="store_true", help="skip the same-GPU library eigensolver yardstick")
     return ap.parse_args()
 
 
@@ -62,33 +69,61 @@ def synth_host(seed, b, dtype):
 # CPU leg: the reference's own algorithm on the host cores (oracle port; "kind": "port")
 # ------------------------------------------------------------------------------------
 def cpu_step_factory(sample):
+    """-> (step, kind): the reference's own CMFuser when oracle/_ref (or /root/reference) is present, else the port."""
     import torch
     from oracle.torch_port import PortCMFuser, erank_torch
+    from oracle import ref_loader
     torch.set_num_threads(os.cpu_count() or 1)
-    fuser = PortCMFuser(C, depth=1, num_heads=8, variant="tokenfusion")
+    torch.manual_seed(0)
+    cls = ref_loader.load("tokenfusion")
+    if cls is not None:
+        fuser, kind = cls(dim=C, depth=1, num_heads=8), "reference"
+    else:
+        fuser, kind = PortCMFuser(C, depth=1, num_heads=8, variant="tokenfusion"), "port"
+    fuser.train()
+    fuser.embd_drop.p = 0.0                                     # dropout off on both arms (parity, determinism)
     buf = synth_host(1234, sample, torch.bfloat16).float()     # fp32 on the bf16-rounded inputs
-    gst = torch.randn(sample, T, 2, C, generator=torch.Generator().manual_seed(4321))
+    gy = torch.randn(sample, T, C, generator=torch.Generator().manual_seed(4321))
 
     def step():
         rgb = buf[0].clone().requires_grad_(True)
         dep = buf[1].clone().requires_grad_(True)
-        st = fuser.token_fusion(rgb, dep, "test")
+        fuser.zero_grad(set_to_none=True)
+        y = fuser({"rgb": rgb, "depth": dep}, "test")
         er = torch.cat([erank_torch(rgb), erank_torch(dep)])
-        torch.autograd.backward([st, er], [gst, torch.full_like(er, 1.0 / er.numel())])
+        torch.autograd.backward([y, er], [gy, torch.full_like(er, 1.0 / er.numel())])
         return float(er.detach().mean())
 
-    return step
+    return step, kind
+
+
+def cpu_gram_route_ms(sample):
+    """Extra yardstick: the effective-rank forward through the cheaper CPU route (fp32 Gram + eigvalsh, BASELINE.md
+    section 2 measured it 2.6x faster than svdvals at this shape) -- ms per clip pair (rgb + depth)."""
+    import torch
+    x = synth_host(1234, sample, torch.bfloat16).float().reshape(2 * sample, T, C)
+    t0 = time.perf_counter()
+    lam = torch.linalg.eigvalsh(x.transpose(1, 2) @ x)
+    sg = lam.clamp_min(0).sqrt()
+    p = sg / sg.sum(-1, keepdim=True)
+    _ = torch.exp(-(p * torch.log(p.clamp_min(1e-30))).sum(-1))
+    return (time.perf_counter() - t0) * 1e3 / sample
 
 
 def run_cpu(steps, warmup, sample):
-    step = cpu_step_factory(sample)
+    step, kind = cpu_step_factory(sample)
     for _ in range(warmup):
         step()
     t0 = time.perf_counter()
     for _ in range(steps):
         step()
     dt = time.perf_counter() - t0
-    return sample * steps / dt, dt / steps * 1e3
+    return sample * steps / dt, dt / steps * 1e3, kind
+
+
+CPU_SAMPLE_TEXT = ("{n} clips/step of the same shape (T=512, C=512): the reference's CMFuser forward + backward "
+                   "({kind}; train mode, dropout 0, eval-branch score) + the svdvals effective-rank restatement forward "
+                   "+ backward for both modalities, fp32 on the bf16-rounded inputs")
 
 
 def main_reference(args):
@@ -97,17 +132,20 @@ def main_reference(args):
         return
     import torch
     sample = args.cpu_sample
-    val, ms = run_cpu(args.steps, args.warmup, sample)
+    val, ms, kind = run_cpu(args.steps, args.warmup, sample)
     cores = torch.get_num_threads()
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"DARai RGB+depth fuser fwd+bwd, T={T}, C={C} (BASELINE.json configs[1]); CPU step = "
-                               f"{sample} clips of that shape", "B_per_step": sample, "T": T, "C": C},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{sample} clips/step x {args.steps} steps: torch-CPU port of the reference "
-                                   "token_fusion fwd+bwd + svdvals erank restatement fwd+bwd, fp32"},
+        "config": {"workload": f"DARai RGB+depth fuser training step fwd+bwd, T={T}, C={C} (BASELINE.json configs[1]); CPU "
+                               f"step = {sample} clips of that shape", "B_per_step": sample, "cpu_clips_per_step": sample,
+                   "T": T, "C": C},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": CPU_SAMPLE_TEXT.format(n=sample, kind="oracle/_ref: unmodified reference module"
+                                                          if kind == "reference" else "torch-CPU port") +
+                                   f" x {args.steps} steps",
+                         "erank_part": "restatement (the reference has no effective-rank code, SURVEY.md F1)"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -226,14 +264,14 @@ def peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
 
 
-def stage_table(prof, steps, world, panel_tiles=None):
+def stage_table(prof, steps, world, panel_tiles=None, B=B):
     """Per-stage algorithmic bytes / flops per launch -> achieved and fraction of peak.
     The Jacobi launch sequence is fixed and launches after convergence exit at once, so for the panel passes the
     algorithmic bytes of the region are counted by the kernel itself (tiles actually processed x 64 KB) and divided
     by the stage's total time -- not launches x one full pass."""
     pk = peaks()
     es = 2                       # bf16 inputs
-    N = B * T * C                # elements per modality per rank
+    N = B * T * C                # elements per modality per rank (B = clips per rank and step)
     n = min(T, C); m = max(T, C); nb2 = 2 * B
     npad = ((n + 63) // 64) * 64
     alg = {
@@ -399,6 +437,34 @@ def full_fuser_numbers(dev, dtype, steps=10):
     return out
 
 
+def library_yardstick(buf, dev):
+    """The same eigen / singular-value problem on the same GPU through the libraries (cuSOLVER behind torch.linalg):
+    the 2B = 128 samples of 512 x 512 of one step.  Forward only (no gradient), one warm-up + one timed call each --
+    answers "does the hand-written eigensolver beat the library", independent of the CPU baseline."""
+    import torch
+    x = buf.reshape(-1, T, C).float()
+    out = {"batch": int(x.shape[0]), "shape": [T, C], "dtype": "fp32"}
+
+    def t1(fn):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
+
+    try:
+        G = x.transpose(1, 2) @ x
+        out["torch_linalg_eigh_on_gram_ms"] = t1(lambda: torch.linalg.eigh(G))
+        out["torch_linalg_eigvalsh_on_gram_ms"] = t1(lambda: torch.linalg.eigvalsh(G))
+        out["torch_linalg_svdvals_ms"] = t1(lambda: torch.linalg.svdvals(x))
+    except Exception as ex:   # pragma: no cover
+        out["error"] = repr(ex)[:200]
+    return out
+
+
 def main_ours(args):
     import torch
     import torch.distributed as dist
@@ -424,13 +490,21 @@ def main_ours(args):
         _lib.set_option(k_, float(v_))
     dtype = torch.bfloat16
     gram_impl = {"auto": ops.GRAM_TCGEN05, "tcgen05": ops.GRAM_TCGEN05, "simt": ops.GRAM_SIMT}[args.gram]
-    step = ops.FuserStep(B, T, C, dtype, dev, gram_impl=gram_impl)
-    host_in = [synth_host(1234 + rank * 100 + i, B, dtype).pin_memory() for i in range(NSETS)]
+    Bl = B                                        # clips per rank and step
+    if args.global_batch:
+        if args.global_batch % world:
+            raise SystemExit("--global-batch must be a multiple of the number of ranks")
+        Bl = args.global_batch // world
+    torch.manual_seed(0)                          # identical (replicated) fuser weights on every rank
+    fuser = r3d_b200.CMFuser(C, depth=1, num_heads=8, score_scope="global").to(dev).to(dtype).train()
+    fuser.embd_drop.p = 0.0                       # dropout off on both arms (parity, determinism)
+    step = ops.FuserTrainStep(fuser, Bl, T, C, dtype, dev, gram_impl=gram_impl)
+    host_in = [synth_host(1234 + rank * 100 + i, Bl, dtype).pin_memory() for i in range(NSETS)]
     dev_in = [h.to(dev) for h in host_in]
     gg = torch.Generator(device=dev).manual_seed(4321 + rank)
-    dev_g = [torch.randn(B, T, 2, C, generator=gg, device=dev).to(dtype) for _ in range(NSETS)]
+    dev_g = [torch.randn(Bl, T, C, generator=gg, device=dev).to(dtype) for _ in range(NSETS)]
     stage_buf = torch.empty_like(dev_in[0])
-    er_host = torch.empty(2 * B, dtype=torch.float32).pin_memory()
+    er_host = torch.empty(2 * Bl, dtype=torch.float32).pin_memory()
 
     def barrier():
         torch.cuda.synchronize()
@@ -477,7 +551,7 @@ def main_ours(args):
         if i + 1 < e2e_state["steps"]:
             issue_copy(i + 1)
         main.wait_event(ev_copied[i % 2])
-        _, er, _ = step(stage[i % 2], dev_g[i % NSETS])
+        _, er, _, _ = step(stage[i % 2], dev_g[i % NSETS])
         ev_consumed[i % 2].record(main)
         er_host.copy_(er, non_blocking=True)                            # D2H of the step's statistic
         main.synchronize()
@@ -511,16 +585,29 @@ def main_ours(args):
     e2e_state["steps"] = args.steps
     ms_e2e = timed(end_to_end, args.steps)
 
-    value = world * B * args.steps / (ms * 1e-3)
-    e2e = world * B * args.steps / (ms_e2e * 1e-3)
+    # the gradient all-reduce alone (N > 1): K back-to-back reductions of the flat fp32 bucket, max over ranks
+    ar = None
+    if world > 1:
+        ar_ms = timed(lambda i: step.bucket.allreduce(average=True), args.steps) / args.steps
+        ar = {"ms": ar_ms, "bytes": int(step.bucket.flat.numel() * 4),
+              "note": "flat fp32 parameter-gradient bucket: copy in + NCCL all-reduce + copy out, timed alone; inside the "
+                      "step it runs on a side stream beside the effective-rank backward"}
+    value = world * Bl * args.steps / (ms * 1e-3)
+    e2e = world * Bl * args.steps / (ms_e2e * 1e-3)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-    stages, pk = stage_table(prof, args.steps, world, tiles)
-    isolated = isolated_stage_numbers(dev_in, dev_g, pk) if world == 1 else None
-    dom = max(stages.items(), key=lambda kv: kv[1]["ms_per_step"])
-    dname, d = dom
+    stages, pk = stage_table(prof, args.steps, world, tiles, Bl)
+    isolated = None
+    if world == 1 and not args.global_batch:
+        gst = [torch.randn(Bl, T, 2, C, generator=gg, device=dev).to(dtype) for _ in range(NSETS)]
+        isolated = isolated_stage_numbers(dev_in, gst, pk)
+        del gst
+    largest = max(stages.items(), key=lambda kv: kv[1]["ms_per_step"])[0]
+    # the roofline object is for the dominant kernel that HAS a roofline (HBM- or tensor-bound); the inner Jacobi
+    # solver is bound by instruction issue and is reported under `stages` only
+    dname, d = max(((k, v) for k, v in stages.items() if v.get("frac") is not None), key=lambda kv: kv[1]["ms_per_step"])
     traffic = None
     tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
     if os.path.exists(tp):
@@ -529,34 +616,50 @@ def main_ours(args):
     roofline = {"kernel": dname, "bound": d.get("bound", "hbm"), "achieved": d.get("achieved"),
                 "peak": d.get("peak"), "unit": d.get("unit", "GB/s"), "frac": d.get("frac"),
                 "peak_source": pk["source"], "traffic": traffic,
-                "share_of_step": d["ms_per_step"] / (ms_prof / args.steps)}
+                "bytes_basis": "kernel traffic: tiles the kernel actually processed x 64 KB (32 KB read + 32 KB written "
+                               "of fp32 working matrix) / the stage's total time, not an algorithmic lower bound"
+                               if dname.startswith("jacobi") else "algorithmic bytes / flops of the stage (DESIGN.md section 4)",
+                "share_of_step": d["ms_per_step"] / (ms_prof / args.steps), "largest_stage_by_time": largest}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "DARai RGB+depth fuser fwd+bwd bf16 B=64 T=512 C=512 per GPU (BASELINE.json configs[1]): "
-                               "erank(rgb,depth) + score/bottom-k/exchange fwd + exchange/erank bwd",
-                   "B_per_gpu": B, "T": T, "C": C, "global_batch": B * world, "parallelism": f"dp{world}",
-                   "l2": f"{NSETS} rotating input+grad sets ({NSETS * 2 * 2 * B * T * C * 2 / 1e6:.0f} MB) > 126 MB L2",
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if args.global_batch else "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": ("DARai RGB+depth fuser training step fwd+bwd bf16 B=64 T=512 C=512 per GPU (BASELINE.json "
+                                "configs[1])" if not args.global_batch else
+                                f"NTU RGB+D-shaped fuser training step, global batch {args.global_batch} sharded over the ranks "
+                                "(BASELINE.json configs[2]; T=512, C=512 bf16 -- the config names no T/C)") +
+                               ": erank(rgb, depth) fwd + CMFuser fwd (score/bottom-k/exchange + Block + LN + token mean) + "
+                               "CMFuser bwd (input and parameter gradients) + erank bwd + parameter-gradient all-reduce",
+                   "B_per_gpu": Bl, "T": T, "C": C, "global_batch": Bl * world, "parallelism": f"dp{world}",
+                   "dropout": "p=0 on both arms",
+                   "l2": f"{NSETS} rotating input+grad sets ({NSETS * 3 * Bl * T * C * 2 / 1e6:.0f} MB) > 126 MB L2",
                    "jacobi_sweeps_mean": sweeps, "jacobi_not_converged": not_converged, "erank_mean": er_mean, "gram": args.gram},
         "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
-                "h2d_bytes_per_step": int(2 * B * T * C * 2), "d2h_bytes_per_step": int(2 * B * 4)},
+                "h2d_bytes_per_step": int(2 * Bl * T * C * 2), "d2h_bytes_per_step": int(2 * Bl * 4)},
         "gpu_launches": int(launches),
         "clocks": clk,
         "roofline": roofline,
         "ms_per_step_with_stage_events": ms_prof / args.steps,
         "stages": stages,
     }
+    if ar:
+        line["grad_allreduce"] = ar
     if isolated:
         line["stages_isolated"] = isolated
-    if world == 1:
+    if world == 1 and not args.global_batch:
         line["full_fuser_fwd_bwd"] = full_fuser_numbers(dev, dtype)
+        if not args.no_yardstick:
+            line["gpu_library_yardstick"] = library_yardstick(dev_in[0], dev)
     if world == 1 and not args.no_cpu_baseline:
-        val, cms = run_cpu(4, 1, args.cpu_sample)
-        line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                                "sample": f"{args.cpu_sample} clips/step x 4 steps (1 warm-up) of the same shape: "
-                                          "torch-CPU port of the reference token_fusion fwd+bwd + svdvals erank "
-                                          "restatement fwd+bwd, fp32 on the bf16-rounded inputs"}
+        val, cms, kind = run_cpu(4, 1, args.cpu_sample)
+        line["config"]["cpu_clips_per_step"] = args.cpu_sample
+        line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
+                                "sample": CPU_SAMPLE_TEXT.format(n=args.cpu_sample,
+                                                                 kind="oracle/_ref: unmodified reference module"
+                                                                 if kind == "reference" else "torch-CPU port") +
+                                          " x 4 steps (1 warm-up)",
+                                "erank_part": "restatement (the reference has no effective-rank code, SURVEY.md F1)",
+                                "erank_fwd_gram_eigvalsh_ms_per_clip": cpu_gram_route_ms(min(args.cpu_sample, 8))}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -102,6 +102,12 @@ int r3d_score_finalize(const float* partial, int64_t rows, int64_t C, float* sum
  * then 0).  This buffer is what global-score mode all-reduces; r3d_bottomk_scaled consumes it. */
 int r3d_score_finalize_packed(const float* partial, int64_t rows, int64_t C, const float* er, int64_t n_er,
                               float* packed_out, void* stream);
+/* The same packed statistic from column-sum partials that the producers of rgb / depth emitted as a by-product
+ * (r3d_gemm's colsum_partial of the RGB embedding, tokenfusion.py:179-183; r3d_ln_relu_fwd's of the depth projection,
+ * :194-197): part_r (parts_r, C), part_d (parts_d, C) -> packed_out (2C + 2).  With it the separate score pass (a1)
+ * disappears from the launch list. */
+int r3d_score_pack(const float* part_r, int64_t parts_r, const float* part_d, int64_t parts_d, int64_t rows, int64_t C,
+                   const float* er, int64_t n_er, float* packed_out, void* stream);
 
 /* ---- a4: bottom-k -----------------------------------------------------------
  * Replaces  torch.topk(score, k, dim=-1, largest=False)[1]  for `nvec` score
@@ -189,6 +195,47 @@ size_t r3d_jacobi_workspace_bytes(int64_t B, int64_t n);
 int r3d_token_informativeness(const float* sigma, const float* U, int64_t B, int64_t n, float rtol,
                               float* score_out, void* stream);
 
+/* ---- f1 / f2 / f3: linear-layer GEMM on tcgen05 with fused epilogues ---------------------------------------
+ * Replaces nn.Linear + the elementwise ops around it in the fuser Block (model/extras/transformerblock.py:79-93,
+ * 118-135 as called from model/futr_safuser_tokenfusion.py:86-95) and in the input projections
+ * (tokenfusion.py:111,143,179-197), forward and backward:
+ *     D (M, N) = epilogue( sum_k A[m, k] * B[n, k] ),   row-major D with pitch N.
+ * a_kmajor: A is stored (M, K) [1] or (K, M) [0];  b_kmajor: B is stored (N, K) [1, an nn.Linear weight] or (K, N) [0].
+ *     forward            Y  = X W^T      A = X (1),  B = W (1)
+ *     input gradient     dX = dY W       A = dY (1), B = W (0)
+ *     weight gradient    dW = dY^T X     A = dY (0), B = X (0)       (split along K internally, fixed-order reduce)
+ * dtype R3D_BF16: bf16 operands / outputs, fp32 accumulate.  R3D_F32: fp32 tensors, computed from three bf16 planes
+ * per operand (six plane products, ~2^-24 relative) -- needs the workspace.  The contiguous dimension of A and B must
+ * be a multiple of 8 elements, bases 16-byte aligned.
+ * Epilogue (NULL = none; every member optional; applied in this order to the fp32 accumulator x):
+ *     x += bias[n];  aux_out[m, n] = x;  x = act(x);  x *= gelu'(aux_in[m, n]);  x += residual[m, n];  D[m, n] = x;
+ *     colsum_partial[m / 128][n] = sum over the 128-row tile of D[m, n] (|D[m, n]| with colsum_abs), rounded values:
+ *     ceil(M / 128) partial rows, finalised by r3d_colsum_finalize -- the bias gradient of the NEXT layer down, or the
+ *     channel-score sums of tokenfusion.py:49-50 for free.
+ * bias (N), residual / aux_* (M, N) have the output dtype.  Weight-gradient calls (split-K) take no epilogue. */
+typedef struct r3d_epilogue {
+  const void* bias;
+  const void* residual;
+  void* aux_out;
+  const void* aux_in;
+  float* colsum_partial;
+  int act;         /* 0 none, 1 GELU (erf form, nn.GELU default), 2 ReLU */
+  int colsum_abs;
+} r3d_epilogue;
+size_t r3d_gemm_workspace_bytes(int64_t M, int64_t N, int64_t K, int dtype);
+int r3d_gemm(const void* A, const void* B, void* D, int64_t M, int64_t N, int64_t K, int a_kmajor, int b_kmajor,
+             int dtype, const r3d_epilogue* epi, void* workspace, void* stream);
+/* out (N) of dtype `dtype` = sum over `parts` partial rows (fixed order). */
+int r3d_colsum_finalize(const float* partial, int64_t parts, int64_t N, int dtype, void* out, void* stream);
+/* out (C) = column sums of x (rows, C) -- the bias gradient of a Linear whose output gradient is x; two fixed-order
+ * stages.  workspace: r3d_colsum_workspace_floats(rows, C) floats. */
+size_t r3d_colsum_workspace_floats(int64_t rows, int64_t C);
+int r3d_colsum(const void* x, int64_t rows, int64_t C, int dtype, float* workspace, void* out, void* stream);
+/* ReLU backward of the input projections (F.relu at tokenfusion.py:183,197): dpre (rows, C) = y > 0 ? dy : 0 and
+ * dbias (C) = column sums of dpre in one pass (same workspace size as r3d_colsum). */
+int r3d_relu_bwd(const void* dy, const void* y, int64_t rows, int64_t C, int dtype, float* workspace, void* dpre,
+                 void* dbias, void* stream);
+
 /* ---- N1: token-axis selection (north_star kernels 3-6) -----------------------------------------------------
  * No reference symbol: the reference ships only the channel exchange (model/futr_safuser_tokenfusion.py:33-66,
  * SURVEY.md F2) and describes the token form in prose (README.md:13).  PARITY UNPINNED; oracle:
@@ -227,6 +274,26 @@ int r3d_ln_fwd(const void* x, const void* gamma, const void* beta, int64_t rows,
                int pair_mean, void* y, float* mean, float* rstd, void* stream);
 int r3d_ln_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const void* gamma, int64_t rows,
                int64_t C, int dtype, int pair_mean, void* dx, float* workspace, float* dgamma_dbeta, void* stream);
+/* The same two kernels with the Block's row swap and residual gradient fused in.  flags: bit 0 = pair_mean, bit 1 =
+ * swap the two rows of every pair (forward: row r is written to row r ^ 1; backward: dy is read from row r ^ 1) --
+ * the closed-form 2-token attention hands token m the V of token 1 - m, and swapping inside norm1 keeps
+ * every GEMM of the Block plain.  addend (backward, may be NULL): dx += addend, the gradient arriving over the
+ * residual connection. */
+int r3d_ln_fwd2(const void* x, const void* gamma, const void* beta, int64_t rows, int64_t C, int dtype, float eps,
+                int flags, void* y, float* mean, float* rstd, void* stream);
+int r3d_ln_bwd2(const void* dy, const void* x, const float* mean, const float* rstd, const void* gamma, int64_t rows,
+                int64_t C, int dtype, int flags, const void* addend, void* dx, float* workspace, float* dgamma_dbeta,
+                void* stream);
+/* f2 tail -- depth projection (model/futr_safuser_tokenfusion.py:195-197): y = relu(LayerNorm(x)) in one pass, with the
+ * channel-score partial sums of |y| (tokenfusion.py:49-50) as a by-product: colsum_partial gets r3d_ln_relu_parts(rows)
+ * rows of C floats, finalised by r3d_colsum_finalize.  The backward masks dy by the ReLU (recomputed, y is not needed)
+ * and applies the LayerNorm backward; dgamma_dbeta (2, C) float. */
+int64_t r3d_ln_relu_parts(int64_t rows);
+int r3d_ln_relu_fwd(const void* x, const void* gamma, const void* beta, int64_t rows, int64_t C, int dtype, float eps,
+                    void* y, float* mean, float* rstd, float* colsum_partial, void* stream);
+int r3d_ln_relu_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const void* gamma,
+                    const void* beta, int64_t rows, int64_t C, int dtype, void* dx, float* workspace,
+                    float* dgamma_dbeta, void* stream);
 /* Residual add of the closed-form 2-token attention: out[row] = a[row] + b[row ^ 1] (token m receives the projected
  * V of token 1-m: transformerblock.py:19-36 with the -inf diagonal mask of tokenfusion.py:68-72), which
  * replaces  x + proj(v.flip(1)).  a == NULL gives the pair-swapped copy (its backward).  rows even. */

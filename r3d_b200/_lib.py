@@ -32,6 +32,7 @@ SIGNATURES = {
     "r3d_score_finalize": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
     "r3d_bottomk": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p]),
     "r3d_score_finalize_packed": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p]),
+    "r3d_score_pack": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p]),
     "r3d_bottomk_scaled": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "r3d_bn_workspace_floats": (c_size_t, [c_int64, c_int64]),
     "r3d_bn_stats": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
@@ -53,6 +54,13 @@ SIGNATURES = {
                                 c_void_p]),
     "r3d_jacobi_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "r3d_token_informativeness": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_float, c_void_p, c_void_p]),
+    "r3d_gemm_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int]),
+    "r3d_gemm": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_int, c_int, c_void_p, c_void_p,
+                         c_void_p]),
+    "r3d_colsum_finalize": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p]),
+    "r3d_colsum_workspace_floats": (c_size_t, [c_int64, c_int64]),
+    "r3d_colsum": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
+    "r3d_relu_bwd": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "r3d_token_scores": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_float, c_void_p, c_void_p]),
     "r3d_token_mask": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p]),
     "r3d_token_exchange_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p]),
@@ -64,10 +72,25 @@ SIGNATURES = {
                            c_void_p, c_void_p]),
     "r3d_ln_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p,
                            c_void_p, c_void_p, c_void_p]),
+    "r3d_ln_fwd2": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_float, c_int, c_void_p, c_void_p,
+                            c_void_p, c_void_p]),
+    "r3d_ln_bwd2": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p,
+                            c_void_p, c_void_p, c_void_p, c_void_p]),
+    "r3d_ln_relu_parts": (c_int64, [c_int64]),
+    "r3d_ln_relu_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_float, c_void_p, c_void_p, c_void_p,
+                                c_void_p, c_void_p]),
+    "r3d_ln_relu_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int,
+                                c_void_p, c_void_p, c_void_p, c_void_p]),
     "r3d_swap_add": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p]),
     "r3d_token_fusion_host": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_int64, c_void_p,
                                       c_void_p, c_void_p, c_void_p]),
 }
+
+
+class Epilogue(ctypes.Structure):
+    """struct r3d_epilogue (include/r3d_b200.h)."""
+    _fields_ = [("bias", c_void_p), ("residual", c_void_p), ("aux_out", c_void_p), ("aux_in", c_void_p),
+                ("colsum_partial", c_void_p), ("act", c_int), ("colsum_abs", c_int)]
 
 
 class R3DError(RuntimeError):

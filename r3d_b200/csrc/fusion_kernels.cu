@@ -728,6 +728,57 @@ extern "C" int r3d_score_finalize(const float* partial, int64_t rows, int64_t C,
   return 0;
 }
 
+// Packed statistic from column-sum partials that other kernels produced as a by-product (the GEMM epilogue of the RGB
+// embedding, the LayerNorm+ReLU kernel of the depth projection): blockIdx.y = modality, its own number of partial rows.
+__global__ void __launch_bounds__(256) score_pack_kernel(const float* __restrict__ part_r, int parts_r,
+                                                         const float* __restrict__ part_d, int parts_d, int64_t rows,
+                                                         int64_t C, const float* __restrict__ er, int n_er,
+                                                         float* __restrict__ packed) {
+  __shared__ float red[8][33];
+  const int cl = threadIdx.x & 31, g = threadIdx.x >> 5;
+  if (blockIdx.x == 0 && blockIdx.y == 0) {
+    __shared__ float ered[256];
+    float a = 0.f;
+    for (int i = threadIdx.x; i < n_er; i += 256) a += er[i];
+    ered[threadIdx.x] = a;
+    __syncthreads();
+    for (int st = 128; st > 0; st >>= 1) {
+      if (threadIdx.x < st) ered[threadIdx.x] += ered[threadIdx.x + st];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) { packed[2 * C] = er ? ered[0] : 0.f; packed[2 * C + 1] = float(rows); }
+  }
+  const float* p = blockIdx.y ? part_d : part_r;
+  const int parts = blockIdx.y ? parts_d : parts_r;
+  const int64_t c = int64_t(blockIdx.x) * 32 + cl;
+  float s = 0.f;
+  if (c < C) {
+    const int per = (parts + 7) / 8;
+    const int i0 = g * per, i1 = min(parts, i0 + per);
+    for (int i = i0; i < i1; ++i) s += p[int64_t(i) * C + c];
+  }
+  red[g][cl] = s;
+  __syncthreads();
+  if (g == 0 && c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k][cl];
+    packed[blockIdx.y * C + c] = t;
+  }
+}
+
+extern "C" int r3d_score_pack(const float* part_r, int64_t parts_r, const float* part_d, int64_t parts_d, int64_t rows,
+                              int64_t C, const float* er, int64_t n_er, float* packed_out, void* stream) {
+  R3D_CHECK(part_r && part_d && packed_out, "null pointer");
+  R3D_CHECK(parts_r >= 1 && parts_d >= 1 && rows >= 1 && C >= 1 && n_er >= 0, "bad shape");
+  dim3 grid((unsigned)((C + 31) / 32), 2);
+  R3D_STAGE(ST_SCORE_FINALIZE, (cudaStream_t)stream);
+  score_pack_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(part_r, (int)parts_r, part_d, (int)parts_d, rows, C, er,
+                                                           (int)n_er, packed_out);
+  R3D_LAUNCH_CHECK();
+  return 0;
+}
+
 extern "C" int r3d_score_finalize_packed(const float* partial, int64_t rows, int64_t C, const float* er, int64_t n_er,
                                          float* packed_out, void* stream) {
   R3D_CHECK(partial != nullptr && packed_out != nullptr, "null pointer");

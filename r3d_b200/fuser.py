@@ -80,6 +80,12 @@ class Block(nn.Module):
 
     def forward(self, x: torch.Tensor, attn_mask=None):
         C = self.dim
+        fc1, fc2 = self.mlp.mlp[0], self.mlp.mlp[2]
+        if ops.fused_block_supported(x, C, fc1.out_features) and self.norm1.elementwise_affine \
+                and self.norm2.elementwise_affine and fc1.bias is not None and fc2.bias is not None \
+                and self.attn.proj.bias is not None:
+            # the whole Block on hand-written kernels: tcgen05 GEMMs with fused epilogues, LayerNorm kernels
+            return ops.fused_block(x, self.norm1, self.attn.qkv, self.attn.proj, self.norm2, fc1, fc2), None
         h = _ln(self.norm1, x)
         w_v = self.attn.qkv.weight[2 * C:]
         b_v = None if self.attn.qkv.bias is None else self.attn.qkv.bias[2 * C:]
@@ -132,6 +138,11 @@ class CMFuser(nn.Module):
         self.process_group = process_group
         self.select_axis = select_axis
         self.last_erank = None
+        # optional per-sample statistic (e.g. the effective ranks of the step) whose SUM rides in the packed score
+        # buffer [sum|rgb| | sum|depth| | sum statistic | rows], so that global scope needs ONE all-reduce for both;
+        # last_packed is that buffer after the (possible) all-reduce
+        self.statistic_extra = None
+        self.last_packed = None
         self.blocks = nn.ModuleList([Block(dim, num_heads, mlp_ratio, qkv_bias) for _ in range(depth)])
         self.norm = nn.LayerNorm(dim)
         self.embd_drop = nn.Dropout(0.1)
@@ -166,8 +177,10 @@ class CMFuser(nn.Module):
             dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=self.process_group)
         return packed
 
-    def select_channels(self, rgb: torch.Tensor, depth: torch.Tensor, mode: str):
-        """score -> bottom-k.  Returns (idx_r, idx_d) int64 (k,) each."""
+    def select_channels(self, rgb: torch.Tensor, depth: torch.Tensor, mode: str, score_parts=None):
+        """score -> bottom-k.  Returns (idx_r, idx_d) int64 (k,) each.  score_parts: optional pair of
+        embed.ScoreParts (the |x| column-sum partials the producers of rgb / depth emitted); the score pass is then
+        skipped."""
         B, T, C = rgb.shape
         k = self.k_for(C)
         if self.variant == "batchnorm":
@@ -179,13 +192,19 @@ class CMFuser(nn.Module):
             idx = torch.arange(k, device=rgb.device, dtype=torch.int64)
             return idx, idx.clone()
         else:
-            packed = self._maybe_allreduce(ops.channel_score_packed(rgb.detach(), depth.detach()))
+            if score_parts is not None and self.variant in ("tokenfusion", "vary"):
+                from .embed import pack_score_parts
+                packed = pack_score_parts(score_parts[0], score_parts[1], self.statistic_extra)
+            else:
+                packed = ops.channel_score_packed(rgb.detach(), depth.detach(), self.statistic_extra)
+            packed = self._maybe_allreduce(packed)
+            self.last_packed = packed
             idx = ops.bottomk_packed(packed, k)        # the mean = sums / rows is formed inside the kernel
             return idx[0], idx[1]
         idx = ops.bottomk(score, k)
         return idx[0], idx[1]
 
-    def token_fusion(self, rgb_feats: torch.Tensor, depth_feats: torch.Tensor, mode: str) -> torch.Tensor:
+    def token_fusion(self, rgb_feats: torch.Tensor, depth_feats: torch.Tensor, mode: str, score_parts=None) -> torch.Tensor:
         """(B,T,C) x2 -> (B,T,2,C).  tokenfusion.py:33-66 / vary.py:34-59 / batchnorm.py:38-77."""
         if self.variant == "safuser":
             raise R3DError("the safuser variant has no token_fusion (futr_safuser_depth.py has none)")
@@ -198,7 +217,7 @@ class CMFuser(nn.Module):
             idx_r, idx_d = ops.bottomk(s_r, T // 4), ops.bottomk(s_d, T // 4)          # (B, k) each, ties -> lower index
             self.last_indices, self.last_erank = (idx_r, idx_d), (er_r, er_d)
             return ops.token_exchange(rgb_feats, depth_feats, idx_r, idx_d)
-        idx_r, idx_d = self.select_channels(rgb_feats, depth_feats, mode)
+        idx_r, idx_d = self.select_channels(rgb_feats, depth_feats, mode, score_parts)
         self.last_indices = (idx_r, idx_d)
         if self.variant == "tokenfusion":
             return ops.exchange(rgb_feats, depth_feats, idx_r, idx_d, None, ops.BLEND_SWAP)
@@ -225,7 +244,7 @@ class CMFuser(nn.Module):
         return ops.token_fusion_bn(rgb, depth, self.alpha, bn_r.weight, bn_r.bias, bn_d.weight, bn_d.bias, mean, var,
                                    idx_r, idx_d, bn_r.eps, use_batch)
 
-    def forward(self, modal_feats: Dict[str, torch.Tensor], mode: Optional[str] = None):
+    def forward(self, modal_feats: Dict[str, torch.Tensor], mode: Optional[str] = None, score_parts=None):
         rgb, depth = modal_feats["rgb"], modal_feats["depth"]
         B, T, C = rgb.shape
         M = len(modal_feats)
@@ -233,7 +252,7 @@ class CMFuser(nn.Module):
             # futr_safuser_depth.py:43-49: concat + learned modality token (no exchange)
             x = torch.stack([rgb, depth], dim=2) + self.modality_token
         else:
-            x = self.token_fusion(rgb, depth, "test" if mode is None else mode)
+            x = self.token_fusion(rgb, depth, "test" if mode is None else mode, score_parts)
         x = self.embd_drop(x.view(B * T, 2, C))
         x_res = x
         for blk in self.blocks:

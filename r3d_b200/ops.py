@@ -540,6 +540,162 @@ def token_informativeness(sigma: torch.Tensor, U: torch.Tensor, rtol: float = DE
 
 
 # ---------------------------------------------------------------------------------
+# f1 / f2 / f3: tcgen05 linear GEMM with fused epilogues (csrc/linear_tcgen05.cu)
+# ---------------------------------------------------------------------------------
+ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
+
+
+def gemm(A: torch.Tensor, B: torch.Tensor, a_kmajor: bool = True, b_kmajor: bool = True, *, bias=None, act: int = 0,
+         residual=None, want_aux: bool = False, aux_in=None, colsum: bool = False, colsum_abs: bool = False, out=None):
+    """D (M, N) = epilogue(sum_k A[m, k] B[n, k]) on the hand-written tcgen05 GEMM (no library call).
+
+    a_kmajor: A is (M, K), else (K, M);  b_kmajor: B is (N, K) [an nn.Linear weight], else (K, N).
+    Epilogue: +bias -> aux (pre-activation copy) -> act -> * gelu'(aux_in) -> +residual -> D; optional column sums of D
+    (returned as (N,) float32 after the fixed-order finalize).  Returns D, or (D, aux, colsum) items as requested."""
+    _need_cuda(A, B, bias, residual, aux_in)
+    dt = _dt(A)
+    if B.dtype != A.dtype:
+        raise R3DError("gemm operands must have the same dtype")
+    A, B = A.contiguous(), B.contiguous()
+    M, K = (A.shape if a_kmajor else A.shape[::-1])
+    N, K2 = (B.shape if b_kmajor else B.shape[::-1])
+    if K != K2:
+        raise R3DError(f"gemm: contraction sizes differ ({K} vs {K2})")
+    L = _lib.lib()
+    dev = A.device
+    with _on(dev):
+        D = torch.empty(M, N, dtype=A.dtype, device=dev) if out is None else out
+        ws = torch.empty(L.r3d_gemm_workspace_bytes(M, N, K, dt), dtype=torch.uint8, device=dev)
+        aux = torch.empty(M, N, dtype=A.dtype, device=dev) if want_aux else None
+        parts = (M + 127) // 128
+        cs = torch.empty(parts, N, dtype=torch.float32, device=dev) if colsum else None
+        ep = _lib.Epilogue()
+        ep.bias = None if bias is None else bias.to(A.dtype).contiguous().data_ptr()
+        ep.residual = None if residual is None else residual.contiguous().data_ptr()
+        ep.aux_out = None if aux is None else aux.data_ptr()
+        ep.aux_in = None if aux_in is None else aux_in.contiguous().data_ptr()
+        ep.colsum_partial = None if cs is None else cs.data_ptr()
+        ep.act, ep.colsum_abs = int(act), int(bool(colsum_abs))
+        check(L.r3d_gemm(_p(A), _p(B), _p(D), M, N, K, int(a_kmajor), int(b_kmajor), dt, ctypes.byref(ep), _p(ws),
+                         _stream()))
+        csum = None
+        if colsum:
+            csum = torch.empty(N, dtype=torch.float32, device=dev)
+            check(L.r3d_colsum_finalize(_p(cs), parts, N, 0, _p(csum), _stream()))
+    outs = [D]
+    if want_aux:
+        outs.append(aux)
+    if colsum:
+        outs.append(csum)
+    return outs[0] if len(outs) == 1 else tuple(outs)
+
+
+def colsum(x: torch.Tensor) -> torch.Tensor:
+    """Column sums of a (rows, C) tensor in its own dtype (deterministic two-stage tree): a bias gradient."""
+    _need_cuda(x)
+    x = x.contiguous()
+    rows, C = x.shape
+    L = _lib.lib()
+    with _on(x.device):
+        ws = torch.empty(L.r3d_colsum_workspace_floats(rows, C), dtype=torch.float32, device=x.device)
+        out = torch.empty(C, dtype=x.dtype, device=x.device)
+        check(L.r3d_colsum(_p(x), rows, C, _dt(x), _p(ws), _p(out), _stream()))
+    return out
+
+
+# ---------------------------------------------------------------------------------
+# f1: the whole fuser Block (transformerblock.py:118-135 with the 2-token mask of tokenfusion.py:68-72, closed form of
+# SURVEY.md F4) as ONE autograd node over hand-written kernels only: 2 LayerNorm + 4 GEMM launches forward,
+# 2 LayerNorm + 8 GEMM + 2 column-sum launches backward; bias / GELU / residual / gelu' / bias-gradient sums live in the
+# GEMM epilogues, the token swap and the residual-gradient add in the LayerNorm kernels.
+# ---------------------------------------------------------------------------------
+def _ln_fwd_raw(x2d, w, b, eps, flags):
+    rows, C = x2d.shape
+    L = _lib.lib()
+    y = torch.empty_like(x2d)
+    mean = torch.empty(rows, dtype=torch.float32, device=x2d.device)
+    rstd = torch.empty(rows, dtype=torch.float32, device=x2d.device)
+    check(L.r3d_ln_fwd2(_p(x2d), _p(w), _p(b), rows, C, _dt(x2d), float(eps), int(flags), _p(y), _p(mean), _p(rstd),
+                        _stream()))
+    return y, mean, rstd
+
+
+def _ln_bwd_raw(dy, x2d, mean, rstd, w, flags, addend):
+    rows, C = x2d.shape
+    L = _lib.lib()
+    dx = torch.empty_like(x2d)
+    ws = torch.empty(L.r3d_ln_bwd_workspace_floats(rows, C), dtype=torch.float32, device=x2d.device)
+    dgb = torch.empty(2, C, dtype=torch.float32, device=x2d.device)
+    check(L.r3d_ln_bwd2(_p(dy), _p(x2d), _p(mean), _p(rstd), _p(w), rows, C, _dt(x2d), int(flags), _p(addend), _p(dx),
+                        _p(ws), _p(dgb), _stream()))
+    return dx, dgb[0], dgb[1]
+
+
+def fused_block_supported(x: torch.Tensor, C: int, hidden: int) -> bool:
+    return (x.is_cuda and x.dtype in _DT and x.dim() == 3 and x.shape[1] == 2 and C % 8 == 0 and hidden % 8 == 0
+            and layer_norm_supported(x, C))
+
+
+class _FusedBlock(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, n1w, n1b, qkv_w, qkv_b, wp, bp, n2w, n2b, w1, b1, w2, b2, eps1, eps2):
+        dt = x.dtype
+        C = x.shape[-1]
+        xc = x.contiguous().view(-1, C)
+        cast = lambda t: None if t is None else t.detach().to(dt).contiguous()
+        n1w_, n1b_, n2w_, n2b_ = cast(n1w), cast(n1b), cast(n2w), cast(n2b)
+        wv = cast(qkv_w[2 * C:])
+        bv = None if qkv_b is None else cast(qkv_b[2 * C:])
+        wp_, bp_, w1_, b1_, w2_, b2_ = cast(wp), cast(bp), cast(w1), cast(b1), cast(w2), cast(b2)
+        with _on(x.device):
+            h1sw, m1, r1 = _ln_fwd_raw(xc, n1w_, n1b_, eps1, 2)          # norm1, rows of each pair swapped on the write
+            vsw = gemm(h1sw, wv, bias=bv)                                 # V of the OTHER token (qkv's V third only)
+            x1 = gemm(vsw, wp_, bias=bp_, residual=xc)                    # x + proj(V[other])
+            h2, m2, r2 = _ln_fwd_raw(x1, n2w_, n2b_, eps2, 0)
+            g1, H = gemm(h2, w1_, bias=b1_, act=ACT_GELU, want_aux=True)  # GELU(fc1) with the pre-activation saved
+            x2 = gemm(g1, w2_, bias=b2_, residual=x1)                     # x1 + fc2
+        ctx.save_for_backward(xc, m1, r1, h1sw, vsw, x1, m2, r2, h2, H, g1, n1w_, wv, wp_, n2w_, w1_, w2_)
+        ctx.meta = (x.shape, qkv_w.shape, qkv_b is not None,
+                    [None if t is None else t.dtype for t in (n1w, n1b, qkv_w, qkv_b, wp, bp, n2w, n2b, w1, b1, w2, b2)])
+        return x2.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, dx2):
+        xc, m1, r1, h1sw, vsw, x1, m2, r2, h2, H, g1, n1w, wv, wp, n2w, w1, w2 = ctx.saved_tensors
+        xshape, qkv_shape, has_qkv_b, pdt = ctx.meta
+        C = xc.shape[1]
+        dx2 = dx2.contiguous().view(-1, C)
+        with _on(dx2.device):
+            db2 = colsum(dx2)
+            dH, db1 = gemm(dx2, w2, True, False, aux_in=H, colsum=True)      # (dx2 W2) * gelu'(H), + column sums = d b1
+            dW2 = gemm(dx2, g1, False, False)
+            dh2 = gemm(dH, w1, True, False)
+            dW1 = gemm(dH, h2, False, False)
+            dx1, dg2, dbt2 = _ln_bwd_raw(dh2, x1, m2, r2, n2w, 0, dx2)       # norm2 backward + residual gradient
+            dbp = colsum(dx1)
+            dvsw = gemm(dx1, wp, True, False)
+            dWp = gemm(dx1, vsw, False, False)
+            dh1sw = gemm(dvsw, wv, True, False)
+            dWv = gemm(dvsw, h1sw, False, False)
+            dx, dg1, dbt1 = _ln_bwd_raw(dh1sw, xc, m1, r1, n1w, 2, dx1)      # norm1 backward (dy read swapped) + residual
+            dqkv = torch.zeros(qkv_shape, dtype=dWv.dtype, device=dWv.device)  # W_q / W_k: exactly zero (SURVEY.md F4)
+            dqkv[2 * C:] = dWv
+            dqkv_b = None
+            if has_qkv_b:
+                dqkv_b = torch.zeros(qkv_shape[0], dtype=dWv.dtype, device=dWv.device)
+                dqkv_b[2 * C:] = colsum(dvsw)
+        g = [dg1, dbt1, dqkv, dqkv_b, dWp, dbp, dg2, dbt2, dW1, db1, dW2, db2]
+        g = [None if (t is None or d is None) else t.to(d) for t, d in zip(g, pdt)]
+        return (dx.view(xshape), *g, None, None)
+
+
+def fused_block(x, norm1, qkv, proj, norm2, fc1, fc2):
+    """x (R, 2, C) -> (R, 2, C): LN -> V -> proj(+swapped residual) -> LN -> MLP(+residual), see _FusedBlock."""
+    return _FusedBlock.apply(x, norm1.weight, norm1.bias, qkv.weight, qkv.bias, proj.weight, proj.bias, norm2.weight,
+                             norm2.bias, fc1.weight, fc1.bias, fc2.weight, fc2.bias, norm1.eps, norm2.eps)
+
+
+# ---------------------------------------------------------------------------------
 # N1: token-axis selection (north_star kernels 3-6; no reference symbol -- the reference ships the channel exchange
 # only, SURVEY.md F2; oracle: oracle/fuser_oracle.py:token_fusion_tokens, parity unpinned)
 # ---------------------------------------------------------------------------------
@@ -732,3 +888,69 @@ class FuserStep:
         check(L.r3d_erank_bwd(_p(self.gvec), _p(self.er), _p(self.sigma), _p(self.U), _p(self.Y), 2 * B, T, C, dt,
                               self.rtol, _p(self.ws_er), _p(self.dgrad), 1, st))
         return self.out, self.er, self.dgrad
+
+
+
+class FuserTrainStep:
+    """One TRAINING step of the fuser path on (2, B, T, C) inputs (rgb = buf[0], depth = buf[1]) -- what bench.py times:
+
+      forward : effective rank of both modalities (2B samples, the collapse statistic / regulariser);
+                CMFuser.forward = channel score -> [one all-reduce of the packed statistic in global scope] -> bottom-k
+                -> exchange -> Block (LayerNorm, V / proj / MLP GEMMs) -> LayerNorm -> mean over the two tokens;
+      backward: an upstream gradient through CMFuser (input and parameter gradients), d(mean erank)/dX accumulated
+                into the input gradients, and -- with more than one rank -- the all-reduce of the fuser's parameter
+                gradients (dist.GradBucket; the reference's nn.DataParallel reduce-add, main_utkinects.py:129) on a side
+                stream, overlapped with the effective-rank backward.
+    """
+
+    def __init__(self, fuser, B, T, C, dtype, device, rtol=DEFAULT_RTOL, gram_impl=GRAM_TCGEN05, group=None,
+                 erank_weight=1.0):
+        from . import dist as D
+        self.fuser, self.B, self.T, self.C, self.dtype, self.device = fuser, B, T, C, dtype, device
+        self.rtol, self.gram_impl, self.group, self.w = float(rtol), int(gram_impl), group, float(erank_weight)
+        L = _lib.lib()
+        n, m = (T, C) if T < C else (C, T)
+        f32 = dict(dtype=torch.float32, device=device)
+        dt = _DT[dtype]
+        self.ws_er = torch.empty(L.r3d_erank_workspace_bytes(2 * B, T, C, dt), dtype=torch.uint8, device=device)
+        self.er = torch.empty(2 * B, **f32)
+        self.sigma = torch.empty(2 * B, n, **f32)
+        self.U = torch.empty(2 * B, n, n, **f32)
+        self.Y = torch.empty(2 * B, n, m, **f32)
+        self.sweeps = torch.empty(2 * B, dtype=torch.int32, device=device)
+        self.world = 1
+        if group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            self.world = torch.distributed.get_world_size(group)
+        self.gvec = torch.full((2 * B,), self.w / float(2 * B * self.world), **f32)   # d(global mean erank)/d erank_b
+        self.bucket = D.GradBucket(fuser.parameters(), group=group) if self.world > 1 else None
+        self.side = torch.cuda.Stream(device=device) if self.world > 1 else None
+        self.allreduce_ms = None
+
+    def __call__(self, buf: torch.Tensor, gy: torch.Tensor):
+        B, T, C = self.B, self.T, self.C
+        L = _lib.lib()
+        dt = _DT[self.dtype]
+        st = _stream()
+        check(L.r3d_erank_fwd(buf.data_ptr(), 2 * B, T, C, dt, self.rtol, self.gram_impl, _p(self.ws_er), _p(self.er),
+                              _p(self.sigma), _p(self.U), _p(self.Y), _p(self.sweeps), st))
+        r = buf[0].detach().requires_grad_(True)
+        d = buf[1].detach().requires_grad_(True)
+        for p in self.fuser.parameters():             # what optimizer.zero_grad(set_to_none=True) does in a training loop
+            p.grad = None
+        self.fuser.statistic_extra = self.er          # its sum rides in the packed score buffer (one all-reduce)
+        y = self.fuser({"rgb": r, "depth": d}, "test")
+        y.backward(gy)
+        main = torch.cuda.current_stream()
+        if self.bucket is not None:                  # gradient all-reduce beside the effective-rank backward
+            self.side.wait_stream(main)
+            with torch.cuda.stream(self.side):
+                self.bucket.allreduce(average=True)
+        n, m = (T, C) if T < C else (C, T)
+        for h, g in ((0, r.grad), (1, d.grad)):      # per modality: B samples each, accumulated into the input gradient
+            o = h * B
+            check(L.r3d_erank_bwd(self.gvec.data_ptr() + o * 4, self.er.data_ptr() + o * 4,
+                                  self.sigma.data_ptr() + o * n * 4, self.U.data_ptr() + o * n * n * 4,
+                                  self.Y.data_ptr() + o * n * m * 4, B, T, C, dt, self.rtol, _p(self.ws_er), _p(g), 1, st))
+        if self.bucket is not None:
+            main.wait_stream(self.side)
+        return y, self.er, r.grad, d.grad

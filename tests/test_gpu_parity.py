@@ -917,3 +917,170 @@ def test_token_axis_fuser_module(dev):
     assert torch.isfinite(r.grad).all() and torch.isfinite(d.grad).all()
     with pytest.raises(ValueError):
         r3d_b200.CMFuser(C, variant="vary", select_axis="token")
+
+
+# ------------------------------------------------------------------ f1: tcgen05 linear GEMM with fused epilogues
+def _gelu_ref(x):
+    return torch.nn.functional.gelu(x)
+
+
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("M,N,K", [(256, 512, 512), (300, 136, 72), (1024, 2048, 512), (128, 64, 64)])
+def test_gemm_forward_epilogues(M, N, K, dt, dev):
+    from r3d_b200 import ops
+    g = torch.Generator().manual_seed(M + N + K)
+    X = (torch.randn(M, K, generator=g) / K ** 0.5).to(dt).to(dev)
+    W = torch.randn(N, K, generator=g).to(dt).to(dev)
+    b = torch.randn(N, generator=g).to(dt).to(dev)
+    R = torch.randn(M, N, generator=g).to(dt).to(dev)
+    tol = dict(rtol=2e-2, atol=2e-2) if dt == torch.bfloat16 else dict(rtol=2e-5, atol=5e-5)
+    ref = X.double() @ W.double().T
+    D = ops.gemm(X, W)
+    torch.testing.assert_close(D.double(), ref, **tol)
+    # bias + GELU with the pre-activation saved, residual, column sums of the stored result
+    D, H, cs = ops.gemm(X, W, bias=b, act=ops.ACT_GELU, residual=R, want_aux=True, colsum=True)
+    pre = ref + b.double()
+    torch.testing.assert_close(H.double(), pre, **tol)
+    want = _gelu_ref(H.double()) + R.double()              # GELU of the STORED pre-activation (what autograd would see)
+    torch.testing.assert_close(D.double(), want, **tol)
+    torch.testing.assert_close(cs.double(), D.double().sum(0), rtol=1e-4, atol=1e-3 * M ** 0.5)
+    # ReLU + |.| column sums (the channel-score epilogue of the input projections)
+    D, cs = ops.gemm(X, W, bias=b, act=ops.ACT_RELU, colsum=True, colsum_abs=True)
+    torch.testing.assert_close(D.double(), torch.relu(pre), **tol)
+    torch.testing.assert_close(cs.double(), D.double().abs().sum(0), rtol=1e-4, atol=1e-3 * M ** 0.5)
+
+
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("M,N,K", [(512, 256, 128), (4096, 512, 512), (264, 72, 136)])
+def test_gemm_backward_forms(M, N, K, dt, dev):
+    """dX = dY W (B operand MN-major) with the gelu' epilogue, dW = dY^T X (both MN-major, split along K)."""
+    from r3d_b200 import ops
+    g = torch.Generator().manual_seed(7 * M + N)
+    X = torch.randn(M, K, generator=g).to(dt).to(dev)
+    W = (torch.randn(N, K, generator=g) / K ** 0.5).to(dt).to(dev)
+    dY = (torch.randn(M, N, generator=g) / N ** 0.5).to(dt).to(dev)
+    H = torch.randn(M, K, generator=g).to(dt).to(dev)
+    tol = dict(rtol=2e-2, atol=2e-2) if dt == torch.bfloat16 else dict(rtol=2e-5, atol=5e-5)
+    dX = ops.gemm(dY, W, True, False)
+    torch.testing.assert_close(dX.double(), dY.double() @ W.double(), **tol)
+    dXg, cs = ops.gemm(dY, W, True, False, aux_in=H, colsum=True)
+    hd = H.double().requires_grad_(True)
+    _gelu_ref(hd).sum().backward()
+    torch.testing.assert_close(dXg.double(), (dY.double() @ W.double()) * hd.grad, **tol)
+    torch.testing.assert_close(cs.double(), dXg.double().sum(0), rtol=1e-4, atol=1e-3 * M ** 0.5)
+    dW = ops.gemm(dY, X, False, False)
+    ref = dY.double().T @ X.double()
+    tolw = dict(rtol=2e-2, atol=2e-2 * M ** 0.5 / 8) if dt == torch.bfloat16 else dict(rtol=1e-5, atol=1e-4)
+    torch.testing.assert_close(dW.double(), ref, **tolw)
+    torch.testing.assert_close(ops.colsum(dY).double(), dY.double().sum(0), rtol=2e-2 if dt == torch.bfloat16 else 1e-5,
+                               atol=1e-2 if dt == torch.bfloat16 else 1e-4)
+
+
+def test_fuser_train_step_vs_oracle(dev):
+    """ops.FuserTrainStep (what bench.py times): fused output and input gradients = CMFuser backward + d(mean erank)/dX,
+    against the torch port (autograd) + the float64 erank oracle; parameter gradients against the port."""
+    import r3d_b200
+    from r3d_b200 import ops
+    from oracle.torch_port import PortCMFuser
+    B, T, C = 3, 32, 64
+    rgb, dep = synth(B, T, C, 21)
+    gy = torch.randn(B, T, C, generator=torch.Generator().manual_seed(8))
+    torch.manual_seed(0)
+    ref = PortCMFuser(C, depth=1, num_heads=4, variant="tokenfusion").train()
+    ref.embd_drop.p = 0.0
+    f = r3d_b200.CMFuser(C, depth=1, num_heads=4, score_scope="global")
+    f.load_state_dict(ref.state_dict())
+    f = f.to(dev).train()
+    f.embd_drop.p = 0.0
+    step = ops.FuserTrainStep(f, B, T, C, torch.float32, dev)
+    buf = torch.stack([rgb, dep]).to(dev)
+    y, er, gr, gd = step(buf, gy.to(dev))
+    r = rgb.clone().requires_grad_(True)
+    d = dep.clone().requires_grad_(True)
+    yr = ref({"rgb": r, "depth": d}, "test")
+    yr.backward(gy)
+    w = np.full(B, 1.0 / (2 * B))
+    g_r = r.grad.numpy() + EO.erank_bwd(rgb.numpy(), w)
+    g_d = d.grad.numpy() + EO.erank_bwd(dep.numpy(), w)
+    np.testing.assert_allclose(y.detach().cpu().numpy(), yr.detach().numpy(), rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(er.cpu().numpy(), np.concatenate([EO.erank(rgb.numpy()), EO.erank(dep.numpy())]), rtol=1e-4)
+    np.testing.assert_allclose(gr.cpu().numpy(), g_r, rtol=1e-3, atol=2e-5)
+    np.testing.assert_allclose(gd.cpu().numpy(), g_d, rtol=1e-3, atol=2e-5)
+    for (n, p), (_, q) in zip(f.named_parameters(), ref.named_parameters()):
+        if q.grad is not None and p.grad is not None:
+            np.testing.assert_allclose(p.grad.cpu().numpy(), q.grad.numpy(), rtol=1e-3,
+                                       atol=1e-4 * max(1.0, q.grad.abs().max().item()), err_msg=n)
+    # the packed statistic carries the erank sum of the step
+    np.testing.assert_allclose(f.last_packed[2 * C].item(), er.sum().item(), rtol=1e-5)
+
+
+# ------------------------------------------------------------------ f2 / f3: input projections with the score by-product
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+def test_rgb_and_depth_embed_vs_torch(dt, dev):
+    """relu(Linear) (tokenfusion.py:179-183) and relu(LN(Linear)) (:194-197) against torch in float64, forward, all
+    gradients, and the |output| column sums that replace the fuser's score pass."""
+    import r3d_b200
+    B, S, K, HW, C = 3, 40, 256, 24 * 24, 128
+    g = torch.Generator().manual_seed(4)
+    feats = torch.randn(B, S, K, generator=g)
+    depth = torch.randn(B, S, 24, 24, generator=g)
+    torch.manual_seed(1)
+    rgbm, depm = r3d_b200.RGBEmbed(K, C), r3d_b200.DepthEmbed(HW, C)
+    with torch.no_grad():
+        depm.depth_layernorm.weight.uniform_(0.5, 1.5)
+        depm.depth_layernorm.bias.uniform_(-0.3, 0.3)
+    ref_r, ref_d = [torch.nn.Linear(K, C).double(), torch.nn.Linear(HW, C).double()]
+    ref_ln = torch.nn.LayerNorm(C).double()
+    ref_r.load_state_dict({k: v.double() for k, v in rgbm.input_embed.state_dict().items()})
+    ref_d.load_state_dict({k: v.double() for k, v in depm.depth_projection.state_dict().items()})
+    ref_ln.load_state_dict({k: v.double() for k, v in depm.depth_layernorm.state_dict().items()})
+    rgbm, depm = rgbm.to(dev).to(dt), depm.to(dev).to(dt)
+    if dt == torch.bfloat16:          # the reference computes on the rounded parameters / inputs too
+        for m_, r_ in ((rgbm.input_embed, ref_r), (depm.depth_projection, ref_d), (depm.depth_layernorm, ref_ln)):
+            r_.load_state_dict({k: v.double().cpu() for k, v in m_.state_dict().items()})
+    f = feats.to(dt).to(dev).requires_grad_(True)
+    d = depth.to(dt).to(dev).requires_grad_(True)
+    y_r, y_d = rgbm(f), depm(d)
+    gy = torch.randn(B, S, C, generator=g)
+    (y_r * gy.to(dt).to(dev)).sum().backward()
+    (y_d * gy.to(dt).to(dev)).sum().backward()
+    f64 = feats.to(dt).double().requires_grad_(True)
+    d64 = depth.to(dt).double().requires_grad_(True)
+    yr = torch.relu(ref_r(f64))
+    yd = torch.relu(ref_ln(ref_d(d64.view(B, S, -1))))
+    (yr * gy.to(dt).double()).sum().backward()
+    (yd * gy.to(dt).double()).sum().backward()
+    tol = dict(rtol=3e-2, atol=3e-2) if dt == torch.bfloat16 else dict(rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(y_r.double().cpu(), yr.detach(), **tol)
+    torch.testing.assert_close(y_d.double().cpu(), yd.detach(), **tol)
+    torch.testing.assert_close(f.grad.double().cpu(), f64.grad, **tol)
+    torch.testing.assert_close(d.grad.double().cpu().view(B, S, -1), d64.grad.view(B, S, -1), **tol)
+    gtol = dict(rtol=5e-2, atol=0.25) if dt == torch.bfloat16 else dict(rtol=1e-4, atol=1e-3)
+    for ours, ref in ((rgbm.input_embed, ref_r), (depm.depth_projection, ref_d), (depm.depth_layernorm, ref_ln)):
+        for (n, p), (_, q) in zip(ours.named_parameters(), ref.named_parameters()):
+            torch.testing.assert_close(p.grad.double().cpu(), q.grad, **gtol, msg=lambda m, n=n: f"{n}: {m}")
+    # score by-products = column sums of |stored output|
+    torch.testing.assert_close(rgbm.last_score.sums().double().cpu(), y_r.detach().double().abs().sum((0, 1)).cpu(),
+                               rtol=1e-4, atol=1e-3)
+    torch.testing.assert_close(depm.last_score.sums().double().cpu(), y_d.detach().double().abs().sum((0, 1)).cpu(),
+                               rtol=1e-4, atol=1e-3)
+
+
+def test_fuser_front_skips_score_pass(dev):
+    """FuserFront (tokenfusion.py:179-199 wiring): the channel selection fed by the producers' by-products equals the
+    selection of the stand-alone score pass, and the fused output equals CMFuser on the embedded tensors."""
+    import r3d_b200
+    from r3d_b200 import _lib
+    B, S, K, HW, C = 2, 48, 128, 16 * 16, 64
+    g = torch.Generator().manual_seed(9)
+    feats, depth = torch.randn(B, S, K, generator=g).to(dev), torch.randn(B, S, 16, 16, generator=g).to(dev)
+    torch.manual_seed(3)
+    front = r3d_b200.FuserFront(K, HW, C, n_head=4).to(dev).eval()
+    y = front(feats, depth, "test")
+    idx = [i.clone() for i in front.fuser.last_indices]
+    src, dep = front.rgb(feats), front.depth(depth)
+    y2 = front.fuser({"rgb": src, "depth": dep}, "test")               # own score pass
+    assert torch.equal(idx[0], front.fuser.last_indices[0]) and torch.equal(idx[1], front.fuser.last_indices[1])
+    torch.testing.assert_close(y, y2, rtol=1e-5, atol=1e-6)
+    ref_idx = O.bottomk(O.channel_score(src.detach().cpu().numpy()), C // 4)
+    np.testing.assert_array_equal(idx[0].cpu().numpy(), ref_idx)
