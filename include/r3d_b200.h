@@ -236,6 +236,29 @@ int r3d_colsum(const void* x, int64_t rows, int64_t C, int dtype, float* workspa
 int r3d_relu_bwd(const void* dy, const void* y, int64_t rows, int64_t C, int dtype, float* workspace, void* dpre,
                  void* dbias, void* stream);
 
+/* ---- N2: M-modality fuser (BASELINE.json configs[4]: RGB + depth + gaze) --------------------------------------
+ * The reference reads M = len(modal_feats) (model/futr_safuser_tokenfusion.py:76) but hard-codes two modalities
+ * (:77,:79).  Semantics fixed here -- for M = 2 exactly the reference, beyond that PARITY UNPINNED (oracle:
+ * oracle/torch_port.py:PortCMFuserM): modality m swaps its k lowest-score channels for those of modality (m+1) mod M;
+ * the Block attends over the M modality tokens with the -inf diagonal mask of tokenfusion.py:68-72 generalised to
+ * M x M; the final LayerNorm is followed by the mean over the M tokens (:93-95).
+ * r3d_exchange_one_fwd: one stream of the stack -- out (row pitch out_pitch, already offset to slot m) =
+ *   c in idx ? other[row, c] : own[row, c].
+ * r3d_exchange_one_bwd: dx of modality j = g_j outside idx_j + g_prev inside idx_prev (prev = (j-1) mod M); g_* point
+ *   at their slots of the stacked gradient, row pitch g_pitch.
+ * r3d_mtoken_attn_fwd / _bwd: qkv (rows, M, 3C) as nn.Linear(C, 3C) lays it out (transformerblock.py:22-23) ->
+ *   out (rows, M, C), softmax over the OTHER tokens per head, scale head_dim^-0.5; 2 <= M <= 4, head_dim a multiple
+ *   of 32 and <= 256.  The backward recomputes the weights.
+ * r3d_token_mean: (rows, M, C) -> (rows, C) mean over the tokens; backward != 0: (rows, C) -> (rows, M, C) / M. */
+int r3d_exchange_one_fwd(const void* own, const void* other, const int64_t* idx, int64_t k, void* out,
+                         int64_t out_pitch, int64_t rows, int64_t C, int dtype, void* stream);
+int r3d_exchange_one_bwd(const void* g_own, const void* g_prev, int64_t g_pitch, const int64_t* idx_own,
+                         const int64_t* idx_prev, int64_t k, void* dx, int64_t rows, int64_t C, int dtype, void* stream);
+int r3d_mtoken_attn_fwd(const void* qkv, void* out, int64_t rows, int M, int64_t C, int heads, int dtype, void* stream);
+int r3d_mtoken_attn_bwd(const void* qkv, const void* dout, void* dqkv, int64_t rows, int M, int64_t C, int heads,
+                        int dtype, void* stream);
+int r3d_token_mean(const void* x, void* out, int64_t rows, int M, int64_t C, int dtype, int backward, void* stream);
+
 /* ---- N1: token-axis selection (north_star kernels 3-6) -----------------------------------------------------
  * No reference symbol: the reference ships only the channel exchange (model/futr_safuser_tokenfusion.py:33-66,
  * SURVEY.md F2) and describes the token form in prose (README.md:13).  PARITY UNPINNED; oracle:

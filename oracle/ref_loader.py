@@ -37,6 +37,13 @@ class _StayOnDevice:
         return self.t
 
 
+def load_futr(variant: str = "tokenfusion"):
+    """-> the reference module's FUTR class with its CMFuser shimmed for the CPU, or None."""
+    if load(variant) is None:
+        return None
+    return importlib.import_module(_MODULES[variant]).FUTR
+
+
 def load(variant: str = "tokenfusion"):
     """-> the reference module's CMFuser class (CPU-runnable), or None when no reference tree is available."""
     root = reference_root()

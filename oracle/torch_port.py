@@ -171,3 +171,49 @@ def erank_torch(x: torch.Tensor, rtol: float = 1e-4) -> torch.Tensor:
     p = s / s.sum(dim=-1, keepdim=True)
     plogp = torch.where(keep, p * torch.log(torch.where(keep, p, torch.ones_like(p))), torch.zeros_like(p))
     return torch.exp(-plogp.sum(dim=-1))
+
+
+
+class PortCMFuserM(nn.Module):
+    """M-modality generalisation of the tokenfusion fuser -- NOT reference code beyond M = 2 (PARITY UNPINNED).
+
+    The reference reads ``M = len(modal_feats)`` (model/futr_safuser_tokenfusion.py:76) but hard-codes the keys
+    'rgb' / 'depth' (:79) and a 2 x 2 mask (:77).  This restates the obvious extension r3d_b200 implements: modality m
+    swaps its k = C // 4 lowest-score channels (eval-branch score, :49-50) for those of modality (m + 1) mod M; the
+    streams are stacked to (B, T, M, C); the Block attends over the M tokens with the M x M -inf-diagonal mask
+    (generate_cross_attention_mask(M), :68-72); outer residual, LayerNorm and the mean over the M tokens as :92-95.
+    For M = 2 it equals PortCMFuser(variant='tokenfusion') -- tests/test_oracle_golden.py checks that."""
+
+    def __init__(self, dim, depth=1, num_heads=4, mlp_ratio=4.0, qkv_bias=False):
+        super().__init__()
+        self.blocks = nn.ModuleList([PortBlock(dim, num_heads, mlp_ratio, qkv_bias) for _ in range(depth)])
+        self.norm = nn.LayerNorm(dim)
+        self.embd_drop = nn.Dropout(0.1)
+        self.modality_token = nn.Parameter(torch.randn(1, 1, 1, dim))
+        self.projection = nn.Linear(dim, dim)
+        self.fusion_conv = nn.Conv2d(2, 1, kernel_size=1)
+
+    def token_fusion(self, feats):
+        M = len(feats)
+        C = feats[0].shape[-1]
+        k = C // 4
+        idx = [torch.sort(f.detach().abs().mean(dim=(0, 1)), stable=True)[1][:k] for f in feats]
+        outs = []
+        for m in range(M):
+            ex = feats[m].clone()
+            ex[:, :, idx[m]] = feats[(m + 1) % M][:, :, idx[m]]
+            outs.append(ex)
+        self.last_indices = idx
+        return torch.stack(outs, dim=2)
+
+    def forward(self, modal_feats, mode="test"):
+        feats = list(modal_feats.values())
+        B, T, C = feats[0].shape
+        M = len(feats)
+        mask = torch.zeros(M, M, dtype=feats[0].dtype).masked_fill(torch.eye(M) == 1, float("-inf"))
+        x = self.embd_drop(self.token_fusion(feats).reshape(B * T, M, C))
+        x_res = x
+        for blk in self.blocks:
+            x, _ = blk(x, mask)
+        x = x + x_res
+        return self.norm(x).mean(dim=1).view(B, T, C)

@@ -9,6 +9,7 @@ from . import ops  # noqa: F401
 from .fuser import (CMFuser, TokenFusionCMFuser, VaryCMFuser, BatchNormCMFuser, SAFuser, Block, VARIANTS)  # noqa: F401
 from .ops import erank, channel_score, bottomk, exchange  # noqa: F401
 from .embed import RGBEmbed, DepthEmbed, FuserFront  # noqa: F401
+from .futr import FUTR  # noqa: F401
 
 __all__ = ["CMFuser", "TokenFusionCMFuser", "VaryCMFuser", "BatchNormCMFuser", "SAFuser", "Block", "ops", "erank",
-           "channel_score", "bottomk", "exchange", "RGBEmbed", "DepthEmbed", "FuserFront", "R3DError", "launch_count", "LIB_PATH", "VARIANTS"]
+           "channel_score", "bottomk", "exchange", "RGBEmbed", "DepthEmbed", "FuserFront", "FUTR", "R3DError", "launch_count", "LIB_PATH", "VARIANTS"]

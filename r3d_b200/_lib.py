@@ -61,6 +61,13 @@ SIGNATURES = {
     "r3d_colsum_workspace_floats": (c_size_t, [c_int64, c_int64]),
     "r3d_colsum": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     "r3d_relu_bwd": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "r3d_exchange_one_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int,
+                                     c_void_p]),
+    "r3d_exchange_one_bwd": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int64,
+                                     c_int, c_void_p]),
+    "r3d_mtoken_attn_fwd": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int64, c_int, c_int, c_void_p]),
+    "r3d_mtoken_attn_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int64, c_int, c_int, c_void_p]),
+    "r3d_token_mean": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int64, c_int, c_int, c_void_p]),
     "r3d_token_scores": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_float, c_void_p, c_void_p]),
     "r3d_token_mask": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p]),
     "r3d_token_exchange_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p]),

@@ -14,7 +14,7 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SOURCES = ["fusion_kernels.cu", "erank_kernels.cu", "gram_tcgen05.cu", "jacobi_tc.cu", "jacobi_sym.cu", "pgemm_tcgen05.cu", "block_kernels.cu", "token_kernels.cu", "linear_tcgen05.cu"]
+SOURCES = ["fusion_kernels.cu", "erank_kernels.cu", "gram_tcgen05.cu", "jacobi_tc.cu", "jacobi_sym.cu", "pgemm_tcgen05.cu", "block_kernels.cu", "token_kernels.cu", "linear_tcgen05.cu", "multi_kernels.cu"]
 HEADERS = ["common.cuh", os.path.join("..", "..", "include", "r3d_b200.h")]
 LIB = os.path.join(HERE, "libr3d_b200.so")
 

@@ -601,11 +601,12 @@ __global__ void __launch_bounds__(kLinThreads, 1) lin_kernel(const __grid_consta
 // D[m, n] (+)= sum over splits (in order) of partial[s][m, n]; output fp32 or bf16
 __global__ void __launch_bounds__(256) lin_splitk_reduce_kernel(const float* __restrict__ partial, int splits, int64_t MN,
                                                                 int64_t N, void* __restrict__ D, int64_t ldd, int out_f32,
-                                                                int accumulate) {
+                                                                int accumulate, const void* __restrict__ bias) {
   for (int64_t e = int64_t(blockIdx.x) * 256 + threadIdx.x; e < MN; e += int64_t(gridDim.x) * 256) {
     float s = 0.f;
     for (int k = 0; k < splits; ++k) s += partial[int64_t(k) * MN + e];
     const int64_t m = e / N, n = e - m * N;
+    if (bias) s += out_f32 ? ((const float*)bias)[n] : __bfloat162float(((const __nv_bfloat16*)bias)[n]);
     if (out_f32) {
       float* p = (float*)D + m * ldd + n;
       *p = accumulate ? *p + s : s;
@@ -814,12 +815,17 @@ extern "C" int r3d_gemm(const void* A, const void* Bm, void* D, int64_t M, int64
   }
   int TN, splits, kb_per;
   lin_plan(M, N, K, planes, TN, splits, kb_per);
+  // split-K outputs go through the fp32 partial buffer and a reduce kernel that knows only the bias; any other
+  // epilogue member keeps the GEMM in one piece
+  const bool epi_beyond_bias = epi != nullptr && (epi->residual || epi->aux_out || epi->aux_in || epi->colsum_partial ||
+                                                  epi->act != 0);
+  if (epi_beyond_bias && splits > 1) { splits = 1; kb_per = (int)((K + LBK - 1) / LBK); }
   g.splits = splits; g.kb_per_split = kb_per;
+  const void* reduce_bias = nullptr;
   if (splits > 1) {
     R3D_CHECK(workspace != nullptr, "split-K GEMMs need the workspace");
-    R3D_CHECK(epi == nullptr || (!epi->bias && !epi->residual && !epi->aux_out && !epi->aux_in && !epi->colsum_partial &&
-                                 epi->act == 0), "split-K GEMMs (weight gradients) take no epilogue");
     g.partial = (float*)ws;
+    if (epi != nullptr) reduce_bias = epi->bias;
   }
   g.stage_bytes = planes * LM * 128 + planes * TN * 128;
   g.stages = std::max(2, std::min(4, (197 * 1024) / g.stage_bytes));
@@ -856,7 +862,7 @@ extern "C" int r3d_gemm(const void* A, const void* Bm, void* D, int64_t M, int64
     if (splits > 1) {
       const int64_t MN = M * N;
       const int rg = (int)std::min<int64_t>((MN + 255) / 256, int64_t(kNumSMs) * 8);
-      lin_splitk_reduce_kernel<<<rg, 256, 0, st>>>(g.partial, splits, MN, N, D, N, g.out_f32, 0);
+      lin_splitk_reduce_kernel<<<rg, 256, 0, st>>>(g.partial, splits, MN, N, D, N, g.out_f32, 0, reduce_bias);
       R3D_LAUNCH_CHECK();
     }
   }

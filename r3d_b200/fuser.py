@@ -81,6 +81,14 @@ class Block(nn.Module):
     def forward(self, x: torch.Tensor, attn_mask=None):
         C = self.dim
         fc1, fc2 = self.mlp.mlp[0], self.mlp.mlp[2]
+        if x.shape[1] != 2:
+            # M >= 3 modality tokens: a real masked softmax over the other M - 1 tokens (csrc/multi_kernels.cu)
+            hd = C // self.attn.num_heads
+            if not (x.is_cuda and x.shape[1] <= 4 and C % self.attn.num_heads == 0 and hd % 32 == 0 and hd <= 256
+                    and C % 8 == 0 and ops.layer_norm_supported(x, C)):
+                raise R3DError("the M-modality Block needs CUDA tensors, 3 <= M <= 4, head_dim a multiple of 32 (<= 256)")
+            return ops.fused_block_multi(x, self.norm1, self.attn.qkv, self.attn.proj, self.norm2, fc1, fc2,
+                                         self.attn.num_heads), None
         if ops.fused_block_supported(x, C, fc1.out_features) and self.norm1.elementwise_affine \
                 and self.norm2.elementwise_affine and fc1.bias is not None and fc2.bias is not None \
                 and self.attn.proj.bias is not None:
@@ -244,7 +252,43 @@ class CMFuser(nn.Module):
         return ops.token_fusion_bn(rgb, depth, self.alpha, bn_r.weight, bn_r.bias, bn_d.weight, bn_d.bias, mean, var,
                                    idx_r, idx_d, bn_r.eps, use_batch)
 
+    def _forward_multi(self, modal_feats: Dict[str, torch.Tensor]):
+        """M >= 3 modalities (BASELINE.json configs[4]: rgb + depth + gaze): modality m swaps its k lowest-score
+        channels for those of modality (m + 1) mod M, the Block attends over the M tokens (M x M -inf-diagonal mask),
+        then LayerNorm and the mean over the M tokens.  The reference hard-codes M = 2 (tokenfusion.py:77,79); this is
+        its extension, parity unpinned (oracle/torch_port.py:PortCMFuserM)."""
+        if self.variant != "tokenfusion" or self.select_axis != "channel":
+            raise R3DError("more than two modalities are defined for the channel-exchange 'tokenfusion' variant only")
+        feats = list(modal_feats.values())
+        B, T, C = feats[0].shape
+        M = len(feats)
+        k = self.k_for(C)
+        sums = []
+        for i in range(0, M, 2):                                   # the score kernel takes two tensors per launch
+            a, b = feats[i].detach(), feats[min(i + 1, M - 1)].detach()
+            s2 = ops.channel_score_sums(a, b)
+            sums.append(s2 if i + 1 < M else s2[:1])
+        packed = torch.cat([torch.cat(sums).reshape(-1), feats[0].new_zeros(1, dtype=torch.float32),
+                            torch.full((1,), float(B * T), dtype=torch.float32, device=feats[0].device)])
+        import torch.distributed as dist
+        if self.score_scope == "global" and dist.is_available() and dist.is_initialized() \
+                and dist.get_world_size(self.process_group) > 1:
+            dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=self.process_group)
+        score = packed[:M * C].reshape(M, C) / packed[M * C + 1]
+        idx = ops.bottomk(score, k)                                 # (M, k), ties -> lower index
+        self.last_indices = tuple(idx[m] for m in range(M))
+        x = ops.exchange_multi(feats, idx)                          # (B, T, M, C)
+        x = self.embd_drop(x.view(B * T, M, C))
+        x_res = x
+        for blk in self.blocks:
+            x, _ = blk(x)
+        x = x + x_res                                               # tokenfusion.py:92
+        y = ops.token_mean(_ln(self.norm, x).contiguous())          # norm, then the mean over the M tokens (:93-95)
+        return y.view(B, T, C)
+
     def forward(self, modal_feats: Dict[str, torch.Tensor], mode: Optional[str] = None, score_parts=None):
+        if len(modal_feats) > 2:
+            return self._forward_multi(modal_feats)
         rgb, depth = modal_feats["rgb"], modal_feats["depth"]
         B, T, C = rgb.shape
         M = len(modal_feats)

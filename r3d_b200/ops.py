@@ -696,6 +696,182 @@ def fused_block(x, norm1, qkv, proj, norm2, fc1, fc2):
 
 
 # ---------------------------------------------------------------------------------
+# N2: M-modality fuser pieces (csrc/multi_kernels.cu): cyclic channel exchange, M-token masked attention, token mean
+# ---------------------------------------------------------------------------------
+class _ExchangeMulti(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, idx, *feats):
+        M = len(feats)
+        B, T, C = feats[0].shape
+        out = torch.empty(B, T, M, C, dtype=feats[0].dtype, device=feats[0].device)
+        L = _lib.lib()
+        es = out.element_size()
+        if B * T:
+            with _on(out.device):
+                for m in range(M):
+                    check(L.r3d_exchange_one_fwd(_p(feats[m]), _p(feats[(m + 1) % M]), _p(idx[m]), idx.shape[1],
+                                                 out.data_ptr() + m * C * es, M * C, B * T, C, _dt(out), _stream()))
+        ctx.save_for_backward(idx)
+        ctx.M = M
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (idx,) = ctx.saved_tensors
+        M = ctx.M
+        g = g.contiguous()
+        B, T, _, C = g.shape
+        L = _lib.lib()
+        es = g.element_size()
+        outs = []
+        with _on(g.device):
+            for j in range(M):
+                dx = torch.empty(B, T, C, dtype=g.dtype, device=g.device)
+                if B * T:
+                    p = (j - 1) % M
+                    check(L.r3d_exchange_one_bwd(g.data_ptr() + j * C * es, g.data_ptr() + p * C * es, M * C, _p(idx[j]),
+                                                 _p(idx[p]), idx.shape[1], _p(dx), B * T, C, _dt(g), _stream()))
+                outs.append(dx)
+        return (None, *outs)
+
+
+def exchange_multi(feats, idx: torch.Tensor) -> torch.Tensor:
+    """M tensors (B,T,C) + idx (M, k) int64 -> stacked (B,T,M,C): stream m takes the channels idx[m] from modality
+    (m + 1) mod M.  For M = 2 this is ops.exchange with BLEND_SWAP."""
+    feats = [f.contiguous() for f in feats]
+    _need_cuda(*feats, idx)
+    for f in feats[1:]:
+        if f.shape != feats[0].shape or f.dtype != feats[0].dtype:
+            raise R3DError("all modalities must agree in shape and dtype")
+    C = feats[0].shape[-1]
+    if C % (4 if feats[0].dtype == torch.float32 else 8):
+        raise R3DError("exchange_multi needs C to be a multiple of the 128-bit vector width")
+    return _ExchangeMulti.apply(idx.to(torch.int64).contiguous(), *feats)
+
+
+class _MTokenAttn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, qkv, M, heads):
+        rows = qkv.shape[0]
+        C = qkv.shape[-1] // 3
+        qkv = qkv.contiguous()
+        out = torch.empty(rows, M, C, dtype=qkv.dtype, device=qkv.device)
+        with _on(qkv.device):
+            check(_lib.lib().r3d_mtoken_attn_fwd(_p(qkv), _p(out), rows, M, C, heads, _dt(qkv), _stream()))
+        ctx.save_for_backward(qkv)
+        ctx.meta = (M, heads)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (qkv,) = ctx.saved_tensors
+        M, heads = ctx.meta
+        rows, C = qkv.shape[0], qkv.shape[-1] // 3
+        dqkv = torch.empty_like(qkv)
+        with _on(qkv.device):
+            check(_lib.lib().r3d_mtoken_attn_bwd(_p(qkv), _p(g.contiguous()), _p(dqkv), rows, M, C, heads, _dt(qkv),
+                                                 _stream()))
+        return dqkv, None, None
+
+
+def mtoken_attention(qkv: torch.Tensor, heads: int) -> torch.Tensor:
+    """qkv (R, M, 3C) -> (R, M, C): per head, token m attends to the OTHER M - 1 tokens (diagonal masked with -inf,
+    tokenfusion.py:68-72), scale head_dim^-0.5 (transformerblock.py:11,27)."""
+    _need_cuda(qkv)
+    _dt(qkv)
+    return _MTokenAttn.apply(qkv, qkv.shape[1], int(heads))
+
+
+class _TokenMean(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        R, M, C = x.shape
+        x = x.contiguous()
+        out = torch.empty(R, C, dtype=x.dtype, device=x.device)
+        with _on(x.device):
+            check(_lib.lib().r3d_token_mean(_p(x), _p(out), R, M, C, _dt(x), 0, _stream()))
+        ctx.M = M
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous()
+        R, C = g.shape
+        dx = torch.empty(R, ctx.M, C, dtype=g.dtype, device=g.device)
+        with _on(g.device):
+            check(_lib.lib().r3d_token_mean(_p(g), _p(dx), R, ctx.M, C, _dt(g), 1, _stream()))
+        return dx
+
+
+def token_mean(x: torch.Tensor) -> torch.Tensor:
+    """(R, M, C) -> (R, C): mean over the modality tokens (tokenfusion.py:95)."""
+    _need_cuda(x)
+    _dt(x)
+    return _TokenMean.apply(x)
+
+
+class _FusedBlockM(torch.autograd.Function):
+    """The Block for M >= 3 modality tokens (a real (M-1)-way softmax per head): LN -> qkv GEMM -> M-token attention ->
+    proj GEMM (+bias +residual) -> LN -> fc1 GEMM (GELU) -> fc2 GEMM (+bias +residual); hand-written kernels only."""
+
+    @staticmethod
+    def forward(ctx, x, n1w, n1b, qkv_w, qkv_b, wp, bp, n2w, n2b, w1, b1, w2, b2, eps1, eps2, heads):
+        dt = x.dtype
+        R, M, C = x.shape
+        xc = x.contiguous().view(R * M, C)
+        cast = lambda t: None if t is None else t.detach().to(dt).contiguous()
+        n1w_, n1b_, n2w_, n2b_ = cast(n1w), cast(n1b), cast(n2w), cast(n2b)
+        wq, bq, wp_, bp_, w1_, b1_, w2_, b2_ = cast(qkv_w), cast(qkv_b), cast(wp), cast(bp), cast(w1), cast(b1), cast(w2), cast(b2)
+        L = _lib.lib()
+        with _on(x.device):
+            h1, m1, r1 = _ln_fwd_raw(xc, n1w_, n1b_, eps1, 0)
+            qkv = gemm(h1, wq, bias=bq)                                   # (R*M, 3C)
+            att = torch.empty(R * M, C, dtype=dt, device=x.device)
+            check(L.r3d_mtoken_attn_fwd(_p(qkv), _p(att), R, M, C, heads, _dt(xc), _stream()))
+            x1 = gemm(att, wp_, bias=bp_, residual=xc)
+            h2, m2, r2 = _ln_fwd_raw(x1, n2w_, n2b_, eps2, 0)
+            g1, H = gemm(h2, w1_, bias=b1_, act=ACT_GELU, want_aux=True)
+            x2 = gemm(g1, w2_, bias=b2_, residual=x1)
+        ctx.save_for_backward(xc, m1, r1, h1, qkv, att, x1, m2, r2, h2, H, g1, n1w_, wq, wp_, n2w_, w1_, w2_)
+        ctx.meta = (x.shape, heads, qkv_b is not None,
+                    [None if t is None else t.dtype for t in (n1w, n1b, qkv_w, qkv_b, wp, bp, n2w, n2b, w1, b1, w2, b2)])
+        return x2.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, dx2):
+        xc, m1, r1, h1, qkv, att, x1, m2, r2, h2, H, g1, n1w, wq, wp, n2w, w1, w2 = ctx.saved_tensors
+        xshape, heads, has_qkv_b, pdt = ctx.meta
+        R, M, C = xshape
+        dx2 = dx2.contiguous().view(-1, C)
+        L = _lib.lib()
+        with _on(dx2.device):
+            db2 = colsum(dx2)
+            dH, db1 = gemm(dx2, w2, True, False, aux_in=H, colsum=True)
+            dW2 = gemm(dx2, g1, False, False)
+            dh2 = gemm(dH, w1, True, False)
+            dW1 = gemm(dH, h2, False, False)
+            dx1, dg2, dbt2 = _ln_bwd_raw(dh2, x1, m2, r2, n2w, 0, dx2)
+            dbp = colsum(dx1)
+            datt = gemm(dx1, wp, True, False)
+            dWp = gemm(dx1, att, False, False)
+            dqkv = torch.empty_like(qkv)
+            check(L.r3d_mtoken_attn_bwd(_p(qkv), _p(datt), _p(dqkv), R, M, C, heads, _dt(qkv), _stream()))
+            dh1 = gemm(dqkv, wq, True, False)
+            dWq = gemm(dqkv, h1, False, False)
+            dbq = colsum(dqkv) if has_qkv_b else None
+            dx, dg1, dbt1 = _ln_bwd_raw(dh1, xc, m1, r1, n1w, 0, dx1)
+        g = [dg1, dbt1, dWq, dbq, dWp, dbp, dg2, dbt2, dW1, db1, dW2, db2]
+        g = [None if (t is None or d is None) else t.to(d) for t, d in zip(g, pdt)]
+        return (dx.view(xshape), *g, None, None, None)
+
+
+def fused_block_multi(x, norm1, qkv, proj, norm2, fc1, fc2, heads):
+    """x (R, M, C), M >= 3 -> (R, M, C), see _FusedBlockM."""
+    return _FusedBlockM.apply(x, norm1.weight, norm1.bias, qkv.weight, qkv.bias, proj.weight, proj.bias, norm2.weight,
+                              norm2.bias, fc1.weight, fc1.bias, fc2.weight, fc2.bias, norm1.eps, norm2.eps, int(heads))
+
+
+# ---------------------------------------------------------------------------------
 # N1: token-axis selection (north_star kernels 3-6; no reference symbol -- the reference ships the channel exchange
 # only, SURVEY.md F2; oracle: oracle/fuser_oracle.py:token_fusion_tokens, parity unpinned)
 # ---------------------------------------------------------------------------------
@@ -818,6 +994,77 @@ def _register():
     @_er.register_fake
     def _(x, rtol):
         return x.new_empty((x.shape[0],), dtype=torch.float32)
+
+    # ---- the remaining schemas of SURVEY.md 8(b): exchange_bwd, erank_fwd (tuple), erank_bwd, with autograd wired
+    # through torch.library (register_autograd), so the ops are differentiable when called as torch.ops.r3d.*
+    @custom_op("r3d::exchange_bwd", mutates_args=(), device_types="cuda")
+    def _eb(g: torch.Tensor, rgb: torch.Tensor, depth: torch.Tensor, idx_r: torch.Tensor, idx_d: torch.Tensor,
+            alpha: Optional[torch.Tensor], blend_mode: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        a = None if alpha is None else alpha.reshape(-1).float().contiguous()
+        swap = blend_mode == BLEND_SWAP
+        d_r, d_d, cs = _exchange_bwd_raw(g.contiguous(), None if swap else rgb.contiguous(),
+                                         None if swap else depth.contiguous(), idx_r.contiguous(), idx_d.contiguous(), a,
+                                         None, None, blend_mode)
+        d_alpha = torch.zeros(rgb.shape[-1], dtype=torch.float32, device=g.device) if cs is None else cs[0].clone()
+        return d_r, d_d, d_alpha
+
+    @_eb.register_fake
+    def _(g, rgb, depth, idx_r, idx_d, alpha, blend_mode):
+        B, T, _, C = g.shape
+        return g.new_empty((B, T, C)), g.new_empty((B, T, C)), g.new_empty((C,), dtype=torch.float32)
+
+    def _ef_setup(ctx, inputs, output):
+        rgb, depth, idx_r, idx_d, alpha, blend_mode = inputs
+        ctx.save_for_backward(rgb, depth, idx_r, idx_d, alpha if alpha is not None else rgb.new_empty(0))
+        ctx.has_alpha, ctx.blend = alpha is not None, blend_mode
+
+    def _ef_backward(ctx, g):
+        rgb, depth, idx_r, idx_d, alpha = ctx.saved_tensors
+        d_r, d_d, d_a = torch.ops.r3d.exchange_bwd(g, rgb, depth, idx_r, idx_d, alpha if ctx.has_alpha else None, ctx.blend)
+        return d_r, d_d, None, None, (d_a.reshape(alpha.shape).to(alpha.dtype) if ctx.has_alpha else None), None
+
+    _ef.register_autograd(_ef_backward, setup_context=_ef_setup)
+
+    @custom_op("r3d::erank_fwd", mutates_args=(), device_types="cuda")
+    def _erf(x: torch.Tensor, rtol: float) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+        er, sigma, U, Y, _ = _erank_fwd_raw(x.contiguous(), rtol, GRAM_TCGEN05)
+        return er, sigma, U, Y
+
+    @_erf.register_fake
+    def _(x, rtol):
+        B, T, C = x.shape
+        n, m = min(T, C), max(T, C)
+        f = dict(dtype=torch.float32)
+        return x.new_empty((B,), **f), x.new_empty((B, n), **f), x.new_empty((B, n, n), **f), x.new_empty((B, n, m), **f)
+
+    @custom_op("r3d::erank_bwd", mutates_args=(), device_types="cuda")
+    def _erb(g: torch.Tensor, x: torch.Tensor, sigma: torch.Tensor, U: torch.Tensor, Y: torch.Tensor, erank: torch.Tensor,
+             rtol: float) -> torch.Tensor:
+        B, T, C = x.shape
+        L = _lib.lib()
+        dt = _dt(x)
+        with _on(x.device):
+            ws = torch.empty(L.r3d_erank_workspace_bytes(B, T, C, dt), dtype=torch.uint8, device=x.device)
+            dx = torch.empty_like(x)
+            check(L.r3d_erank_bwd(_p(g.contiguous().float()), _p(erank), _p(sigma), _p(U), _p(Y), B, T, C, dt, rtol, _p(ws),
+                                  _p(dx), 0, _stream()))
+        return dx
+
+    @_erb.register_fake
+    def _(g, x, sigma, U, Y, erank, rtol):
+        return torch.empty_like(x)
+
+    def _erf_setup(ctx, inputs, output):
+        x, rtol = inputs
+        er, sigma, U, Y = output
+        ctx.save_for_backward(x, sigma, U, Y, er)
+        ctx.rtol = rtol
+
+    def _erf_backward(ctx, g_er, g_sigma, g_U, g_Y):
+        x, sigma, U, Y, er = ctx.saved_tensors
+        return torch.ops.r3d.erank_bwd(g_er, x, sigma, U, Y, er, ctx.rtol), None
+
+    _erf.register_autograd(_erf_backward, setup_context=_erf_setup)
 
 
 _register()

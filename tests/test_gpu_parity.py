@@ -1053,12 +1053,20 @@ def test_rgb_and_depth_embed_vs_torch(dt, dev):
     tol = dict(rtol=3e-2, atol=3e-2) if dt == torch.bfloat16 else dict(rtol=1e-4, atol=1e-4)
     torch.testing.assert_close(y_r.double().cpu(), yr.detach(), **tol)
     torch.testing.assert_close(y_d.double().cpu(), yd.detach(), **tol)
-    torch.testing.assert_close(f.grad.double().cpu(), f64.grad, **tol)
-    torch.testing.assert_close(d.grad.double().cpu().view(B, S, -1), d64.grad.view(B, S, -1), **tol)
-    gtol = dict(rtol=5e-2, atol=0.25) if dt == torch.bfloat16 else dict(rtol=1e-4, atol=1e-3)
+    if dt == torch.bfloat16:
+        # a pre-activation that rounds across zero in bf16 flips its ReLU mask relative to the float64 reference: a few
+        # rows differ by O(1) terms, so the input gradients are compared norm-wise
+        for got, ref in ((f.grad.double().cpu(), f64.grad), (d.grad.double().cpu().view(B, S, -1), d64.grad.view(B, S, -1))):
+            assert (got - ref).norm() <= 5e-2 * ref.norm()
+    else:
+        torch.testing.assert_close(f.grad.double().cpu(), f64.grad, **tol)
+        torch.testing.assert_close(d.grad.double().cpu().view(B, S, -1), d64.grad.view(B, S, -1), **tol)
     for ours, ref in ((rgbm.input_embed, ref_r), (depm.depth_projection, ref_d), (depm.depth_layernorm, ref_ln)):
         for (n, p), (_, q) in zip(ours.named_parameters(), ref.named_parameters()):
-            torch.testing.assert_close(p.grad.double().cpu(), q.grad, **gtol, msg=lambda m, n=n: f"{n}: {m}")
+            if dt == torch.bfloat16:
+                assert (p.grad.double().cpu() - q.grad).norm() <= 5e-2 * q.grad.norm() + 1e-2, n
+            else:
+                torch.testing.assert_close(p.grad.double().cpu(), q.grad, rtol=1e-4, atol=1e-3, msg=lambda m, n=n: f"{n}: {m}")
     # score by-products = column sums of |stored output|
     torch.testing.assert_close(rgbm.last_score.sums().double().cpu(), y_r.detach().double().abs().sum((0, 1)).cpu(),
                                rtol=1e-4, atol=1e-3)
@@ -1084,3 +1092,138 @@ def test_fuser_front_skips_score_pass(dev):
     torch.testing.assert_close(y, y2, rtol=1e-5, atol=1e-6)
     ref_idx = O.bottomk(O.channel_score(src.detach().cpu().numpy()), C // 4)
     np.testing.assert_array_equal(idx[0].cpu().numpy(), ref_idx)
+
+
+# ------------------------------------------------------------------ N2: M-modality fuser (rgb + depth + gaze)
+@pytest.mark.parametrize("M", [3, 4])
+def test_multi_modality_fuser_vs_oracle(M, dev):
+    """CMFuser with M >= 3 modal features (configs[4]) against oracle/torch_port.py:PortCMFuserM (the reference's
+    modules with the M x M -inf-diagonal mask; parity unpinned beyond M = 2): selected channels bit-exact, output and all
+    gradients within the fp32 bars."""
+    import r3d_b200
+    from oracle.torch_port import PortCMFuserM
+    B, T, C, H = 2, 24, 128, 4                      # head_dim 32
+    g = torch.Generator().manual_seed(40 + M)
+    c = torch.arange(C, dtype=torch.float32)
+    names = ["rgb", "depth", "gaze", "audio"][:M]
+    feats = {}
+    for i, n in enumerate(names):
+        perm = torch.randperm(C, generator=g)
+        feats[n] = (torch.relu(torch.randn(B, T, C, generator=g)) * (1 + (i + 1) * c / C))[:, :, perm].contiguous()
+    gy = torch.randn(B, T, C, generator=g)
+    torch.manual_seed(0)
+    ref = PortCMFuserM(C, depth=1, num_heads=H).train()
+    ref.embd_drop.p = 0.0
+    f = r3d_b200.CMFuser(C, depth=1, num_heads=H)
+    f.load_state_dict(ref.state_dict())
+    f = f.to(dev).train()
+    f.embd_drop.p = 0.0
+    ours_in = {n: v.to(dev).requires_grad_(True) for n, v in feats.items()}
+    ref_in = {n: v.clone().requires_grad_(True) for n, v in feats.items()}
+    y = f(ours_in, "test")
+    yr = ref(ref_in, "test")
+    for m in range(M):
+        np.testing.assert_array_equal(f.last_indices[m].cpu().numpy(), ref.last_indices[m].numpy())
+    np.testing.assert_allclose(y.detach().cpu().numpy(), yr.detach().numpy(), rtol=1e-4, atol=1e-5)
+    y.backward(gy.to(dev))
+    yr.backward(gy)
+    for n in names:
+        np.testing.assert_allclose(ours_in[n].grad.cpu().numpy(), ref_in[n].grad.numpy(), rtol=1e-3, atol=2e-5, err_msg=n)
+    for (n, p), (_, q) in zip(f.named_parameters(), ref.named_parameters()):
+        if q.grad is not None:
+            assert p.grad is not None, n
+            np.testing.assert_allclose(p.grad.cpu().numpy(), q.grad.numpy(), rtol=1e-3,
+                                       atol=1e-4 * max(1.0, q.grad.abs().max().item()), err_msg=n)
+
+
+def test_multi_modality_kernels_bf16_and_m2_equivalence(dev):
+    """exchange_multi with M = 2 equals the reference swap; the M-token attention in bf16 against torch's masked
+    softmax attention in float64; token_mean against torch."""
+    from r3d_b200 import ops
+    B, T, C, H, M = 2, 16, 256, 8, 3
+    rgb, dep = synth(B, T, C, 50)
+    idx = torch.stack([torch.randperm(C)[:C // 4], torch.randperm(C)[:C // 4]]).to(dev)
+    a = ops.exchange_multi([rgb.to(dev), dep.to(dev)], idx)
+    b = ops.exchange(rgb.to(dev), dep.to(dev), idx[0], idx[1])
+    assert torch.equal(a, b)
+    g = torch.Generator().manual_seed(3)
+    qkv = torch.randn(B * T, M, 3 * C, generator=g).to(torch.bfloat16)
+    q = qkv.to(dev).requires_grad_(True)
+    out = ops.mtoken_attention(q, H)
+    go = torch.randn(B * T, M, C, generator=g).to(torch.bfloat16)
+    out.backward(go.to(dev))
+    q64 = qkv.double().requires_grad_(True)
+    hd = C // H
+    t = q64.view(B * T, M, 3, H, hd).permute(2, 0, 3, 1, 4)
+    w = (t[0] @ t[1].transpose(-2, -1)) * hd ** -0.5 + torch.zeros(M, M).masked_fill(torch.eye(M) == 1, float("-inf"))
+    ref = (w.softmax(-1) @ t[2]).transpose(1, 2).reshape(B * T, M, C)
+    ref.backward(go.double())
+    torch.testing.assert_close(out.double().cpu(), ref.detach(), rtol=2e-2, atol=2e-2)
+    assert (q.grad.double().cpu() - q64.grad).norm() <= 2e-2 * q64.grad.norm()
+    x = torch.randn(40, M, C, generator=g).to(dev).requires_grad_(True)
+    m = ops.token_mean(x)
+    torch.testing.assert_close(m, x.mean(1))
+    m.sum().backward()
+    torch.testing.assert_close(x.grad, torch.full_like(x, 1.0 / M))
+
+
+# ------------------------------------------------------------------ f4: FUTR around the fuser path
+def test_futr_matches_reference_module(dev):
+    """r3d_b200.FUTR against the UNMODIFIED reference FUTR (oracle/_ref or /root/reference, run on the CPU) with the same
+    weights and inputs: identical state_dict names (strict load both ways), eval outputs within fp32 tolerance."""
+    import types
+    import r3d_b200
+    from oracle import ref_loader
+    RefFUTR = ref_loader.load_futr("tokenfusion")
+    if RefFUTR is None:
+        pytest.skip("no reference tree (oracle/_ref not staged)")
+    args = types.SimpleNamespace(input_dim=256, seg=True, anticipate=True, max_pos_len=64, input_type="i3d_transcript")
+    torch.manual_seed(0)
+    ref = RefFUTR(n_class=12, hidden_dim=64, src_pad_idx=13, device="cpu", args=args, n_query=8, n_head=4,
+                  num_encoder_layers=1, num_decoder_layers=2, query_num=20).eval()
+    ours = r3d_b200.FUTR(n_class=12, hidden_dim=64, src_pad_idx=13, device=dev, args=args, n_query=8, n_head=4,
+                         num_encoder_layers=1, num_decoder_layers=2, query_num=20)
+    assert set(ours.state_dict().keys()) == set(ref.state_dict().keys())
+    ours.load_state_dict(ref.state_dict(), strict=True)
+    ours = ours.to(dev).eval()
+    g = torch.Generator().manual_seed(2)
+    B, S = 2, 12
+    feats = torch.randn(B, S, 256, generator=g)
+    depth = torch.randn(B, S, 224, 224, generator=g) * 0.1
+    with torch.no_grad():
+        want = ref((feats, None), depth, mode="test")
+        got = ours((feats.to(dev), None), depth.to(dev), mode="test")
+    assert set(got) == set(want) == {"action", "duration", "seg"}
+    for k in want:
+        np.testing.assert_allclose(got[k].cpu().numpy(), want[k].numpy(), rtol=2e-3, atol=2e-4, err_msg=k)
+    # and it trains: gradients reach the input projections through the fuser
+    ours.train()
+    out = ours((feats.to(dev), torch.zeros(B, S, dtype=torch.long, device=dev)), depth.to(dev), mode="train")
+    (out["action"].sum() + out["duration"].sum() + out["seg"].sum()).backward()
+    assert ours.input_embed.weight.grad is not None and ours.depth_projection.weight.grad is not None
+    assert torch.isfinite(ours.depth_projection.weight.grad).all()
+
+
+def test_torch_ops_schemas_with_autograd(dev):
+    """torch.ops.r3d.* (SURVEY.md 8b): exchange_fwd / exchange_bwd / erank_fwd / erank_bwd are registered with autograd
+    and agree with the Python-level operators."""
+    from r3d_b200 import ops
+    B, T, C = 2, 16, 64
+    rgb, dep = synth(B, T, C, 12)
+    r = rgb.to(dev).requires_grad_(True)
+    d = dep.to(dev).requires_grad_(True)
+    idx = ops.bottomk(ops.channel_score(r.detach(), d.detach()), C // 4)
+    alpha = torch.rand(1, 1, C, device=dev, requires_grad=True)
+    out = torch.ops.r3d.exchange_fwd(r, d, idx[0], idx[1], alpha, ops.BLEND_SCALE)
+    g = torch.randn_like(out)
+    out.backward(g)
+    r2, d2, a2 = rgb.to(dev).requires_grad_(True), dep.to(dev).requires_grad_(True), alpha.detach().clone().requires_grad_(True)
+    ops.exchange(r2, d2, idx[0], idx[1], a2, ops.BLEND_SCALE).backward(g)
+    assert torch.equal(r.grad, r2.grad) and torch.equal(d.grad, d2.grad)
+    torch.testing.assert_close(alpha.grad, a2.grad)
+    x = torch.from_numpy(_spectra("relu", 2, 64, 128, 5)).to(dev).requires_grad_(True)
+    er, sigma, U, Y = torch.ops.r3d.erank_fwd(x, 1e-4)
+    er.sum().backward()
+    x2 = x.detach().clone().requires_grad_(True)
+    ops.erank(x2).sum().backward()
+    assert torch.equal(x.grad, x2.grad)

@@ -147,3 +147,22 @@ def test_train_branch_is_all_ties():
     C = 64
     s2 = np.arange(C, dtype=np.float32); s2[::3] = 0
     np.testing.assert_array_equal(O.bottomk(s2, C // 4), np.arange(0, C, 3)[: C // 4])
+
+
+def test_multi_modality_port_reduces_to_the_pinned_two_modality_port():
+    """oracle/torch_port.py:PortCMFuserM (the unpinned M-modality extension) must equal the golden-pinned
+    PortCMFuser('tokenfusion') for M = 2, forward and gradients."""
+    from oracle.torch_port import PortCMFuserM
+    torch.manual_seed(0)
+    a = PortCMFuser(32, 1, 4, variant="tokenfusion").eval()
+    b = PortCMFuserM(32, 1, 4).eval()
+    b.load_state_dict(a.state_dict())
+    g = torch.Generator().manual_seed(1)
+    r = torch.relu(torch.randn(2, 5, 32, generator=g)).requires_grad_(True)
+    d = torch.relu(torch.randn(2, 5, 32, generator=g)).requires_grad_(True)
+    ya = a({"rgb": r, "depth": d}, "test")
+    ya.sum().backward()
+    gr = r.grad.clone(); r.grad = None; d.grad = None
+    yb = b({"rgb": r, "depth": d}, "test")
+    yb.sum().backward()
+    assert torch.allclose(ya, yb, atol=1e-6) and torch.allclose(gr, r.grad, atol=1e-6)
