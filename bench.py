@@ -53,6 +53,9 @@ def parse():
     ap.add_argument("--opt", action="append", default=[], help="library tuning knob key=value (r3d_set_option)")
     ap.add_argument("--global-batch", type=int, default=0, help="strong scaling: total clips per step, split over the ranks")
     ap.add_argument("--no-yardstick", action="store_true", help="skip the same-GPU library eigensolver yardstick")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="timed steps only: no isolated stages, full-fuser comparison, yardsticks, C-ABI or CPU legs "
+                         "(for ncu launch lists)")
     return ap.parse_args()
 
 
@@ -437,6 +440,31 @@ def full_fuser_numbers(dev, dtype, steps=10):
     return out
 
 
+def c_abi_e2e(host_in, Bl, dtype, steps):
+    """The hot path the reference-facing C entry covers -- erank of both modalities, score -> bottom-k -> exchange,
+    exchange backward + erank gradient; NOT the Block, which lives in the nn.Module -- through ONE C-ABI call per step
+    with HOST buffers (r3d_fuser_step_host: H2D, kernels, D2H, stream sync inside the call), pinned memory."""
+    import torch
+    from r3d_b200 import ops
+    gst = torch.randn(Bl, T, 2, C, generator=torch.Generator().manual_seed(7)).to(dtype).pin_memory()
+    out = (torch.empty(Bl, T, 2, C, dtype=dtype).pin_memory(), torch.empty(2 * Bl, dtype=torch.float32).pin_memory(),
+           torch.empty(Bl, T, C, dtype=dtype).pin_memory(), torch.empty(Bl, T, C, dtype=dtype).pin_memory(),
+           torch.empty(2, C // 4, dtype=torch.int64).pin_memory())
+    for i in range(2):
+        ops.fuser_step_host(host_in[i % NSETS][0], host_in[i % NSETS][1], gst, out=out)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(steps):
+        ops.fuser_step_host(host_in[i % NSETS][0], host_in[i % NSETS][1], gst, out=out)
+    dt_s = time.perf_counter() - t0                       # the call synchronises its stream: wall clock is device-complete
+    es = 2
+    return {"value": Bl * steps / dt_s, "unit": UNIT, "ms_per_step": dt_s / steps * 1e3,
+            "h2d_bytes_per_step": int(4 * Bl * T * C * es), "d2h_bytes_per_step": int(4 * Bl * T * C * es + 2 * Bl * 4),
+            "entry": "r3d_fuser_step_host (include/r3d_b200.h)",
+            "note": "token-fuse + effective-rank fwd/bwd only (the Block is nn.Module-side); copies not overlapped with "
+                    "compute -- one synchronous call per step"}
+
+
 def library_yardstick(buf, dev):
     """The same eigen / singular-value problem on the same GPU through the libraries (cuSOLVER behind torch.linalg):
     the 2B = 128 samples of 512 x 512 of one step.  Forward only (no gradient), one warm-up + one timed call each --
@@ -600,7 +628,7 @@ def main_ours(args):
         return
     stages, pk = stage_table(prof, args.steps, world, tiles, Bl)
     isolated = None
-    if world == 1 and not args.global_batch:
+    if world == 1 and not args.global_batch and not args.no_extras:
         gst = [torch.randn(Bl, T, 2, C, generator=gg, device=dev).to(dtype) for _ in range(NSETS)]
         isolated = isolated_stage_numbers(dev_in, gst, pk)
         del gst
@@ -644,13 +672,15 @@ def main_ours(args):
     }
     if ar:
         line["grad_allreduce"] = ar
+    if world == 1 and not args.global_batch and not args.no_extras:
+        line["e2e_c_abi"] = c_abi_e2e(host_in, Bl, dtype, args.steps)
     if isolated:
         line["stages_isolated"] = isolated
-    if world == 1 and not args.global_batch:
+    if world == 1 and not args.global_batch and not args.no_extras:
         line["full_fuser_fwd_bwd"] = full_fuser_numbers(dev, dtype)
         if not args.no_yardstick:
             line["gpu_library_yardstick"] = library_yardstick(dev_in[0], dev)
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and not args.no_extras:
         val, cms, kind = run_cpu(4, 1, args.cpu_sample)
         line["config"]["cpu_clips_per_step"] = args.cpu_sample
         line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,

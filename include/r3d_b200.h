@@ -329,6 +329,16 @@ int r3d_swap_add(const void* a, const void* b, int64_t rows, int64_t C, int dtyp
 int r3d_token_fusion_host(const void* rgb_host, const void* depth_host, int64_t B, int64_t T, int64_t C,
                           int dtype, int64_t k, void* out_host, int64_t* idx_r_host, int64_t* idx_d_host,
                           void* stream);
+/* The whole hot path from HOST buffers (what a non-Python caller binds; `e2e_c_abi` in bench.py):
+ *   H2D -> erank(rgb), erank(depth) -> channel score -> bottom-k -> exchange/stack -> [exchange backward of the
+ *   upstream gradient gst + d(erank_weight * mean erank)/dX accumulated] -> D2H.
+ * rgb_host, depth_host (B, T, C); gst_host (B, T, 2, C) or NULL (forward only; then d_*_host must be NULL too).
+ * Outputs: stacked_out_host (B, T, 2, C); erank_out_host (2B) float (rgb samples, then depth); d_rgb_host, d_depth_host
+ * (B, T, C); idx_host (2, k) int64 or NULL.  One stream-ordered device arena per call; returns after the stream has
+ * been synchronised. */
+int r3d_fuser_step_host(const void* rgb_host, const void* depth_host, const void* gst_host, int64_t B, int64_t T,
+                        int64_t C, int dtype, int64_t k, float rtol, float erank_weight, void* stacked_out_host,
+                        float* erank_out_host, void* d_rgb_host, void* d_depth_host, int64_t* idx_host, void* stream);
 
 #ifdef __cplusplus
 }

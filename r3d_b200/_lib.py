@@ -89,6 +89,8 @@ SIGNATURES = {
     "r3d_ln_relu_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int,
                                 c_void_p, c_void_p, c_void_p, c_void_p]),
     "r3d_swap_add": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p]),
+    "r3d_fuser_step_host": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_int64, c_float, c_float,
+                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "r3d_token_fusion_host": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_int64, c_void_p,
                                       c_void_p, c_void_p, c_void_p]),
 }

@@ -1789,3 +1789,82 @@ extern "C" int r3d_token_informativeness(const float* sigma, const float* U, int
   R3D_LAUNCH_CHECK();
   return 0;
 }
+
+
+// ================================================================================
+// The whole hot path from HOST buffers through the C ABI (what a non-Python caller binds; bench.py's `e2e_c_abi`):
+//   H2D inputs (+ upstream gradient) -> erank(rgb), erank(depth) -> channel score -> bottom-k -> exchange/stack
+//   -> exchange backward of the upstream gradient + d(mean erank)/dX accumulated -> D2H of every result.
+// One device arena per call (cudaMallocAsync, stream-ordered); synchronises the stream before returning.
+// ================================================================================
+extern "C" int r3d_fuser_step_host(const void* rgb_host, const void* depth_host, const void* gst_host, int64_t B,
+                                   int64_t T, int64_t C, int dtype, int64_t k, float rtol, float erank_weight,
+                                   void* stacked_out_host, float* erank_out_host, void* d_rgb_host, void* d_depth_host,
+                                   int64_t* idx_host, void* stream) {
+  R3D_CHECK(rgb_host && depth_host && stacked_out_host && erank_out_host, "null host pointer");
+  R3D_CHECK(dtype == R3D_F32 || dtype == R3D_BF16, "bad dtype %d", dtype);
+  R3D_CHECK(B >= 1 && T >= 1 && C >= 1 && C <= 8192 && k >= 0 && k <= C, "bad shape");
+  R3D_CHECK((gst_host == nullptr) == (d_rgb_host == nullptr) && (gst_host == nullptr) == (d_depth_host == nullptr),
+            "the backward needs gst_host, d_rgb_host and d_depth_host together");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t rows = B * T;
+  int64_t n, m; bool ts; side(T, C, n, m, ts);
+  const size_t es = dtype == R3D_F32 ? 4 : 2;
+  const size_t nb = size_t(rows) * C * es;                       // one modality
+  auto al = [](size_t v) { return (v + 255) & ~size_t(255); };
+  size_t off = 0;
+  auto take = [&](size_t bytes) { const size_t o = off; off += al(bytes); return o; };
+  const size_t o_in = take(2 * nb), o_out = take(2 * nb), o_g = take(gst_host ? 2 * nb : 0), o_dg = take(gst_host ? 2 * nb : 0);
+  const size_t o_ws = take(r3d_erank_workspace_bytes(2 * B, T, C, dtype));
+  const size_t o_er = take(size_t(2 * B) * 4), o_sig = take(size_t(2 * B) * n * 4), o_U = take(size_t(2 * B) * n * n * 4);
+  const size_t o_Y = take(size_t(2 * B) * n * m * 4), o_sw = take(size_t(2 * B) * 4), o_gv = take(size_t(2 * B) * 4);
+  const size_t o_sws = take(r3d_score_workspace_floats(rows, C) * 4), o_pk = take(size_t(2 * C + 2) * 4);
+  const size_t o_idx = take(size_t(2) * (k > 0 ? k : 1) * 8);
+  char* buf = nullptr;
+  R3D_CUDA(cudaMallocAsync((void**)&buf, off + 256, st));
+  int rc = 0;
+  do {
+    if (cudaMemcpyAsync(buf + o_in, rgb_host, nb, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+        cudaMemcpyAsync(buf + o_in + nb, depth_host, nb, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+        (gst_host && cudaMemcpyAsync(buf + o_g, gst_host, 2 * nb, cudaMemcpyHostToDevice, st) != cudaSuccess)) {
+      set_error("H2D copy failed"); rc = 2; break;
+    }
+    float* er = (float*)(buf + o_er);
+    int64_t* idx = (int64_t*)(buf + o_idx);
+    float* packed = (float*)(buf + o_pk);
+    if ((rc = r3d_erank_fwd(buf + o_in, 2 * B, T, C, dtype, rtol, 0, buf + o_ws, er, (float*)(buf + o_sig),
+                            (float*)(buf + o_U), (float*)(buf + o_Y), (int32_t*)(buf + o_sw), st))) break;
+    if ((rc = r3d_channel_score_partial(buf + o_in, buf + o_in + nb, rows, C, dtype, (float*)(buf + o_sws), st))) break;
+    if ((rc = r3d_score_finalize_packed((float*)(buf + o_sws), rows, C, er, 2 * B, packed, st))) break;
+    if ((rc = r3d_bottomk_scaled(packed, 2, C, k, packed + 2 * C + 1, idx, nullptr, st))) break;
+    if ((rc = r3d_exchange_fwd(buf + o_in, buf + o_in + nb, idx, idx + k, k, nullptr, nullptr, R3D_BLEND_SWAP, buf + o_out,
+                               rows, C, dtype, st))) break;
+    if (gst_host) {
+      std::vector<float> gv(size_t(2 * B), erank_weight / float(2 * B));
+      if (cudaMemcpyAsync(buf + o_gv, gv.data(), gv.size() * 4, cudaMemcpyHostToDevice, st) != cudaSuccess) {
+        set_error("H2D copy failed"); rc = 2; break;
+      }
+      if (cudaStreamSynchronize(st) != cudaSuccess) { set_error("stream sync failed"); rc = 2; break; }   // gv is a stack vector
+      if ((rc = r3d_exchange_bwd(buf + o_g, nullptr, nullptr, idx, idx + k, k, nullptr, nullptr, nullptr, R3D_BLEND_SWAP,
+                                 buf + o_dg, buf + o_dg + nb, nullptr, rows, C, dtype, st))) break;
+      if ((rc = r3d_erank_bwd((float*)(buf + o_gv), er, (float*)(buf + o_sig), (float*)(buf + o_U), (float*)(buf + o_Y),
+                              2 * B, T, C, dtype, rtol, buf + o_ws, buf + o_dg, 1, st))) break;
+      if (cudaMemcpyAsync(d_rgb_host, buf + o_dg, nb, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+          cudaMemcpyAsync(d_depth_host, buf + o_dg + nb, nb, cudaMemcpyDeviceToHost, st) != cudaSuccess) {
+        set_error("D2H copy failed"); rc = 2; break;
+      }
+    }
+    if (cudaMemcpyAsync(stacked_out_host, buf + o_out, 2 * nb, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+        cudaMemcpyAsync(erank_out_host, er, size_t(2 * B) * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess) {
+      set_error("D2H copy failed"); rc = 2; break;
+    }
+    if (k > 0 && idx_host) cudaMemcpyAsync(idx_host, idx, size_t(2) * k * 8, cudaMemcpyDeviceToHost, st);
+  } while (0);
+  cudaFreeAsync(buf, st);
+  cudaError_t e = cudaStreamSynchronize(st);
+  if (rc == 0 && e != cudaSuccess) {
+    set_error("stream sync failed: %s", cudaGetErrorString(e));
+    rc = 2;
+  }
+  return rc;
+}

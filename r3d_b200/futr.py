@@ -60,8 +60,8 @@ class _DecoderLayer(nn.Module):
         self.dropout3 = nn.Dropout(dropout)
 
     def forward(self, tgt, memory, memory_key_padding_mask, pos, query_pos):
-        q = k = tgt + query_pos
-        tgt = self.norm1(tgt + self.dropout1(self.self_attn(q, k, value=tgt)[0]))
+        q = tgt + query_pos                      # the reference feeds the position-added tensor as value too (:289-291)
+        tgt = self.norm1(tgt + self.dropout1(self.self_attn(q, q, value=q)[0]))
         mem = memory + pos
         tgt2 = self.multihead_attn(query=tgt + query_pos, key=mem, value=mem, key_padding_mask=memory_key_padding_mask)[0]
         tgt = self.norm2(tgt + self.dropout2(tgt2))

@@ -950,6 +950,29 @@ def token_fusion_host(rgb: torch.Tensor, depth: torch.Tensor, k: int):
     return out, idx[:, :k]
 
 
+def fuser_step_host(rgb: torch.Tensor, depth: torch.Tensor, gst: Optional[torch.Tensor] = None, k: Optional[int] = None,
+                    rtol: float = DEFAULT_RTOL, erank_weight: float = 1.0, out=None):
+    """The whole hot path on HOST tensors through the single C entry r3d_fuser_step_host (H2D, erank of both
+    modalities, score -> bottom-k -> exchange, backward of `gst` + the erank gradient, D2H).  Returns
+    (stacked, erank (2B,), d_rgb, d_depth, idx (2, k)); gradients are None without `gst`.  `out`: optional tuple of
+    preallocated (pinned) result tensors in that order."""
+    if rgb.is_cuda or depth.is_cuda or (gst is not None and gst.is_cuda):
+        raise R3DError("fuser_step_host takes host tensors")
+    B, T, C = rgb.shape
+    k = C // 4 if k is None else k
+    if out is None:
+        stacked = torch.empty(B, T, 2, C, dtype=rgb.dtype)
+        er = torch.empty(2 * B, dtype=torch.float32)
+        d_r = torch.empty_like(rgb) if gst is not None else None
+        d_d = torch.empty_like(rgb) if gst is not None else None
+        idx = torch.empty(2, max(k, 1), dtype=torch.int64)
+    else:
+        stacked, er, d_r, d_d, idx = out
+    check(_lib.lib().r3d_fuser_step_host(_p(rgb), _p(depth), _p(gst), B, T, C, _dt(rgb), k, float(rtol), float(erank_weight),
+                                         _p(stacked), _p(er), _p(d_r), _p(d_d), _p(idx), _stream()))
+    return stacked, er, d_r, d_d, idx[:, :k]
+
+
 # ---------------------------------------------------------------------------------
 # torch.ops.r3d.* registration (SURVEY.md 8b).  Thin wrappers over the functions above.
 # ---------------------------------------------------------------------------------
