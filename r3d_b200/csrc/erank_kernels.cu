@@ -1255,6 +1255,7 @@ extern "C" int r3d_set_option(const char* key, double value) {
   else if (k == "jacobi_v_after_g") options().jacobi_v_after_g = value != 0.0;
   else if (k == "jacobi_schedule") options().jacobi_schedule = (int)value;
   else if (k == "panel_sym") options().panel_sym = (int)value;
+  else if (k == "lin_fast") options().lin_fast = (int)value;
   else if (k == "panel_debug") g_panel_debug = (int)value;
   else if (k == "panel_grid_cap") g_panel_grid_cap = (int)value;
   else R3D_CHECK(false, "unknown option '%s'", key);

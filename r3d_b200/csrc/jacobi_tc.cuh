@@ -82,6 +82,7 @@ struct Options {
   int gemm_tc = 1;              // 1: refinement / backward / fp32 Gram GEMMs on tcgen05 via bf16 planes, 0: SIMT
   int jacobi_v_after_g = 0;     // 0: V(r) starts right after inner(r) and runs beside the G passes (58.9 ms); 1: V(r) starts after the
                                 //    G passes of round r and runs beside inner(r+1) (60.1 ms with the register-resident inner solver)
+  int lin_fast = 1;             // linear GEMM: 16-warp epilogue variant for bf16 full-tile problems (0: the generic 8-warp one)
   int jacobi_overlap_v = 1;     // run V <- V Q on a side stream, overlapped with the next inner solve
   int panel_sym = 1;            // 1: G <- Q^T G Q as ONE in-place pass over the upper block triangle with mirrored stores
                                 //    (jacobi_sym.cu: 0.56 n^2 read + n^2 written per round); 0: two passes through the scratch

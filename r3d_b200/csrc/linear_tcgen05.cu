@@ -25,6 +25,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "jacobi_tc.cuh"
 #include "pgemm.cuh"
 #include "tc_store.cuh"
 
@@ -36,6 +37,12 @@ constexpr int LM = 128;
 constexpr int LBK = 64;
 constexpr int kLinThreads = 384;   // warps 0-2: producer / MMA / TMEM allocator, warp 3 idle, warps 4-11: epilogue
 constexpr int kEpiWarps = 8;
+// FAST variant (bf16 output, full tiles, no split-K): 16 epilogue warps on 16-column chunks.  The epilogue of the wide
+// GEMMs is bound by latency (ncu: issue slots 32 % busy with 2 epilogue warps per scheduler, top stalls long_scoreboard /
+// wait), so the cure is more warps in flight; 640 threads leave 102 registers each, hence the narrower chunks.
+constexpr int kFastThreads = 640;
+constexpr int kFastEpiWarps = 16;
+constexpr int kFastStg = 32 * 48;  // staging bytes per warp: 32 rows x 32 B of payload, 48-byte pitch
 
 __device__ __forceinline__ uint32_t ln_s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void ln_bar_init(uint64_t* bar, uint32_t count) {
@@ -276,6 +283,67 @@ __device__ __forceinline__ void row_block_finish(uint8_t* stg, int lane, const u
   }
 }
 
+// ---- 32 x 16 bf16 blocks (FAST epilogue): 2 lanes per 32-byte row segment ----
+__device__ __forceinline__ void blk16_issue(const void* base, int64_t off0, int64_t pitch, int lane, uint4 (&raw)[2]) {
+  const __nv_bfloat16* src = (const __nv_bfloat16*)base + off0;
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int id = j * 32 + lane, r = id >> 1, c = id & 1;
+    raw[j] = *reinterpret_cast<const uint4*>(src + r * pitch + c * 8);
+  }
+}
+__device__ __forceinline__ void unpack16(const uint4& a, const uint4& b, float (&o)[16]) {
+  const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    o[2 * u] = __uint_as_float(w[u] << 16);
+    o[2 * u + 1] = __uint_as_float(w[u] & 0xffff0000u);
+  }
+}
+__device__ __forceinline__ void blk16_finish(uint8_t* stg, int lane, const uint4 (&raw)[2], float (&o)[16]) {
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int id = j * 32 + lane, r = id >> 1, c = id & 1;
+    *reinterpret_cast<uint4*>(stg + r * 48 + c * 16) = raw[j];
+  }
+  __syncwarp();
+  unpack16(*reinterpret_cast<const uint4*>(stg + lane * 48), *reinterpret_cast<const uint4*>(stg + lane * 48 + 16), o);
+}
+__device__ __forceinline__ void blk16_store(uint8_t* stg, int lane, const float (&f)[16], __nv_bfloat16* dst, int64_t pitch) {
+  uint32_t w[8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * u], f[2 * u + 1]);
+    w[u] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  __syncwarp();
+  *reinterpret_cast<uint4*>(stg + lane * 48) = make_uint4(w[0], w[1], w[2], w[3]);
+  *reinterpret_cast<uint4*>(stg + lane * 48 + 16) = make_uint4(w[4], w[5], w[6], w[7]);
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int id = j * 32 + lane, r = id >> 1, c = id & 1;
+    *reinterpret_cast<uint4*>(dst + r * pitch + c * 8) = *reinterpret_cast<const uint4*>(stg + r * 48 + c * 16);
+  }
+}
+// sum over the warp's 32 rows of 16 per-lane values: lanes 0-15 (and, duplicated, 16-31) end up with column (lane & 15)
+__device__ __forceinline__ float warp_colsum16(float (&v)[16], int lane) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] += __shfl_xor_sync(0xffffffffu, v[j], 16);
+#pragma unroll
+  for (int half = 8; half >= 1; half >>= 1) {
+    const bool up = (lane & half) != 0;
+#pragma unroll
+    for (int j = 0; j < half; ++j) {
+      const float send = up ? v[j] : v[j + half];
+      const float recv = __shfl_xor_sync(0xffffffffu, send, half);
+      v[j] = (up ? v[j + half] : v[j]) + recv;
+    }
+  }
+  return v[0];
+}
+
 // sum over the warp's 32 rows of 32 per-lane values: lane l ends up holding the column-l total (31 shuffles)
 __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
 #pragma unroll
@@ -292,15 +360,18 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
   return v[0];
 }
 
-template <int TN>
-__global__ void __launch_bounds__(kLinThreads, 1) lin_kernel(const __grid_constant__ CUtensorMap map_a,
-                                                             const __grid_constant__ CUtensorMap map_b, LinDev g) {
+template <int TN, bool FAST = false>
+__global__ void __launch_bounds__(FAST ? kFastThreads : kLinThreads, 1) lin_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                                                   const __grid_constant__ CUtensorMap map_b,
+                                                                                   LinDev g) {
+  constexpr int EW = FAST ? kFastEpiWarps : kEpiWarps;
+  constexpr int STGB = FAST ? kFastStg : kStgWarpBytes;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)((uintptr_t(smem_raw) + 1023) & ~uintptr_t(1023));
   const int a_plane_bytes = LM * 128;              // 128 (m) x 64 (k) bf16
   const int b_plane_bytes = TN * 128;
   uint8_t* stg_base = smem + g.stages * g.stage_bytes;                 // 8 x 2560 B load / store staging
-  float* cs_smem = (float*)(stg_base + kEpiWarps * kStgWarpBytes);     // [4 lane quarters][TN] column sums
+  float* cs_smem = (float*)(stg_base + EW * STGB);                     // [4 lane quarters][TN] column sums
   uint64_t* full_bar = (uint64_t*)(cs_smem + 4 * TN);
   uint64_t* empty_bar = full_bar + 4;
   uint64_t* tmem_full = empty_bar + 4;
@@ -318,7 +389,7 @@ __global__ void __launch_bounds__(kLinThreads, 1) lin_kernel(const __grid_consta
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < g.stages; ++s) { ln_bar_init(&full_bar[s], 1); ln_bar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < 2; ++s) { ln_bar_init(&tmem_full[s], 1); ln_bar_init(&tmem_empty[s], kEpiWarps * 32); }
+    for (int s = 0; s < 2; ++s) { ln_bar_init(&tmem_full[s], 1); ln_bar_init(&tmem_empty[s], EW * 32); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -416,7 +487,87 @@ __global__ void __launch_bounds__(kLinThreads, 1) lin_kernel(const __grid_consta
         ln_commit(&tmem_full[ab]);
       }
     }
-  } else if (warp >= 4) {
+  } else if (FAST && warp >= 4) {
+    // ===================== epilogue, FAST variant: bf16, full tiles, 16 warps x 16-column chunks =====================
+    const int q = warp & 3, cset = (warp - 4) >> 2;        // lane quarter, column set 0..3
+    uint8_t* stg = stg_base + (warp - 4) * STGB;
+    __nv_bfloat16* Dp = (__nv_bfloat16*)g.D;
+    int tt = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++tt) {
+      int sp, m0, n0, kb0, kb1;
+      decode(tile, sp, m0, n0, kb0, kb1);
+      const int ab = tt & 1;
+      ln_wait(&tmem_full[ab], (tt >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int row_w = m0 + q * 32;
+#pragma unroll 1
+      for (int c0 = cset * 16; c0 < TN; c0 += 64) {
+        const int col0 = n0 + c0;
+        uint4 raw_x[2], raw_r[2];
+        if (g.dgelu) blk16_issue(g.aux_in, int64_t(row_w) * g.ldx + col0, g.ldx, lane, raw_x);
+        if (g.residual) blk16_issue(g.residual, int64_t(row_w) * g.ldr + col0, g.ldr, lane, raw_r);
+        uint32_t v[16];
+        const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(ab * TN + c0);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        float x[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) x[j] = __uint_as_float(v[j]);
+        if (g.bias) {
+          float bv[16];                                    // broadcast loads: every lane reads the same 32 bytes
+          const uint4* bp = reinterpret_cast<const uint4*>((const __nv_bfloat16*)g.bias + col0);
+          unpack16(bp[0], bp[1], bv);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) x[j] += bv[j];
+        }
+        if (g.aux_out) blk16_store(stg, lane, x, (__nv_bfloat16*)g.aux_out + int64_t(row_w) * g.ldx + col0, g.ldx);
+        if (g.act == 1) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) x[j] = gelu_tanh_f(bf16_round(x[j]));
+        } else if (g.act == 2) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) x[j] = fmaxf(x[j], 0.f);
+        }
+        if (g.dgelu) {
+          float h[16];
+          blk16_finish(stg, lane, raw_x, h);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) x[j] *= dgelu_tanh_f(h[j]);
+        }
+        if (g.residual) {
+          float r[16];
+          blk16_finish(stg, lane, raw_r, r);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) x[j] += r[j];
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) x[j] = bf16_round(x[j]);
+        blk16_store(stg, lane, x, Dp + int64_t(row_w) * g.ldd + col0, g.ldd);
+        if (g.colsum) {
+          if (g.colsum_abs) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) x[j] = fabsf(x[j]);
+          }
+          const float tot = warp_colsum16(x, lane);
+          if (lane < 16) cs_smem[q * TN + c0 + lane] = tot;
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      ln_arrive(&tmem_empty[ab]);
+      if (g.colsum) {
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+        const int t = threadIdx.x - 128;
+        for (int c = t; c < TN; c += 512)
+          g.colsum[int64_t(m0 / LM) * g.N + n0 + c] = ((cs_smem[c] + cs_smem[TN + c]) + cs_smem[2 * TN + c]) + cs_smem[3 * TN + c];
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+      }
+    }
+  } else if (!FAST && warp >= 4) {
     // ===================== epilogue =====================
     // eight warps: warp w reads TMEM lanes 32 (w % 4) .. + 31 (a hardware rule); warps 4-7 take the even 32-column
     // chunks of the tile, warps 8-11 the odd ones
@@ -843,11 +994,24 @@ extern "C" int r3d_gemm(const void* A, const void* Bm, void* D, int64_t M, int64
   if (int e = lin_make_map(&mb, Bp, planes, b_rows, b_cols, b_cols, N * K, g.b_kmajor != 0)) return e;
   const int64_t tiles = int64_t(splits) * ((M + LM - 1) / LM) * ((N + TN - 1) / TN);
   const int grid = (int)std::min<int64_t>(tiles, kNumSMs);
-  const int smem = g.stages * g.stage_bytes + kEpiWarps * kStgWarpBytes + 4 * TN * 4 + 1024 + 256;
+  // FAST epilogue variant: bf16 output, no split-K, whole tiles only, 16-byte aligned row tensors
+  const bool fast = !f32 && splits == 1 && M % LM == 0 && N % TN == 0 && N % 8 == 0 &&
+                    ((uintptr_t(D) | uintptr_t(g.bias) | uintptr_t(g.residual) | uintptr_t(g.aux_out) | uintptr_t(g.aux_in)) & 15) == 0 &&
+                    options().lin_fast != 0;
+  const int smem = fast ? g.stages * g.stage_bytes + kFastEpiWarps * kFastStg + 4 * TN * 4 + 1024 + 256
+                        : g.stages * g.stage_bytes + kEpiWarps * kStgWarpBytes + 4 * TN * 4 + 1024 + 256;
   R3D_CHECK(smem <= 227 * 1024, "linear GEMM: shared memory budget exceeded (%d)", smem);
   {
     R3D_STAGE(ST_BLOCK, st);
-    if (TN == 256) {
+    if (fast) {
+      static bool done[kMaxDevices] = {};
+      if (per_device_once(done)) {
+        R3D_CUDA(cudaFuncSetAttribute(lin_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        R3D_CUDA(cudaFuncSetAttribute(lin_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      }
+      if (TN == 256) lin_kernel<256, true><<<grid, kFastThreads, smem, st>>>(ma, mb, g);
+      else lin_kernel<128, true><<<grid, kFastThreads, smem, st>>>(ma, mb, g);
+    } else if (TN == 256) {
       static bool done[kMaxDevices] = {};
       if (per_device_once(done))
         R3D_CUDA(cudaFuncSetAttribute(lin_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
