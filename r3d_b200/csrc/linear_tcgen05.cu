@@ -372,7 +372,7 @@ __global__ void __launch_bounds__(FAST ? kFastThreads : kLinThreads, 1) lin_kern
   const int b_plane_bytes = TN * 128;
   uint8_t* stg_base = smem + g.stages * g.stage_bytes;                 // 8 x 2560 B load / store staging
   float* cs_smem = (float*)(stg_base + EW * STGB);                     // [4 lane quarters][TN] column sums
-  uint64_t* full_bar = (uint64_t*)(cs_smem + 4 * TN);
+  uint64_t* full_bar = (uint64_t*)(cs_smem + (FAST ? 8 : 4) * TN);
   uint64_t* empty_bar = full_bar + 4;
   uint64_t* tmem_full = empty_bar + 4;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -554,17 +554,19 @@ __global__ void __launch_bounds__(FAST ? kFastThreads : kLinThreads, 1) lin_kern
             for (int j = 0; j < 16; ++j) x[j] = fabsf(x[j]);
           }
           const float tot = warp_colsum16(x, lane);
-          if (lane < 16) cs_smem[q * TN + c0 + lane] = tot;
+          if (lane < 16) cs_smem[(ab * 4 + q) * TN + c0 + lane] = tot;
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       ln_arrive(&tmem_empty[ab]);
       if (g.colsum) {
+        // the per-quarter sums are double-buffered by tile parity: ONE barrier per tile (the barrier of the next tile
+        // also orders this tile's reads before the buffer's reuse two tiles later), so warps can run ahead
         asm volatile("bar.sync 1, 512;" ::: "memory");
+        const float* cs = cs_smem + ab * 4 * TN;
         const int t = threadIdx.x - 128;
         for (int c = t; c < TN; c += 512)
-          g.colsum[int64_t(m0 / LM) * g.N + n0 + c] = ((cs_smem[c] + cs_smem[TN + c]) + cs_smem[2 * TN + c]) + cs_smem[3 * TN + c];
-        asm volatile("bar.sync 1, 512;" ::: "memory");
+          g.colsum[int64_t(m0 / LM) * g.N + n0 + c] = ((cs[c] + cs[TN + c]) + cs[2 * TN + c]) + cs[3 * TN + c];
       }
     }
   } else if (!FAST && warp >= 4) {
@@ -998,7 +1000,7 @@ extern "C" int r3d_gemm(const void* A, const void* Bm, void* D, int64_t M, int64
   const bool fast = !f32 && splits == 1 && M % LM == 0 && N % TN == 0 && N % 8 == 0 &&
                     ((uintptr_t(D) | uintptr_t(g.bias) | uintptr_t(g.residual) | uintptr_t(g.aux_out) | uintptr_t(g.aux_in)) & 15) == 0 &&
                     options().lin_fast != 0;
-  const int smem = fast ? g.stages * g.stage_bytes + kFastEpiWarps * kFastStg + 4 * TN * 4 + 1024 + 256
+  const int smem = fast ? g.stages * g.stage_bytes + kFastEpiWarps * kFastStg + 8 * TN * 4 + 1024 + 256
                         : g.stages * g.stage_bytes + kEpiWarps * kStgWarpBytes + 4 * TN * 4 + 1024 + 256;
   R3D_CHECK(smem <= 227 * 1024, "linear GEMM: shared memory budget exceeded (%d)", smem);
   {
