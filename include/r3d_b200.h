@@ -58,16 +58,21 @@ int64_t r3d_launch_count(int reset);
  *   "jacobi_chunks"       1 (default); 2 = two half-batches on two streams (measured slower)
  *   "panel_merged"        0 (default); 1 = both G passes in one launch with H in an L2-resident ring, sized by
  *                         "panel_group_mb" (8) and "panel_ring" (6) (less DRAM traffic, measured slower)
- *   "jacobi_schedule"     1 (default) = spread schedule where the block count allows it (a power of two >= 8, i.e.
- *                         n in (192,256], (448,512], (960,1024], ...): the rounds of a sweep are XOR matchings grouped three
- *                         at a time into super-rounds confined to 128-column groups, so G and V are streamed once per
- *                         super-round instead of once per round; 0 = circle-method round robin
+ *   "jacobi_schedule"     0 = circle-method round robin, one panel update of G and V per round;
+ *                         2 = XOR matchings grouped three at a time into super-rounds confined to 128-column groups
+ *                         (where the block count is a power of two >= 8, i.e. n in (192,256], (448,512], (960,1024], ...):
+ *                         G is updated every round, the three V updates of a super-round run as ONE chained pass over V;
+ *                         1 = spread schedule on the same grouping: group-local problems + one K = 128 pass over G and V
+ *                         per super-round (measured slower)
  *   "row_chunk_mult"      row chunks per SM of the column-reduction kernels, default 4
  *   "panel_debug", "panel_grid_cap"   test / timing hooks of the panel kernel */
 int r3d_set_option(const char* key, double value);
 /* Test hook: one tensor-core panel-update round (G <- Q^T G Q via H, V <- V Q) on caller buffers. */
 int r3d_debug_panel_round(float* G, float* H, float* V, const float* Qb, int64_t B, int np, int round,
                           int* scratch, void* stream);
+/* Test hook: the chained V update  V <- V Q1 Q2 Q3  of three XOR rounds (masks ga, gb, ga ^ gb); Q3 = the three rounds'
+ * Q^T buffers back to back, scratch = B * 32 + 3 * B * np/64 ints. */
+int r3d_debug_vchain(float* V, float* Q3, int64_t B, int np, int ga, int gb, int* scratch, void* stream);
 /* Measurement hook: panel tiles (128 rows x 64 output columns: 32 KB read + 32 KB written) the Jacobi panel kernel
  * has actually processed on the current device since the last reset -- out3[0] G passes, out3[1] V passes, out3[2]
  * tiles of the group-local 128 x 128 problems of the spread schedule (an L2-resident working set, not HBM traffic).

@@ -151,6 +151,8 @@ struct JacobiWs {
   float* Sg; float* Sh; float* Pv; float* Pt[2];   // local G, its ping-pong scratch, local V (= P), P^T (double-buffered)
   float* Ql[2];                                    // Q^T of the local rounds (2 tasks of 64 x 64 per group)
   int* lflag[3]; int* gflag[2];                    // per local task flags of the three rounds; per group flags
+  // chained schedule (jacobi_schedule = 2): Q^T and task flags of two slots x three rounds (alias the buffers above)
+  float* Qc[6]; int* qflagc[6];
 };
 
 static inline int jacobi_np(int64_t n) { return int(((n + JM - 1) / JM) * JM); }
@@ -168,7 +170,7 @@ static size_t jacobi_ws_bytes(int64_t B, int64_t n) {   // includes slack so tha
   size_t i = size_t(B) * (JMAX_SWEEPS + 2 * nt) + JMAX_SWEEPS + 2 * (2 * kPanelSyncGroups + 8);
   if (np % 128 == 0) {                                  // spread schedule: Sg, Sh, Pv, Pt[2] + flags
     f += size_t(B) * 6 * np * 128;
-    i += size_t(B) * 5 * nt;
+    i += size_t(B) * 8 * nt;
   }
   return f * 4 + i * 4 + 4096;
 }
@@ -202,6 +204,12 @@ static JacobiWs jacobi_carve(void* ws, int64_t B, int64_t n) {
     w.Ql[1] = (float*)p; p += gsz / 2;
     for (int k = 0; k < 3; ++k) { w.lflag[k] = (int*)p; p += size_t(B) * w.nt * 4; }   // B * ng * 2 local tasks = B * nt
     for (int k = 0; k < 2; ++k) { w.gflag[k] = (int*)p; p += size_t(B) * (w.nt / 2) * 4; }
+    // the chained schedule never runs the group-local problems: its six Q^T buffers (B * nt * 64 * 64 floats = half a
+    // group buffer each) live in Sg, Sh, Pv
+    float* const big[3] = {w.Sg, w.Sh, w.Pv};
+    for (int k = 0; k < 6; ++k) w.Qc[k] = big[k >> 1] + (k & 1) * (gsz / 8);
+    for (int k = 0; k < 3; ++k) w.qflagc[k] = w.lflag[k];
+    for (int k = 3; k < 6; ++k) { w.qflagc[k] = (int*)p; p += size_t(B) * w.nt * 4; }
   }
   return w;
 }
@@ -1221,6 +1229,28 @@ extern "C" int r3d_debug_panel_round(float* G, float* H, float* V, const float* 
   return panel_tc_update_g(&ptc, 0, round, 0, cnt, qflag, st);
 }
 
+// Debug/test hook of the chained V update: V <- V Q1 Q2 Q3 for the XOR rounds with masks ga, gb, ga ^ gb.  Q3 holds the
+// three rounds' Q^T buffers back to back (3 x (B, np/64, 64, 64)); scratch: B * 32 + 3 * B * np/64 ints.
+extern "C" int r3d_debug_vchain(float* V, float* Q3, int64_t B, int np, int ga, int gb, int* scratch, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  R3D_CHECK(panel_chain_supported(np), "np / 32 must be a power of two >= 8");
+  R3D_CHECK(ga > 0 && gb > 0 && ga != gb && ga < np / JB && gb < np / JB, "bad masks");
+  const int nt = np / JM;
+  int* cnt = scratch;
+  int* qflag = scratch + B * JMAX_SWEEPS;
+  R3D_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int) * B * JMAX_SWEEPS, st));
+  std::vector<int> ones(3 * B * nt, 1);
+  R3D_CUDA(cudaMemcpyAsync(qflag, ones.data(), sizeof(int) * 3 * B * nt, cudaMemcpyHostToDevice, st));
+  R3D_CUDA(cudaStreamSynchronize(st));
+  PanelTc ptc;
+  if (int e = panel_tc_prepare(&ptc, V, nullptr, V, Q3, Q3, B, np)) return e;
+  const size_t qsz = size_t(B) * nt * JM * JM;
+  float* qc[6] = {Q3, Q3 + qsz, Q3 + 2 * qsz, Q3, Q3 + qsz, Q3 + 2 * qsz};
+  if (int e = panel_tc_prepare_chain(&ptc, qc)) return e;
+  const int* fl[3] = {qflag, qflag + B * nt, qflag + 2 * B * nt};
+  return panel_tc_update_v_chain(&ptc, 0, groups_of(SuperRound{ga, gb}), 0, cnt, fl, st);
+}
+
 extern "C" int r3d_panel_tiles(uint64_t* out3, int reset) {
   R3D_CHECK(out3 != nullptr, "null pointer");
   unsigned long long v[3];
@@ -1448,6 +1478,7 @@ struct StreamSet {
   cudaStream_t chunk[kMaxChunks] = {nullptr, nullptr};     // chunk 0 uses the caller's stream
   cudaStream_t vst[kMaxChunks] = {nullptr, nullptr};
   cudaEvent_t ev_inner[kMaxChunks][2], ev_v[kMaxChunks][2], ev_fork, ev_join[kMaxChunks];
+  cudaEvent_t ev_inner_c[kMaxChunks][2], ev_v_c[kMaxChunks][2];   // chained schedule: per slot
   int create() {
     for (int c = 0; c < kMaxChunks; ++c) {
       R3D_CUDA(cudaStreamCreateWithFlags(&chunk[c], cudaStreamNonBlocking));
@@ -1456,6 +1487,8 @@ struct StreamSet {
       for (int i = 0; i < 2; ++i) {
         R3D_CUDA(cudaEventCreateWithFlags(&ev_inner[c][i], cudaEventDisableTiming));
         R3D_CUDA(cudaEventCreateWithFlags(&ev_v[c][i], cudaEventDisableTiming));
+        R3D_CUDA(cudaEventCreateWithFlags(&ev_inner_c[c][i], cudaEventDisableTiming));
+        R3D_CUDA(cudaEventCreateWithFlags(&ev_v_c[c][i], cudaEventDisableTiming));
       }
     }
     R3D_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
@@ -1515,9 +1548,11 @@ static int jacobi_run(const float* G, int64_t B, int64_t n, void* workspace, flo
   const bool overlap = tc && options().jacobi_overlap_v != 0;
   StreamRef g_streams;
   std::vector<SuperRound> plan;
-  if (tc && options().jacobi_schedule == 1 && w.Sg != nullptr) plan = spread_plan(w.nb);
-  const bool spread = !plan.empty();
   const bool sym = tc && options().panel_sym != 0 && panel_sym_supported(w.np);
+  const bool want_chain = sym && options().jacobi_schedule == 2 && panel_chain_supported(w.np);
+  if (tc && (options().jacobi_schedule == 1 || want_chain) && w.Sg != nullptr) plan = spread_plan(w.nb);
+  const bool chain = want_chain && !plan.empty();
+  const bool spread = !plan.empty() && !chain;
   if (tc) {
     if (int e = panel_tc_prepare(&ptc, w.Gp, w.H, w.Vt, w.Qb[0], w.Qb[1], B, w.np)) return e;
     if (sym) { if (int e = panel_sym_prepare(&ptc)) return e; }
@@ -1577,6 +1612,46 @@ static int jacobi_run(const float* G, int64_t B, int64_t n, void* workspace, flo
     }
     return 0;
   };
+  // chained schedule: the three XOR rounds of a super-round run as ordinary rounds on G (inner solve + one-pass
+  // symmetric update each), their V updates as ONE chained pass over V on the side stream
+  bool vc_pending[2] = {false, false};
+  int chain_iter = 0;
+  if (chain) { if (int e = panel_tc_prepare_chain(&ptc, w.Qc)) return e; }
+  auto chain_round = [&](const SuperRound& sr, bool first_of_sweep, int sweep) -> int {
+    const int slot = (chain_iter++) & 1;
+    if (overlap && vc_pending[slot]) {      // the chained pass that last read this slot's Q buffers must be done
+      R3D_CUDA(cudaStreamWaitEvent(st, g_streams->ev_v_c[chunk][slot], 0));
+      vc_pending[slot] = false;
+    }
+    const int masks[3] = {sr.a, sr.b, sr.a ^ sr.b};
+    for (int k = 0; k < 3; ++k) {
+      const int qi = 3 * slot + k, code = -masks[k];
+      const bool generic = first_of_sweep && k == 0;
+      {
+        R3D_STAGE(ST_JACOBI_INNER, st);
+        if (!generic && options().jacobi_inner_regs != 0)
+          jacobi_inner_cross_kernel<<<dim3(w.nt, (unsigned)B), 256, 0, st>>>(w.Gp, w.np, w.nb, w.nt, code, sweep, w.cnt,
+                                                                            w.qflagc[qi], w.Qc[qi], tol, w.nu, nullptr, 1);
+        else
+          jacobi_inner_kernel<<<dim3(w.nt, (unsigned)B), 256, 0, st>>>(w.Gp, w.np, w.nb, w.nt, code, sweep, w.cnt,
+                                                                      w.qflagc[qi], w.Qc[qi], tol, w.nu, 1, nullptr, 1,
+                                                                      generic ? 1 : 0);
+        R3D_LAUNCH_CHECK();
+      }
+      // the chain needs the three inner solves only: fork right behind the third one, beside its G update
+      if (k == 2 && overlap) R3D_CUDA(cudaEventRecord(g_streams->ev_inner_c[chunk][slot], st));
+      if (int e = panel_sym_update_g(&ptc, 2 + qi, code, sweep, w.cnt, w.qflagc[qi], st)) return e;
+    }
+    const PanelGroups grp = groups_of(sr);
+    const int* fl[3] = {w.qflagc[3 * slot], w.qflagc[3 * slot + 1], w.qflagc[3 * slot + 2]};
+    if (!overlap) return panel_tc_update_v_chain(&ptc, slot, grp, sweep, w.cnt, fl, st);
+    cudaStream_t vs = g_streams->vst[chunk];
+    R3D_CUDA(cudaStreamWaitEvent(vs, g_streams->ev_inner_c[chunk][slot], 0));
+    if (int e = panel_tc_update_v_chain(&ptc, slot, grp, sweep, w.cnt, fl, vs)) return e;
+    R3D_CUDA(cudaEventRecord(g_streams->ev_v_c[chunk][slot], vs));
+    vc_pending[slot] = true;
+    return 0;
+  };
   PanelTc loc;
   const int ng = w.np / 128;
   if (spread) {
@@ -1629,20 +1704,23 @@ static int jacobi_run(const float* G, int64_t B, int64_t n, void* workspace, flo
       jacobi_active_kernel<<<1, 256, 0, st>>>(w.cnt, (int)B, sweep);
       R3D_LAUNCH_CHECK();
     }
-    const int steps = spread ? (int)plan.size() : rounds;
+    const int steps = (spread || chain) ? (int)plan.size() : rounds;
     for (int r = 0; r < steps; ++r, ++iter) {
       const int qb = tc ? (iter & 1) : 0;
       if (overlap && v_pending[qb]) {        // the V update that last read this Q / P^T buffer must be done
         R3D_CUDA(cudaStreamWaitEvent(st, g_streams->ev_v[chunk][qb], 0));
         v_pending[qb] = false;
       }
-      if (!spread) { if (int e = plain_round(r, r == 0, sweep, qb)) return e; }
+      if (chain && plan[r].b != 0) { if (int e = chain_round(plan[r], r == 0, sweep)) return e; }
+      else if (!spread && !chain) { if (int e = plain_round(r, r == 0, sweep, qb)) return e; }
       else if (plan[r].b == 0) { if (int e = plain_round(-plan[r].a, false, sweep, qb)) return e; }
       else { if (int e = super_round(plan[r], r == 0, sweep, qb)) return e; }
     }
   }
-  for (int i = 0; i < 2; ++i)
+  for (int i = 0; i < 2; ++i) {
     if (overlap && v_pending[i]) R3D_CUDA(cudaStreamWaitEvent(st, g_streams->ev_v[chunk][i], 0));
+    if (overlap && vc_pending[i]) R3D_CUDA(cudaStreamWaitEvent(st, g_streams->ev_v_c[chunk][i], 0));
+  }
   {
     dim3 grid((unsigned)std::min<int64_t>((n + 7) / 8, 64), (unsigned)B);
     R3D_STAGE(ST_JACOBI_EXTRACT, st);

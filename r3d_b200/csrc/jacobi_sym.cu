@@ -471,7 +471,9 @@ int panel_sym_update_g(PanelTc* h, int qbuf, int round, int sweep, const int* cn
   int grid = (int)std::min<int64_t>(total, 2 * kNumSMs);
   if (g_panel_grid_cap > 0) grid = std::min(grid, g_panel_grid_cap);
   StageScope scope(h->local ? ST_JACOBI_LOCAL : ST_JACOBI_UPDATE, st);
-  panel_sym_kernel<<<grid, kSymThreads, SMEM_TOTAL, st>>>(h->map_g32, h->map_q[qbuf], h->G, (int)h->B, h->np, h->nb, h->nt,
+  // qbuf 0/1: the round-parity buffers; 2..7: the buffers of the chained schedule
+  const CUtensorMap& mq = qbuf < 2 ? h->map_q[qbuf] : h->map_qc[qbuf - 2];
+  panel_sym_kernel<<<grid, kSymThreads, SMEM_TOTAL, st>>>(h->map_g32, mq, h->G, (int)h->B, h->np, h->nb, h->nt,
                                                           round, sweep, h->bdiv, cnt, qflag);
   R3D_LAUNCH_CHECK();
   return 0;

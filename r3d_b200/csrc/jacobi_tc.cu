@@ -517,6 +517,330 @@ __global__ void __maxnreg__(72) panel_update_tc_kernel(const __grid_constant__ C
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Chained V update (jacobi_schedule = 2).  With the XOR ordering, three consecutive rounds {a, b, a^b} only pair blocks
+// inside the 4-block cosets of the subspace <a, b> (jacobi_tc.cuh: PanelGroups), so  V <- V Q1 Q2 Q3  restricted to a
+// coset is a product of three 128 x 128 block-diagonal-in-pairs matrices.  One tile = 128 rows x the 4 blocks of a
+// coset: loaded ONCE (64 KB), multiplied by the three rounds' rotations with the intermediate results staying on chip
+// (TMEM -> registers -> hi/lo split -> shared-memory operand slabs), stored ONCE: a third of the HBM traffic of three
+// separate passes.  G keeps its per-round update (the inner solver needs the updated diagonal blocks every round).
+//
+// A tile makes 12 uses of the 2-stage ring, use u = 4 k + 2 p + s: round k, pair p of the coset, K slab s of the pair
+// (M = 128, N = 64, K = 32 per use, 3xTF32).  Round 0 gets its A slabs by TMA, rounds 1-2 from the drainers (warps 6-9),
+// which read the previous round's accumulator; the accumulators ping-pong between two 128-column TMEM buffers.
+// ------------------------------------------------------------------------------------------------------------------
+struct ChainJob {
+  int ga, gb, plo, phi;                 // the coset structure of the three rounds (masks ga, gb, ga ^ gb)
+  const int* qflag[3];                  // task flags of the three rounds
+};
+// per tile: sig = for each round the local block index (2 bits each) at accumulator column positions 0..3
+// ([pair 0: I, J | pair 1: I, J]); task = the rounds' task indices of the two pairs (8 bits each)
+struct ChainPlan { int x; uint32_t sig; uint64_t task; };
+
+__device__ __forceinline__ int chain_blk(const ChainJob& cj, int x, int j) {
+  return x ^ ((j & 1) ? cj.ga : 0) ^ ((j & 2) ? cj.gb : 0);
+}
+__device__ __forceinline__ ChainPlan chain_plan(const ChainJob& cj, int g) {
+  ChainPlan cp;
+  int x = g;
+  x = ((x >> cj.plo) << (cj.plo + 1)) | (x & ((1 << cj.plo) - 1));
+  x = ((x >> cj.phi) << (cj.phi + 1)) | (x & ((1 << cj.phi) - 1));
+  cp.x = x; cp.sig = 0; cp.task = 0;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const int lm = k + 1;
+    const int mk = ((lm & 1) ? cj.ga : 0) ^ ((lm & 2) ? cj.gb : 0);
+    const int hb = 31 - __clz(mk);
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+      const int j = p == 0 ? 0 : (lm == 1 ? 2 : 1), jj = j ^ lm;
+      const int sel = (chain_blk(cj, x, j) >> hb) & 1;            // the block with the mask's top bit clear comes first
+      const int il = sel ? jj : j, jl = sel ? j : jj;
+      cp.sig |= uint32_t(il | (jl << 2)) << (8 * k + 4 * p);
+      const int I = chain_blk(cj, x, il);
+      const int t = ((I >> (hb + 1)) << hb) | (I & ((1 << hb) - 1));
+      cp.task |= uint64_t(t & 0xff) << (16 * k + 8 * p);
+    }
+  }
+  return cp;
+}
+__device__ __forceinline__ int chain_sig(const ChainPlan& cp, int k, int pos) { return (cp.sig >> (8 * k + 2 * pos)) & 3; }
+__device__ __forceinline__ int chain_task(const ChainPlan& cp, int k, int p) { return int((cp.task >> (16 * k + 8 * p)) & 0xff); }
+// accumulator column position of local block l after round k
+__device__ __forceinline__ int chain_pos(const ChainPlan& cp, int k, int l) {
+  int pos = 0;
+#pragma unroll
+  for (int q = 1; q < 4; ++q) if (chain_sig(cp, k, q) == l) pos = q;
+  return pos;
+}
+
+struct ChainTile { int b, g, mt; bool run; ChainPlan cp; };
+__device__ __forceinline__ ChainTile decode_chain(int tile, int ng, int nt, int mtiles, int sweep,
+                                                  const int* __restrict__ cnt, const ChainJob& cj) {
+  ChainTile t;
+  t.b = tile / (ng * mtiles);
+  const int r = tile - t.b * ng * mtiles;
+  t.g = r / mtiles;
+  t.mt = r - t.g * mtiles;
+  t.run = !(sweep > 0 && cnt[t.b * JMAXS + sweep - 1] == 0);
+  if (t.run) {
+    t.cp = chain_plan(cj, t.g);
+    int any = 0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+      for (int p = 0; p < 2; ++p) any |= cj.qflag[k][t.b * nt + chain_task(t.cp, k, p)];
+    t.run = any != 0;
+  }
+  return t;
+}
+
+constexpr int TMEM_COLS_C = 256;       // two 128-column accumulators
+constexpr int CUSES = 12;
+
+__device__ __forceinline__ void tmem_ld32c(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__global__ void __maxnreg__(72) panel_vchain_kernel(const __grid_constant__ CUtensorMap map_v,
+                                                    const __grid_constant__ CUtensorMap map_q0,
+                                                    const __grid_constant__ CUtensorMap map_q1,
+                                                    const __grid_constant__ CUtensorMap map_q2, float* __restrict__ V,
+                                                    ChainJob cj, int B, int np, int nb, int nt, int sweep,
+                                                    const int* __restrict__ cnt) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)((uintptr_t(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* stg_base = smem + NSTAGE * STAGE;
+  uint64_t* raw_full = (uint64_t*)(smem + NSTAGE * STAGE + 4 * STG_WARP);   // TMA -> splitters
+  uint64_t* split_done = raw_full + NSTAGE;      // 128 splitters + 4 (drainer warps, or splitters 0-3 in round 0) -> MMA
+  uint64_t* smem_empty = split_done + NSTAGE;    // MMA commit -> producer / drainers
+  uint64_t* acc_full = smem_empty + NSTAGE;      // [2] MMA commit (a round is complete) -> drainers / epilogue
+  uint64_t* acc_empty = acc_full + 2;            // [2] drainers / epilogue (4 warps) -> MMA
+  uint32_t* tmem_slot = (uint32_t*)(acc_empty + 2);
+
+  if (sweep > 0 && cnt[B * JMAXS + sweep] == 0) return;          // every matrix converged
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int mtiles = np / TM, ng = nb >> 2;
+  const int total = B * ng * mtiles;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_v) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q0) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q1) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q2) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < NSTAGE; ++s) { bar_init(&raw_full[s], 1); bar_init(&split_done[s], 132); bar_init(&smem_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { bar_init(&acc_full[s], 1); bar_init(&acc_empty[s], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_slot)),
+                 "n"(TMEM_COLS_C) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect()) {
+      int it = 0, ntiles = 0;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        const ChainTile ti = decode_chain(tile, ng, nt, mtiles, sweep, cnt, cj);
+        if (!ti.run) continue;
+#pragma unroll 1
+        for (int u = 0; u < CUSES; ++u, ++it) {
+          const int k = u >> 2, p = (u >> 1) & 1, sl = u & 1;
+          const int s = it % NSTAGE;
+          const uint32_t ph = (it / NSTAGE) & 1;
+          bar_wait(&smem_empty[s], ph ^ 1);
+          uint8_t* st = smem + s * STAGE;
+          const CUtensorMap* mq = k == 0 ? &map_q0 : (k == 1 ? &map_q1 : &map_q2);
+          const int qrow = (ti.b * nt + chain_task(ti.cp, k, p)) * PM;
+          if (k == 0) {
+            bar_expect_tx(&raw_full[s], A_RAW + Q_RAW);
+            const int cb = chain_blk(cj, ti.cp.x, chain_sig(ti.cp, 0, 2 * p + sl));
+            tma_3d(st, &map_v, &raw_full[s], 0, ti.mt * TM, ti.b * nb + cb);
+          } else {
+            bar_expect_tx(&raw_full[s], Q_RAW);
+          }
+          tma_2d(st + 2 * A_RAW, mq, &raw_full[s], sl * PB, qrow);
+        }
+        ++ntiles;
+      }
+      // one chained tile moves 64 KB in + 64 KB out: two units of the V counter
+      if (ntiles > 0) atomicAdd(&g_panel_tiles[1], (unsigned long long)(2 * ntiles));
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (elect()) {
+      int it = 0, tt = 0;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        const ChainTile ti = decode_chain(tile, ng, nt, mtiles, sweep, cnt, cj);
+        if (!ti.run) continue;
+#pragma unroll 1
+        for (int k = 0; k < 3; ++k) {
+          const int buf = k & 1;
+          const int n = buf == 0 ? 2 * tt + (k >> 1) : tt;       // how often this accumulator was produced before
+          bar_wait(&acc_empty[buf], (n & 1) ^ 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+          for (int ps = 0; ps < 4; ++ps, ++it) {
+            const int s = it % NSTAGE;
+            const uint32_t ph = (it / NSTAGE) & 1;
+            bar_wait(&split_done[s], ph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t d = tmem_base + buf * 128 + (ps >> 1) * PM;
+            const uint32_t a_hi = s_u32(smem + s * STAGE), a_lo = a_hi + A_RAW;
+            const uint32_t q_hi = a_hi + 2 * A_RAW, q_lo = q_hi + Q_RAW;
+            uint32_t first = ps & 1;                             // the pair's accumulator takes two K slabs
+#pragma unroll
+            for (int prod = 0; prod < 3; ++prod) {
+              const uint32_t ab = (prod == 2) ? a_lo : a_hi;
+              const uint32_t qb = (prod == 1) ? q_lo : q_hi;
+#pragma unroll
+              for (int kk = 0; kk < PB / 8; ++kk) {
+                umma_tf32(d, desc_sw128(ab + kk * 32, 16, 1024), desc_sw128(qb + kk * 32, 16, 1024), first);
+                first = 1;
+              }
+            }
+            umma_commit_to(&smem_empty[s]);
+          }
+          umma_commit_to(&acc_full[buf]);
+        }
+        ++tt;
+      }
+    }
+  } else if (warp >= 2 && warp < 6) {
+    // ===================== splitters =====================
+    const int t = threadIdx.x - 64;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+      const ChainTile ti = decode_chain(tile, ng, nt, mtiles, sweep, cnt, cj);
+      if (!ti.run) continue;
+#pragma unroll 1
+      for (int u = 0; u < CUSES; ++u, ++it) {
+        const int s = it % NSTAGE;
+        const uint32_t ph = (it / NSTAGE) & 1;
+        bar_wait(&raw_full[s], ph);
+        uint8_t* st = smem + s * STAGE;
+        if (u < 4) {
+          float4* a_hi = reinterpret_cast<float4*>(st);
+          float4* a_lo = reinterpret_cast<float4*>(st + A_RAW);
+#pragma unroll 4
+          for (int e = t; e < A_RAW / 16; e += 128) {
+            const float4 x = a_hi[e];
+            float4 h, l;
+            h.x = tf32_rn(x.x); l.x = x.x - h.x;
+            h.y = tf32_rn(x.y); l.y = x.y - h.y;
+            h.z = tf32_rn(x.z); l.z = x.z - h.z;
+            h.w = tf32_rn(x.w); l.w = x.w - h.w;
+            a_hi[e] = h; a_lo[e] = l;
+          }
+        }
+        float4* q_hi = reinterpret_cast<float4*>(st + 2 * A_RAW);
+        float4* q_lo = reinterpret_cast<float4*>(st + 2 * A_RAW + Q_RAW);
+#pragma unroll 4
+        for (int e = t; e < Q_RAW / 16; e += 128) {
+          const float4 x = q_hi[e];
+          float4 h, l;
+          h.x = tf32_rn(x.x); l.x = x.x - h.x;
+          h.y = tf32_rn(x.y); l.y = x.y - h.y;
+          h.z = tf32_rn(x.z); l.z = x.z - h.z;
+          h.w = tf32_rn(x.w); l.w = x.w - h.w;
+          q_hi[e] = h; q_lo[e] = l;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        bar_arrive(&split_done[s]);
+        if (u < 4 && t < 4) bar_arrive(&split_done[s]);          // round 0 has no drainers: arrivals 129-132
+      }
+    }
+  } else if (warp >= 6) {
+    // ===================== drainers (rounds 1, 2) + epilogue =====================
+    const int q = warp & 3;                        // TMEM lanes [32q, 32q + 32) = tile rows
+    const uint32_t lane_addr = uint32_t(q * 32) << 16;
+    const int row = q * 32 + lane;                 // operand row of this lane
+    int tt = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+      const ChainTile ti = decode_chain(tile, ng, nt, mtiles, sweep, cnt, cj);
+      if (!ti.run) continue;
+#pragma unroll 1
+      for (int k = 1; k < 3; ++k) {
+        const int src = (k - 1) & 1;               // accumulator of the previous round
+        const int n = src == 0 ? 2 * tt : tt;      // its production index (round 0 -> buffer 0, round 1 -> buffer 1)
+        bar_wait(&acc_full[src], n & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+        for (int ps = 0; ps < 4; ++ps) {
+          const int it = tt * CUSES + k * 4 + ps;
+          const int s = it % NSTAGE;
+          const uint32_t ph = (it / NSTAGE) & 1;
+          // K slab ps of round k = local block sig[k][ps] = column position pos of the previous accumulator
+          const int pos = chain_pos(ti.cp, k - 1, chain_sig(ti.cp, k, ps));
+          uint32_t v[32];
+          tmem_ld32c(tmem_base + lane_addr + uint32_t(src * 128 + pos * 32), v);
+          bar_wait(&smem_empty[s], ph ^ 1);
+          uint8_t* a_hi = smem + s * STAGE + row * 128;
+          uint8_t* a_lo = a_hi + A_RAW;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            float4 h, l;
+            const float x0 = __uint_as_float(v[4 * c]), x1 = __uint_as_float(v[4 * c + 1]);
+            const float x2 = __uint_as_float(v[4 * c + 2]), x3 = __uint_as_float(v[4 * c + 3]);
+            h.x = tf32_rn(x0); l.x = x0 - h.x;
+            h.y = tf32_rn(x1); l.y = x1 - h.y;
+            h.z = tf32_rn(x2); l.z = x2 - h.z;
+            h.w = tf32_rn(x3); l.w = x3 - h.w;
+            const int off = (c ^ (row & 7)) << 4;
+            *reinterpret_cast<float4*>(a_hi + off) = h;
+            *reinterpret_cast<float4*>(a_lo + off) = l;
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) bar_arrive(&split_done[s]);
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) bar_arrive(&acc_empty[src]);
+      }
+      // ---- round 2's accumulator (buffer 0, second production of this tile) -> V, in place
+      bar_wait(&acc_full[0], (2 * tt + 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      float* out = V + int64_t(ti.b) * np * np;
+#pragma unroll 1
+      for (int pos = 0; pos < 4; ++pos) {
+        uint32_t v[32];
+        tmem_ld32c(tmem_base + lane_addr + uint32_t(pos * 32), v);
+        const int cb = chain_blk(cj, ti.cp.x, chain_sig(ti.cp, 2, pos));
+        staged_store_32x32(stg_base + q * STG_WARP, lane, v, out + (int64_t(cb) * np + ti.mt * TM + q * 32) * PB, PB, 0);
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) bar_arrive(&acc_empty[0]);
+      ++tt;
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS_C) : "memory");
+  }
+}
+
 typedef CUresult (*EncodeTiledFn2)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -563,6 +887,9 @@ int make_map_q(CUtensorMap* m, const float* base, int64_t rows, int pitch = PM) 
 
 }  // namespace
 
+int g_panel_debug = 0;
+int g_panel_grid_cap = 0;
+
 bool panel_tc_supported(int np) { return np % TM == 0; }
 
 int panel_tc_prepare(PanelTc* h, float* G, float* H, float* V, const float* Qb0, const float* Qb1, int64_t B,
@@ -578,6 +905,7 @@ int panel_tc_prepare(PanelTc* h, float* G, float* H, float* V, const float* Qb0,
   if (per_device_once(attr_done)) {
     R3D_CUDA(cudaFuncSetAttribute(panel_update_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
     R3D_CUDA(cudaFuncSetAttribute(panel_update_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    R3D_CUDA(cudaFuncSetAttribute(panel_vchain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
   }
   return 0;
 }
@@ -589,6 +917,36 @@ int panel_tc_prepare_groups(PanelTc* h, const float* Pt0, const float* Pt1) {
   return make_map_q(&h->map_p[1], Pt1, rows, 128);
 }
 
+// Q^T buffers of the chained schedule: two slots of three rounds each
+int panel_tc_prepare_chain(PanelTc* h, float* const Qc[6]) {
+  for (int i = 0; i < 6; ++i)
+    if (int e = make_map_q(&h->map_qc[i], Qc[i], h->B * h->nt * PM)) return e;
+  return 0;
+}
+
+bool panel_chain_supported(int np) {
+  const int nb = np / PB;
+  return np % TM == 0 && nb >= 8 && (nb & (nb - 1)) == 0 && nb / 2 <= 256;
+}
+
+// V <- V Q1 Q2 Q3 for the three rounds of a super-round (masks ga, gb, ga ^ gb), one launch, one pass over V.
+int panel_tc_update_v_chain(PanelTc* h, int slot, const PanelGroups& grp, int sweep, const int* cnt,
+                            const int* const qflag[3], cudaStream_t st) {
+  const int mtiles = h->np / TM;
+  const int64_t tiles = h->B * (h->nb / 4) * mtiles;
+  ChainJob cj;
+  cj.ga = grp.ga; cj.gb = grp.gb; cj.plo = grp.plo; cj.phi = grp.phi;
+  for (int k = 0; k < 3; ++k) cj.qflag[k] = qflag[k];
+  int grid = (int)std::min<int64_t>(tiles, 2 * kNumSMs);
+  if (g_panel_grid_cap > 0) grid = std::min(grid, g_panel_grid_cap);
+  StageScope scope(ST_JACOBI_VUPDATE, st);
+  panel_vchain_kernel<<<grid, kPanelThreads, SMEM_TOTAL, st>>>(h->map_v, h->map_qc[3 * slot], h->map_qc[3 * slot + 1],
+                                                               h->map_qc[3 * slot + 2], h->V, cj, (int)h->B, h->np, h->nb,
+                                                               h->nt, sweep, cnt);
+  R3D_LAUNCH_CHECK();
+  return 0;
+}
+
 int panel_tiles_read(unsigned long long out[3], int reset) {
   R3D_CUDA(cudaMemcpyFromSymbol(out, g_panel_tiles, sizeof(unsigned long long) * 3));
   if (reset) {
@@ -597,9 +955,6 @@ int panel_tiles_read(unsigned long long out[3], int reset) {
   }
   return 0;
 }
-
-int g_panel_debug = 0;
-int g_panel_grid_cap = 0;
 
 static int panel_launch(PanelTc* h, const CUtensorMap& in, const CUtensorMap& q, float* out, int transposed,
                         int skip_on_qflag, int round, int sweep, const int* cnt, const int* qflag, int stage_id,

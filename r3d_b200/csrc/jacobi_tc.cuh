@@ -9,6 +9,7 @@ struct PanelTc {
   CUtensorMap map_g, map_h, map_v, map_q[2];   // Q^T is double-buffered (round parity)
   CUtensorMap map_p[2];                        // spread schedule: P^T of the 4-block groups, double-buffered
   CUtensorMap map_g32;                         // one-pass symmetric update: 32-row boxes of G (jacobi_sym.cu)
+  CUtensorMap map_qc[6];                       // chained schedule: Q^T of two slots x three rounds (qbuf = 2 + 3 slot + k)
   float *G, *H, *V;
   int64_t B;
   int np, nb, nt;
@@ -39,6 +40,12 @@ int panel_tc_update_g_groups(PanelTc* h, int pbuf, const PanelGroups& grp, int s
                              cudaStream_t st);
 int panel_tc_update_v_groups(PanelTc* h, int pbuf, const PanelGroups& grp, int sweep, const int* cnt, const int* gflag,
                              cudaStream_t st);
+
+// Chained V update (jacobi_schedule = 2): V <- V Q1 Q2 Q3 for three XOR rounds inside 4-block cosets, one pass over V.
+bool panel_chain_supported(int np);
+int panel_tc_prepare_chain(PanelTc* h, float* const Qc[6]);
+int panel_tc_update_v_chain(PanelTc* h, int slot, const PanelGroups& grp, int sweep, const int* cnt,
+                            const int* const qflag[3], cudaStream_t st);
 
 // Panel tiles (128 rows x 64 output columns, 32 KB in + 32 KB out of HBM traffic) processed since the last reset:
 // [0] G passes, [1] V passes, [2] tiles of the group-local (L2-resident) problems of the spread schedule.
@@ -87,10 +94,14 @@ struct Options {
   int panel_sym = 1;            // 1: G <- Q^T G Q as ONE in-place pass over the upper block triangle with mirrored stores
                                 //    (jacobi_sym.cu: 0.56 n^2 read + n^2 written per round); 0: two passes through the scratch
                                 //    matrix H (jacobi_tc.cu: 2 n^2 read + 2 n^2 written)
-  int jacobi_schedule = 0;      // 1: spread schedule where the block count allows it (power of two >= 8): the rounds of a sweep
-                                //    are the XOR matchings, grouped three at a time into super-rounds that stay inside 4-block
-                                //    (128-column) groups, so G and V are streamed once per super-round instead of once per round;
-                                //    0: circle-method round robin, one panel update per round
+  int jacobi_schedule = 2;      // 2 (default): where the block count is a power of two >= 8, the rounds of a sweep are the XOR
+                                //    matchings grouped three at a time into super-rounds {a, b, a^b} that stay inside 4-block
+                                //    (128-column) cosets; G is updated every round, the three V updates of a super-round run as
+                                //    ONE chained pass over V (panel_vchain_kernel): 41.96 -> 37.26 ms per step;
+                                // 1: spread schedule on the same grouping: group-local problems + one K = 128 pass over G and V
+                                //    per super-round (measured slower, 44.5 ms);
+                                // 0: circle-method round robin, one panel update of G and V per round (also the fallback for
+                                //    other block counts)
 };
 Options& options();
 }  // namespace r3d

@@ -716,13 +716,15 @@ def test_fuser_step_cuda_graph_capture(dev):
                                   {"jacobi_update_tc": 0}, {"gemm_tc": 0}, {"jacobi_overlap_v": 0},
                                   {"jacobi_chunks": 2}, {"panel_sym": 0}, {"jacobi_schedule": 1},
                                   {"jacobi_schedule": 1, "panel_sym": 0},
-                                  {"jacobi_schedule": 1, "jacobi_inner_regs": 0}])
+                                  {"jacobi_schedule": 1, "jacobi_inner_regs": 0}, {"jacobi_schedule": 0},
+                                  {"jacobi_schedule": 0, "jacobi_overlap_v": 0},
+                                  {"jacobi_schedule": 0, "jacobi_inner_regs": 0}])
 def test_alternative_kernel_paths_agree(opts, dev):
     """Every selectable kernel path (merged panel schedule, shared-memory inner solver, SIMT panel update, SIMT GEMMs,
-    no side stream, two chunks, two-pass panel update through H, spread schedule) must reproduce the default path's effective rank and gradient."""
+    no side stream, two chunks, two-pass panel update through H, spread schedule, round-robin schedule) must reproduce the default path's effective rank and gradient."""
     from r3d_b200 import ops, _lib
     defaults = {"panel_merged": 0, "jacobi_inner_regs": 1, "jacobi_update_tc": 1, "gemm_tc": 1, "jacobi_overlap_v": 1,
-                "jacobi_chunks": 1, "jacobi_schedule": 0, "panel_sym": 1}
+                "jacobi_chunks": 1, "jacobi_schedule": 2, "panel_sym": 1}
     x = _spectra("relu", 6, 256, 256, 77)
     ref = EO.erank(x)
     gref = EO.erank_bwd(x, np.ones(6, np.float32))
@@ -738,6 +740,42 @@ def test_alternative_kernel_paths_agree(opts, dev):
     finally:
         for k, v in defaults.items():
             _lib.set_option(k, v)
+
+
+def test_chained_v_update_matches_float64(dev):
+    """panel_vchain_kernel (jacobi_schedule = 2): V <- V Q1 Q2 Q3 for three XOR rounds {a, b, a^b} in ONE pass over V,
+    intermediate products on chip -- against the float64 product with random (non-orthogonal) 64 x 64 factors."""
+    from r3d_b200 import _lib
+    from r3d_b200.ops import _p, _stream
+    L = _lib.lib()
+
+    def xor_pair(mask, t):
+        hb = mask.bit_length() - 1
+        a = ((t >> hb) << (hb + 1)) | (t & ((1 << hb) - 1))
+        return a, a ^ mask
+
+    for (B, npad, ga, gb) in ((1, 256, 1, 2), (2, 256, 3, 5), (3, 512, 1, 6), (2, 512, 9, 14), (5, 512, 15, 4),
+                              (1, 1024, 21, 10)):
+        rng = np.random.default_rng(B * 1000 + npad + ga)
+        nt = npad // 64
+        V = rng.standard_normal((B, npad, npad)).astype(np.float32)
+        Q = rng.standard_normal((3, B, nt, 64, 64)).astype(np.float32) / 8
+        Vd = torch.from_numpy(np.ascontiguousarray(V.reshape(B, npad, npad // 32, 32).transpose(0, 2, 1, 3))).to(dev)
+        Qd = torch.from_numpy(np.ascontiguousarray(Q.transpose(0, 1, 2, 4, 3))).to(dev)
+        scratch = torch.zeros(B * 32 + 3 * B * nt, dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(L.r3d_debug_vchain(_p(Vd), _p(Qd), B, npad, ga, gb, _p(scratch), _stream()))
+        ref = V.astype(np.float64)
+        for k, mask in enumerate((ga, gb, ga ^ gb)):
+            Qf = np.zeros((B, npad, npad))
+            for b in range(B):
+                for t in range(nt):
+                    I, J = xor_pair(mask, t)
+                    ix = np.concatenate([np.arange(I * 32, I * 32 + 32), np.arange(J * 32, J * 32 + 32)])
+                    Qf[b][np.ix_(ix, ix)] = Q[k, b, t]
+            ref = ref @ Qf
+        got = Vd.cpu().numpy().reshape(B, npad // 32, npad, 32).transpose(0, 2, 1, 3).reshape(B, npad, npad)
+        assert np.abs(got - ref).max() <= 1e-5 * np.abs(ref).max(), (B, npad, ga, gb)
 
 
 # ------------------------------------------------------------------ round 2 additions
