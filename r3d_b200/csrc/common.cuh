@@ -86,9 +86,34 @@ struct VecOf<__nv_bfloat16> {
   static constexpr int N = 8;
 };
 
-// streaming (evict-first) loads/stores: every tensor on this path is touched once
+// load_vec / store_vec: streaming (evict-first) accesses for tensors whose LAST use on the path this is (exchange
+// inputs, gradients).  load_vec_keep: default cache policy for a tensor the next kernel reads again -- the score and
+// BatchNorm-statistics passes read X (67 MB at the headline shape, inside the 126 MB L2) right before the exchange does.
 template <typename T, int V>
 __device__ __forceinline__ void load_vec(const T* __restrict__ p, float (&f)[V]);
+template <typename T, int V>
+__device__ __forceinline__ void load_vec_keep(const T* __restrict__ p, float (&f)[V]);
+template <>
+__device__ __forceinline__ void load_vec_keep<float, 4>(const float* __restrict__ p, float (&f)[4]) {
+  float4 v = *reinterpret_cast<const float4*>(p);
+  f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+}
+template <>
+__device__ __forceinline__ void load_vec_keep<float, 1>(const float* __restrict__ p, float (&f)[1]) { f[0] = *p; }
+template <>
+__device__ __forceinline__ void load_vec_keep<__nv_bfloat16, 8>(const __nv_bfloat16* __restrict__ p, float (&f)[8]) {
+  uint4 v = *reinterpret_cast<const uint4*>(p);
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[2 * i] = __uint_as_float(w[i] << 16);
+    f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+template <>
+__device__ __forceinline__ void load_vec_keep<__nv_bfloat16, 1>(const __nv_bfloat16* __restrict__ p, float (&f)[1]) {
+  f[0] = __bfloat162float(*p);
+}
 
 template <>
 __device__ __forceinline__ void load_vec<float, 4>(const float* __restrict__ p, float (&f)[4]) {

@@ -139,7 +139,8 @@ static int sgemm_launch(bool ta, bool tb, const TA* A, const TB* Bm, TC* Cm, int
 // ------------------------------------------------------------------------------
 // Jacobi workspace layout (all per batch):
 //   Gp  (np, np)  padded symmetric working matrix        Vt (np, np) rows -> eigenvectors
-//   Qb  (nt, 64, 64) TRANSPOSED rotation products Q^T of the current round, nt = nb/2 tasks
+//   Qb  (nt, 2, 64, 64) TRANSPOSED rotation products Q^T of the current round, nt = nb/2 tasks, PRE-SPLIT for the 3xTF32
+//       tensor-core updates: plane 0 = hi (round-to-nearest TF32), plane 1 = lo = Q^T - hi (exact), so hi + lo == Q^T
 //   cnt (JMAX_SWEEPS) significant rotations per sweep     qflag (nt) task rotated anything
 //   nu  (1) absolute significance floor
 // ------------------------------------------------------------------------------
@@ -155,6 +156,9 @@ struct JacobiWs {
   float* Qc[6]; int* qflagc[6];
 };
 
+constexpr int QSTR = 2 * JM * JM;        // floats per task in a Q^T buffer: hi plane, lo plane
+__device__ __forceinline__ float q_hi_of(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
+
 static inline int jacobi_np(int64_t n) { return int(((n + JM - 1) / JM) * JM); }
 
 // The Jacobi working matrices (Gp, H, V) are stored column-block-major: [np/32 column blocks][np rows][32],
@@ -166,10 +170,10 @@ __host__ __device__ __forceinline__ int64_t boff(int np, int r, int c) {
 
 static size_t jacobi_ws_bytes(int64_t B, int64_t n) {   // includes slack so that two half-batch carvings fit
   const size_t np = jacobi_np(n), nt = np / JM;
-  size_t f = size_t(B) * (3 * np * np + 2 * nt * JM * JM + 1);
+  size_t f = size_t(B) * (3 * np * np + 2 * nt * QSTR + 1);
   size_t i = size_t(B) * (JMAX_SWEEPS + 2 * nt) + JMAX_SWEEPS + 2 * (2 * kPanelSyncGroups + 8);
   if (np % 128 == 0) {                                  // spread schedule: Sg, Sh, Pv, Pt[2] + flags
-    f += size_t(B) * 6 * np * 128;
+    f += size_t(B) * 8 * np * 128;
     i += size_t(B) * 8 * nt;
   }
   return f * 4 + i * 4 + 4096;
@@ -184,8 +188,8 @@ static JacobiWs jacobi_carve(void* ws, int64_t B, int64_t n) {
   w.Gp = (float*)p; p += size_t(B) * np2 * 4;
   w.Vt = (float*)p; p += size_t(B) * np2 * 4;
   w.H = (float*)p; p += size_t(B) * np2 * 4;
-  w.Qb[0] = (float*)p; p += size_t(B) * w.nt * JM * JM * 4;
-  w.Qb[1] = (float*)p; p += size_t(B) * w.nt * JM * JM * 4;
+  w.Qb[0] = (float*)p; p += size_t(B) * w.nt * QSTR * 4;
+  w.Qb[1] = (float*)p; p += size_t(B) * w.nt * QSTR * 4;
   w.nu = (float*)p; p += size_t(B) * 4;
   w.cnt = (int*)p; p += (size_t(B) * JMAX_SWEEPS + JMAX_SWEEPS) * 4;   // per-matrix counts, then nact[JMAX_SWEEPS]
   w.qflag[0] = (int*)p; p += size_t(B) * w.nt * 4;
@@ -200,14 +204,15 @@ static JacobiWs jacobi_carve(void* ws, int64_t B, int64_t n) {
     w.Pv = (float*)p; p += gsz;
     w.Pt[0] = (float*)p; p += gsz;
     w.Pt[1] = (float*)p; p += gsz;
-    w.Ql[0] = (float*)p; p += gsz / 2;
-    w.Ql[1] = (float*)p; p += gsz / 2;
+    w.Ql[0] = (float*)p; p += gsz;                    // B * ng * 2 local tasks x 2 planes x 64 x 64
+    w.Ql[1] = (float*)p; p += gsz;
     for (int k = 0; k < 3; ++k) { w.lflag[k] = (int*)p; p += size_t(B) * w.nt * 4; }   // B * ng * 2 local tasks = B * nt
     for (int k = 0; k < 2; ++k) { w.gflag[k] = (int*)p; p += size_t(B) * (w.nt / 2) * 4; }
-    // the chained schedule never runs the group-local problems: its six Q^T buffers (B * nt * 64 * 64 floats = half a
-    // group buffer each) live in Sg, Sh, Pv
-    float* const big[3] = {w.Sg, w.Sh, w.Pv};
-    for (int k = 0; k < 6; ++k) w.Qc[k] = big[k >> 1] + (k & 1) * (gsz / 8);
+    // the chained schedule never runs the group-local problems: five of its six Q^T buffers (B * nt * 2 * 64 * 64 floats
+    // = one group buffer each) live in Sg, Sh, Pv, Pt[0], Pt[1]
+    float* const big[5] = {w.Sg, w.Sh, w.Pv, w.Pt[0], w.Pt[1]};
+    for (int k = 0; k < 5; ++k) w.Qc[k] = big[k];
+    w.Qc[5] = (float*)p; p += gsz;
     for (int k = 0; k < 3; ++k) w.qflagc[k] = w.lflag[k];
     for (int k = 3; k < 6; ++k) { w.qflagc[k] = (int*)p; p += size_t(B) * w.nt * 4; }
   }
@@ -381,8 +386,8 @@ __global__ void __launch_bounds__(256, 5) jacobi_inner_kernel(float* __restrict_
       }
     }
     if (!__syncthreads_or(any)) {
-      float* qo = Qb + (int64_t(b) * nt + t) * JM * JM;
-      for (int e = tid; e < JM * JM; e += 256) qo[e] = (e / JM == e % JM) ? 1.f : 0.f;
+      float* qo = Qb + (int64_t(b) * nt + t) * QSTR;
+      for (int e = tid; e < JM * JM; e += 256) { qo[e] = (e / JM == e % JM) ? 1.f : 0.f; qo[JM * JM + e] = 0.f; }
       if (tid == 0) qflag[b * nt + t] = 0;
       return;
     }
@@ -504,8 +509,11 @@ __global__ void __launch_bounds__(256, 5) jacobi_inner_kernel(float* __restrict_
     sig_total = sig_now;
   }
   if (tid == 0 && sig_total > 0) atomicAdd(&cnt[bm * JMAX_SWEEPS + sweep], sig_total);
-  float* qo = Qb + (int64_t(b) * nt + t) * JM * JM;
-  for (int e = tid; e < JM * JM; e += 256) qo[e] = dsc[e / JM] * Qt[e / JM][e % JM];   // Q^T = D Q~^T, row-major
+  float* qo = Qb + (int64_t(b) * nt + t) * QSTR;
+  for (int e = tid; e < JM * JM; e += 256) {                                            // Q^T = D Q~^T, row-major, hi | lo
+    const float x = dsc[e / JM] * Qt[e / JM][e % JM], h = q_hi_of(x);
+    qo[e] = h; qo[JM * JM + e] = x - h;
+  }
   if (tid == 0) qflag[b * nt + t] = (s_tot > 0);
 }
 
@@ -630,11 +638,12 @@ __global__ void __launch_bounds__(256, 4) jacobi_inner_cross_kernel(float* __res
         any |= x * x > tol2 * fabsf(S[a][a] * S[v][v]);
       }
     if (!__syncthreads_or(any)) {
-      float4* qo = reinterpret_cast<float4*>(Qb + (int64_t(b) * nt + t) * JM * JM);
+      float4* qo = reinterpret_cast<float4*>(Qb + (int64_t(b) * nt + t) * QSTR);
 #pragma unroll
       for (int u = 0; u < JM * JM / 4 / 256; ++u) {
         const int e = tid + u * 256, i = e / (JM / 4), j4 = (e % (JM / 4)) * 4;
         qo[e] = make_float4(i == j4 ? 1.f : 0.f, i == j4 + 1 ? 1.f : 0.f, i == j4 + 2 ? 1.f : 0.f, i == j4 + 3 ? 1.f : 0.f);
+        qo[JM * JM / 4 + e] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
       if (tid == 0) qflag[b * nt + t] = 0;
       return;
@@ -767,13 +776,16 @@ __global__ void __launch_bounds__(256, 4) jacobi_inner_cross_kernel(float* __res
   }
   __syncthreads();
   if (tid == 0 && s_sig > 0) atomicAdd(&cnt[bm * JMAX_SWEEPS + sweep], s_sig);
-  float4* qo = reinterpret_cast<float4*>(Qb + (int64_t(b) * nt + t) * JM * JM);
+  float4* qo = reinterpret_cast<float4*>(Qb + (int64_t(b) * nt + t) * QSTR);
 #pragma unroll
   for (int u = 0; u < JM * JM / 4 / 256; ++u) {
     const int e = tid + u * 256, i = e / (JM / 4), j4 = (e % (JM / 4)) * 4;
     const float d = dsc[i];
     const float4 q4 = *reinterpret_cast<const float4*>(&S[i][j4]);
-    qo[e] = make_float4(d * q4.x, d * q4.y, d * q4.z, d * q4.w);
+    const float4 x = make_float4(d * q4.x, d * q4.y, d * q4.z, d * q4.w);
+    const float4 h = make_float4(q_hi_of(x.x), q_hi_of(x.y), q_hi_of(x.z), q_hi_of(x.w));
+    qo[e] = h;
+    qo[JM * JM / 4 + e] = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
   }
   if (tid == 0) qflag[b * nt + t] = (s_tot > 0);
 }
@@ -807,14 +819,14 @@ __global__ void __launch_bounds__(256) jacobi_update_kernel(float* __restrict__ 
   rr_pair(nb, round, a, Ia, Ja);
   rr_pair(nb, round, c, Ic, Jc);
   float* base = (two_sided ? Gp : Vt) + int64_t(b) * np * np;
-  const float* qa = Qb + (int64_t(b) * nt + a) * JM * JM;
-  const float* qc = Qb + (int64_t(b) * nt + c) * JM * JM;
+  const float* qa = Qb + (int64_t(b) * nt + a) * QSTR;          // hi plane, then lo plane: hi + lo is exact
+  const float* qc = Qb + (int64_t(b) * nt + c) * QSTR;
   for (int e = tid; e < JM * JM; e += 256) {
     const int i = e / JM, j = e % JM;
     const int gj = two_sided ? blk_row(Ic, Jc, j) : slab * JM + j;
     Tm[i][j] = base[boff(np, blk_row(Ia, Ja, i), gj)];
-    Qa[j][i] = qa[e];                 // Qb holds Q^T: Qa[k][i] = Q[k][i] = qa[i*64+k]
-    if (two_sided) Qc[j][i] = qc[e];
+    Qa[j][i] = qa[e] + qa[JM * JM + e];   // Qb holds Q^T: Qa[k][i] = Q[k][i] = qa[i*64+k]
+    if (two_sided) Qc[j][i] = qc[e] + qc[JM * JM + e];
   }
   __syncthreads();
   const int ti = tid / 16, tj = tid % 16;
@@ -1206,6 +1218,22 @@ static inline void side(int64_t T, int64_t C, int64_t& n, int64_t& m, bool& tsid
   m = tside ? C : T;
 }
 
+// fp32 Q^T (tasks, 64, 64) -> the pre-split layout (tasks, 2, 64, 64) the inner solver emits (test hooks only)
+__global__ void split_q_kernel(const float* __restrict__ q, float* __restrict__ out, int64_t total) {
+  for (int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; e < total; e += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t task = e / (JM * JM), r = e % (JM * JM);
+    const float x = q[e], h = q_hi_of(x);
+    out[task * QSTR + r] = h;
+    out[task * QSTR + JM * JM + r] = x - h;
+  }
+}
+static int split_q(const float* q, int64_t tasks, float** out, cudaStream_t st) {
+  R3D_CUDA(cudaMallocAsync((void**)out, size_t(tasks) * QSTR * sizeof(float), st));
+  split_q_kernel<<<(unsigned)std::min<int64_t>((tasks * JM * JM + 255) / 256, 4096), 256, 0, st>>>(q, *out, tasks * JM * JM);
+  R3D_LAUNCH_CHECK();
+  return 0;
+}
+
 // Debug/test hook: one tensor-core panel-update round on caller-provided buffers (all (B, np, np) fp32,
 // Qb (B, np/64, 64, 64)); every task is applied (qflag = 1, nothing converged).
 extern "C" int r3d_debug_panel_round(float* G, float* H, float* V, const float* Qb, int64_t B, int np, int round,
@@ -1219,14 +1247,21 @@ extern "C" int r3d_debug_panel_round(float* G, float* H, float* V, const float* 
   std::vector<int> ones(B * nt, 1);
   R3D_CUDA(cudaMemcpyAsync(qflag, ones.data(), sizeof(int) * B * nt, cudaMemcpyHostToDevice, st));
   R3D_CUDA(cudaStreamSynchronize(st));
+  float* qs = nullptr;
+  if (int e = split_q(Qb, B * nt, &qs, st)) return e;
   PanelTc ptc;
-  if (int e = panel_tc_prepare(&ptc, G, H, V, Qb, Qb, B, np)) return e;
-  if (int e = panel_tc_update_v(&ptc, 0, round, 0, cnt, qflag, st)) return e;
-  if (options().panel_sym != 0 && panel_sym_supported(np)) {       // one in-place pass; H is not touched
-    if (int e = panel_sym_prepare(&ptc)) return e;
-    return panel_sym_update_g(&ptc, 0, round, 0, cnt, qflag, st);
+  int rc = panel_tc_prepare(&ptc, G, H, V, qs, qs, B, np);
+  if (!rc) rc = panel_tc_update_v(&ptc, 0, round, 0, cnt, qflag, st);
+  if (!rc) {
+    if (options().panel_sym != 0 && panel_sym_supported(np)) {     // one in-place pass; H is not touched
+      rc = panel_sym_prepare(&ptc);
+      if (!rc) rc = panel_sym_update_g(&ptc, 0, round, 0, cnt, qflag, st);
+    } else {
+      rc = panel_tc_update_g(&ptc, 0, round, 0, cnt, qflag, st);
+    }
   }
-  return panel_tc_update_g(&ptc, 0, round, 0, cnt, qflag, st);
+  cudaFreeAsync(qs, st);
+  return rc;
 }
 
 // Debug/test hook of the chained V update: V <- V Q1 Q2 Q3 for the XOR rounds with masks ga, gb, ga ^ gb.  Q3 holds the
@@ -1242,13 +1277,17 @@ extern "C" int r3d_debug_vchain(float* V, float* Q3, int64_t B, int np, int ga, 
   std::vector<int> ones(3 * B * nt, 1);
   R3D_CUDA(cudaMemcpyAsync(qflag, ones.data(), sizeof(int) * 3 * B * nt, cudaMemcpyHostToDevice, st));
   R3D_CUDA(cudaStreamSynchronize(st));
+  float* qs = nullptr;
+  if (int e = split_q(Q3, 3 * B * nt, &qs, st)) return e;
   PanelTc ptc;
-  if (int e = panel_tc_prepare(&ptc, V, nullptr, V, Q3, Q3, B, np)) return e;
-  const size_t qsz = size_t(B) * nt * JM * JM;
-  float* qc[6] = {Q3, Q3 + qsz, Q3 + 2 * qsz, Q3, Q3 + qsz, Q3 + 2 * qsz};
-  if (int e = panel_tc_prepare_chain(&ptc, qc)) return e;
+  int rc = panel_tc_prepare(&ptc, V, nullptr, V, qs, qs, B, np);
+  const size_t qsz = size_t(B) * nt * QSTR;
+  float* qc[6] = {qs, qs + qsz, qs + 2 * qsz, qs, qs + qsz, qs + 2 * qsz};
+  if (!rc) rc = panel_tc_prepare_chain(&ptc, qc);
   const int* fl[3] = {qflag, qflag + B * nt, qflag + 2 * B * nt};
-  return panel_tc_update_v_chain(&ptc, 0, groups_of(SuperRound{ga, gb}), 0, cnt, fl, st);
+  if (!rc) rc = panel_tc_update_v_chain(&ptc, 0, groups_of(SuperRound{ga, gb}), 0, cnt, fl, st);
+  cudaFreeAsync(qs, st);
+  return rc;
 }
 
 extern "C" int r3d_panel_tiles(uint64_t* out3, int reset) {

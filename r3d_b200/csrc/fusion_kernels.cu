@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(256) score_partial_kernel(const T* __restrict_
       float a[8][V];
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
-        if (r + u * TY < r1) load_vec<T, V>(p + (r + u * TY) * C, a[u]);
+        if (r + u * TY < r1) load_vec_keep<T, V>(p + (r + u * TY) * C, a[u]);
         else {
 #pragma unroll
           for (int i = 0; i < V; ++i) a[u][i] = 0.f;
@@ -548,7 +548,7 @@ __global__ void __launch_bounds__(256) bn_partial_kernel(const T* __restrict__ r
     const T* p = x + cv * V;
     for (int64_t r = r0 + ty; r < r1; r += TY) {
       float a[V];
-      load_vec<T, V>(p + r * C, a);
+      load_vec_keep<T, V>(p + r * C, a);
       n += 1.f;
       const float inv = 1.f / n;
 #pragma unroll

@@ -187,8 +187,12 @@ __global__ void __maxnreg__(72) panel_sym_kernel(const __grid_constant__ CUtenso
   uint8_t* smem = (uint8_t*)((uintptr_t(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stg_base = smem + NSTAGE * STAGE;
   uint64_t* raw_full = (uint64_t*)(smem + NSTAGE * STAGE + 4 * STG_WARP);   // TMA -> splitters
-  uint64_t* split_done = raw_full + NSTAGE;      // splitters (128) + one extra arrival -> MMA
-  uint64_t* smem_empty = split_done + NSTAGE;    // MMA commit -> producer / transposer
+  uint64_t* split_done = raw_full + NSTAGE;      // step 1: 128 splitters (A slab split) -> MMA
+  uint64_t* tr_done = split_done + NSTAGE;       // step 2: the use's transposer warp (A slab written) -> MMA
+  uint64_t* q_full = tr_done + NSTAGE;           // step 2: TMA (pre-split Q^T planes) -> MMA.  Its own barrier: every
+                                                 // waiter of a barrier must see each of its phases (a waiter that skips
+                                                 // phases can match a stale phase of the same parity)
+  uint64_t* smem_empty = q_full + NSTAGE;        // MMA commit -> producer / transposer
   uint64_t* w_full = smem_empty + NSTAGE;        // MMA commit (step 1 done) -> transposers
   uint64_t* w_empty = w_full + 1;                // transposers (4 warps) -> MMA
   uint64_t* d_full = w_empty + 1;                // [2] MMA commit (step 2 of half h done) -> epilogue
@@ -205,7 +209,10 @@ __global__ void __maxnreg__(72) panel_sym_kernel(const __grid_constant__ CUtenso
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < NSTAGE; ++s) { bar_init(&raw_full[s], 1); bar_init(&split_done[s], 129); bar_init(&smem_empty[s], 1); }
+    for (int s = 0; s < NSTAGE; ++s) {
+      bar_init(&raw_full[s], 1); bar_init(&split_done[s], 128); bar_init(&tr_done[s], 1); bar_init(&smem_empty[s], 1);
+      bar_init(&q_full[s], 1);
+    }
     bar_init(w_full, 1); bar_init(w_empty, 4);
     for (int h = 0; h < 2; ++h) { bar_init(&d_full[h], 1); bar_init(&d_empty[h], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -240,18 +247,23 @@ __global__ void __maxnreg__(72) panel_sym_kernel(const __grid_constant__ CUtenso
           const uint32_t ph = (it / NSTAGE) & 1;
           bar_wait(&smem_empty[s], ph ^ 1);
           uint8_t* st = smem + s * STAGE;
+          // Q^T arrives pre-split from the inner solver: hi plane at row 2 * task * 64, lo plane 64 rows below
+          int qrow, qcol;
+          uint64_t* fb = u < 4 ? &raw_full[s] : &q_full[s];
           if (u < 4) {
-            bar_expect_tx(&raw_full[s], A_RAW + Q_RAW);
+            bar_expect_tx(fb, A_RAW + 2 * Q_RAW);
             // K slab u of step 1 = column block cb[u]; rows = the four 32-row blocks of (a1, a2): contiguous 4 KB each
 #pragma unroll
             for (int rg = 0; rg < 4; ++rg)
-              tma_3d(st + rg * (PB * PB * 4), &map_g32, &raw_full[s], 0, rb[rg] * PB, ti.b * nb + cb[u]);
-            tma_2d(st + 2 * A_RAW, &map_q, &raw_full[s], (u & 1) * PB, (ti.b * nt + 2 * ti.pc + (u >> 1)) * PM);
+              tma_3d(st + rg * (PB * PB * 4), &map_g32, fb, 0, rb[rg] * PB, ti.b * nb + cb[u]);
+            qcol = (u & 1) * PB; qrow = (ti.b * nt + 2 * ti.pc + (u >> 1)) * 2 * PM;
           } else {
-            bar_expect_tx(&raw_full[s], Q_RAW);
+            bar_expect_tx(fb, 2 * Q_RAW);
             const int h = (u - 4) >> 1, ks = (u - 4) & 1;
-            tma_2d(st + 2 * A_RAW, &map_q, &raw_full[s], ks * PB, (ti.b * nt + 2 * ti.pa + h) * PM);
+            qcol = ks * PB; qrow = (ti.b * nt + 2 * ti.pa + h) * 2 * PM;
           }
+          tma_2d(st + 2 * A_RAW, &map_q, fb, qcol, qrow);
+          tma_2d(st + 2 * A_RAW + Q_RAW, &map_q, fb, qcol, qrow + PM);
         }
         units += (ti.pa == ti.pc) ? 2 : 3;
       }
@@ -281,7 +293,13 @@ __global__ void __maxnreg__(72) panel_sym_kernel(const __grid_constant__ CUtenso
               asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             }
           }
-          bar_wait(&split_done[s], ph);
+          // per super tile every stage sees 2 uses of step 1 and 2 of step 2 (8 uses, 2 stages): the phase parities of
+          // the two hand-over barriers follow from the use index alone
+          if (u < 4) bar_wait(&split_done[s], (u >> 1) & 1);            // A split (the Q planes landed before)
+          else {
+            bar_wait(&q_full[s], ((u - 4) >> 1) & 1);                   // pre-split Q^T planes landed (TMA)
+            bar_wait(&tr_done[s], ((u - 4) >> 1) & 1);                  // A slab written by the transposer warp
+          }
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t a_hi = s_u32(smem + s * STAGE), a_lo = a_hi + A_RAW;
           const uint32_t q_hi = a_hi + 2 * A_RAW, q_lo = q_hi + Q_RAW;
@@ -307,45 +325,29 @@ __global__ void __maxnreg__(72) panel_sym_kernel(const __grid_constant__ CUtenso
   } else if (warp >= 2 && warp < 6) {
     // ===================== splitters =====================
     const int t = threadIdx.x - 64;
-    int it = 0;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
       const SymTile ti = decode_sym(tile, nst, npg, nt, sweep, bdiv, cnt, qflag);
       if (!ti.run) continue;
+      // only the four A slabs of step 1 need splitting (Q^T arrives pre-split; step 2 gets A from the transposers)
 #pragma unroll 1
-      for (int u = 0; u < USES; ++u, ++it) {
-        const int s = it % NSTAGE;
-        const uint32_t ph = (it / NSTAGE) & 1;
-        bar_wait(&raw_full[s], ph);
+      for (int u = 0; u < 4; ++u) {
+        const int s = u % NSTAGE;                  // a super tile starts on stage 0 (8 uses per tile)
+        bar_wait(&raw_full[s], (u >> 1) & 1);      // raw_full completes twice per super tile and stage
         uint8_t* st = smem + s * STAGE;
-        if (u < 4) {
-          float4* a_hi = reinterpret_cast<float4*>(st);
-          float4* a_lo = reinterpret_cast<float4*>(st + A_RAW);
+        float4* a_hi = reinterpret_cast<float4*>(st);
+        float4* a_lo = reinterpret_cast<float4*>(st + A_RAW);
 #pragma unroll 4
-          for (int e = t; e < A_RAW / 16; e += 128) {
-            const float4 x = a_hi[e];
-            float4 h, l;
-            h.x = tf32_rn(x.x); l.x = x.x - h.x;
-            h.y = tf32_rn(x.y); l.y = x.y - h.y;
-            h.z = tf32_rn(x.z); l.z = x.z - h.z;
-            h.w = tf32_rn(x.w); l.w = x.w - h.w;
-            a_hi[e] = h; a_lo[e] = l;
-          }
-        }
-        float4* q_hi = reinterpret_cast<float4*>(st + 2 * A_RAW);
-        float4* q_lo = reinterpret_cast<float4*>(st + 2 * A_RAW + Q_RAW);
-#pragma unroll 4
-        for (int e = t; e < Q_RAW / 16; e += 128) {
-          const float4 x = q_hi[e];
+        for (int e = t; e < A_RAW / 16; e += 128) {
+          const float4 x = a_hi[e];
           float4 h, l;
           h.x = tf32_rn(x.x); l.x = x.x - h.x;
           h.y = tf32_rn(x.y); l.y = x.y - h.y;
           h.z = tf32_rn(x.z); l.z = x.z - h.z;
           h.w = tf32_rn(x.w); l.w = x.w - h.w;
-          q_hi[e] = h; q_lo[e] = l;
+          a_hi[e] = h; a_lo[e] = l;
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         bar_arrive(&split_done[s]);
-        if (u < 4 && t == 0) bar_arrive(&split_done[s]);   // step 1 has no transposer: the 129th arrival
       }
     }
   } else if (warp >= 6) {
@@ -390,7 +392,7 @@ __global__ void __maxnreg__(72) panel_sym_kernel(const __grid_constant__ CUtenso
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
-        if (lane == 0) { bar_arrive(w_empty); bar_arrive(&split_done[s]); }
+        if (lane == 0) { bar_arrive(w_empty); bar_arrive(&tr_done[s]); }
       }
       // ---- D_a -> global
       float* out = G + int64_t(ti.b) * np * np;

@@ -337,12 +337,18 @@ __global__ void __maxnreg__(72) panel_update_tc_kernel(const __grid_constant__ C
           const uint32_t ph = (it / NSTAGE) & 1;
           bar_wait(&smem_empty[s], ph ^ 1);
           uint8_t* st = smem + s * STAGE;
-          bar_expect_tx(&raw_full[s], A_RAW + Q_RAW);
+          bar_expect_tx(&raw_full[s], A_RAW + (SL == 2 ? 2 : 1) * Q_RAW);
           // panel slab: rows [mt*128, +128) of column block I (slab 0) or J (slab 1): 16 KB contiguous in HBM
           tma_3d(st, mp, &raw_full[s], 0, ti.mt * TM, mb * nb + blk[slab]);
-          // Q_c^T: 64 rows (j) x the 32 k-columns of this slab (group mode: rows [64 h, 64 h + 64) of the group's
-          // 128 x 128 P^T, so qrow = (b * nt + c) * 64 holds there too)
-          tma_2d(st + 2 * A_RAW, &map_q, &raw_full[s], slab * PB, qrow);
+          // Q_c^T: 64 rows (j) x the 32 k-columns of this slab.  Pair mode: the inner solver wrote it pre-split (hi plane,
+          // lo plane), both land where the MMA reads them.  Group mode: rows [64 h, 64 h + 64) of the group's 128 x 128
+          // P^T (fp32, split in shared memory), qrow = (b * nt + c) * 64.
+          if (SL == 2) {
+            tma_2d(st + 2 * A_RAW, &map_q, &raw_full[s], slab * PB, 2 * qrow);
+            tma_2d(st + 2 * A_RAW + Q_RAW, &map_q, &raw_full[s], slab * PB, 2 * qrow + PM);
+          } else {
+            tma_2d(st + 2 * A_RAW, &map_q, &raw_full[s], slab * PB, qrow);
+          }
         }
         ++ntiles;
       }
@@ -417,15 +423,17 @@ __global__ void __maxnreg__(72) panel_update_tc_kernel(const __grid_constant__ C
             h.w = tf32_rn(x.w); l.w = x.w - h.w;
             a_hi[e] = h; a_lo[e] = l;
           }
+          if (SL != 2) {
 #pragma unroll 4
-          for (int e = t; e < Q_RAW / 16; e += 128) {
-            const float4 x = q_hi[e];
-            float4 h, l;
-            h.x = tf32_rn(x.x); l.x = x.x - h.x;
-            h.y = tf32_rn(x.y); l.y = x.y - h.y;
-            h.z = tf32_rn(x.z); l.z = x.z - h.z;
-            h.w = tf32_rn(x.w); l.w = x.w - h.w;
-            q_hi[e] = h; q_lo[e] = l;
+            for (int e = t; e < Q_RAW / 16; e += 128) {
+              const float4 x = q_hi[e];
+              float4 h, l;
+              h.x = tf32_rn(x.x); l.x = x.x - h.x;
+              h.y = tf32_rn(x.y); l.y = x.y - h.y;
+              h.z = tf32_rn(x.z); l.z = x.z - h.z;
+              h.w = tf32_rn(x.w); l.w = x.w - h.w;
+              q_hi[e] = h; q_lo[e] = l;
+            }
           }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to UMMA
@@ -621,8 +629,12 @@ __global__ void __maxnreg__(72) panel_vchain_kernel(const __grid_constant__ CUte
   uint8_t* smem = (uint8_t*)((uintptr_t(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stg_base = smem + NSTAGE * STAGE;
   uint64_t* raw_full = (uint64_t*)(smem + NSTAGE * STAGE + 4 * STG_WARP);   // TMA -> splitters
-  uint64_t* split_done = raw_full + NSTAGE;      // 128 splitters + 4 (drainer warps, or splitters 0-3 in round 0) -> MMA
-  uint64_t* smem_empty = split_done + NSTAGE;    // MMA commit -> producer / drainers
+  uint64_t* split_done = raw_full + NSTAGE;      // round 0: 128 splitters (A slab split) -> MMA
+  uint64_t* drain_done = split_done + NSTAGE;    // rounds 1-2: 4 drainer warps (A slab written) -> MMA
+  uint64_t* q_full = drain_done + NSTAGE;        // rounds 1-2: TMA (pre-split Q^T planes) -> MMA.  A barrier of its own:
+                                                 // every waiter of a barrier must see each of its phases (a waiter that
+                                                 // skips phases can match a stale phase of the same parity)
+  uint64_t* smem_empty = q_full + NSTAGE;        // MMA commit -> producer / drainers
   uint64_t* acc_full = smem_empty + NSTAGE;      // [2] MMA commit (a round is complete) -> drainers / epilogue
   uint64_t* acc_empty = acc_full + 2;            // [2] drainers / epilogue (4 warps) -> MMA
   uint32_t* tmem_slot = (uint32_t*)(acc_empty + 2);
@@ -639,7 +651,10 @@ __global__ void __maxnreg__(72) panel_vchain_kernel(const __grid_constant__ CUte
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q2) : "memory");
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < NSTAGE; ++s) { bar_init(&raw_full[s], 1); bar_init(&split_done[s], 132); bar_init(&smem_empty[s], 1); }
+    for (int s = 0; s < NSTAGE; ++s) {
+      bar_init(&raw_full[s], 1); bar_init(&split_done[s], 128); bar_init(&drain_done[s], 4); bar_init(&smem_empty[s], 1);
+      bar_init(&q_full[s], 1);
+    }
     for (int s = 0; s < 2; ++s) { bar_init(&acc_full[s], 1); bar_init(&acc_empty[s], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -669,15 +684,17 @@ __global__ void __maxnreg__(72) panel_vchain_kernel(const __grid_constant__ CUte
           bar_wait(&smem_empty[s], ph ^ 1);
           uint8_t* st = smem + s * STAGE;
           const CUtensorMap* mq = k == 0 ? &map_q0 : (k == 1 ? &map_q1 : &map_q2);
-          const int qrow = (ti.b * nt + chain_task(ti.cp, k, p)) * PM;
+          const int qrow = (ti.b * nt + chain_task(ti.cp, k, p)) * 2 * PM;      // hi plane; lo plane 64 rows below
+          uint64_t* fb = k == 0 ? &raw_full[s] : &q_full[s];
           if (k == 0) {
-            bar_expect_tx(&raw_full[s], A_RAW + Q_RAW);
+            bar_expect_tx(fb, A_RAW + 2 * Q_RAW);
             const int cb = chain_blk(cj, ti.cp.x, chain_sig(ti.cp, 0, 2 * p + sl));
-            tma_3d(st, &map_v, &raw_full[s], 0, ti.mt * TM, ti.b * nb + cb);
+            tma_3d(st, &map_v, fb, 0, ti.mt * TM, ti.b * nb + cb);
           } else {
-            bar_expect_tx(&raw_full[s], Q_RAW);
+            bar_expect_tx(fb, 2 * Q_RAW);
           }
-          tma_2d(st + 2 * A_RAW, mq, &raw_full[s], sl * PB, qrow);
+          tma_2d(st + 2 * A_RAW, mq, fb, sl * PB, qrow);
+          tma_2d(st + 2 * A_RAW + Q_RAW, mq, fb, sl * PB, qrow + PM);
         }
         ++ntiles;
       }
@@ -701,7 +718,13 @@ __global__ void __maxnreg__(72) panel_vchain_kernel(const __grid_constant__ CUte
           for (int ps = 0; ps < 4; ++ps, ++it) {
             const int s = it % NSTAGE;
             const uint32_t ph = (it / NSTAGE) & 1;
-            bar_wait(&split_done[s], ph);
+            // per tile every stage sees 2 uses of round 0 and 4 of rounds 1-2 (12 uses, 2 stages): the phase parities of
+            // the two hand-over barriers follow from the use index alone
+            if (k == 0) bar_wait(&split_done[s], (ps >> 1) & 1);                 // A split (the Q planes landed before)
+            else {
+              bar_wait(&q_full[s], ((4 * (k - 1) + ps) >> 1) & 1);               // pre-split Q^T planes landed (TMA)
+              bar_wait(&drain_done[s], ((4 * (k - 1) + ps) >> 1) & 1);           // A slab written by the drainers
+            }
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t d = tmem_base + buf * 128 + (ps >> 1) * PM;
             const uint32_t a_hi = s_u32(smem + s * STAGE), a_lo = a_hi + A_RAW;
@@ -727,45 +750,29 @@ __global__ void __maxnreg__(72) panel_vchain_kernel(const __grid_constant__ CUte
   } else if (warp >= 2 && warp < 6) {
     // ===================== splitters =====================
     const int t = threadIdx.x - 64;
-    int it = 0;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
       const ChainTile ti = decode_chain(tile, ng, nt, mtiles, sweep, cnt, cj);
       if (!ti.run) continue;
+      // only the four A slabs of round 0 need splitting (Q^T arrives pre-split; rounds 1-2 get A from the drainers)
 #pragma unroll 1
-      for (int u = 0; u < CUSES; ++u, ++it) {
-        const int s = it % NSTAGE;
-        const uint32_t ph = (it / NSTAGE) & 1;
-        bar_wait(&raw_full[s], ph);
+      for (int u = 0; u < 4; ++u) {
+        const int s = u % NSTAGE;                  // a tile starts on stage 0 (12 uses per tile)
+        bar_wait(&raw_full[s], (u >> 1) & 1);      // raw_full completes twice per tile and stage
         uint8_t* st = smem + s * STAGE;
-        if (u < 4) {
-          float4* a_hi = reinterpret_cast<float4*>(st);
-          float4* a_lo = reinterpret_cast<float4*>(st + A_RAW);
+        float4* a_hi = reinterpret_cast<float4*>(st);
+        float4* a_lo = reinterpret_cast<float4*>(st + A_RAW);
 #pragma unroll 4
-          for (int e = t; e < A_RAW / 16; e += 128) {
-            const float4 x = a_hi[e];
-            float4 h, l;
-            h.x = tf32_rn(x.x); l.x = x.x - h.x;
-            h.y = tf32_rn(x.y); l.y = x.y - h.y;
-            h.z = tf32_rn(x.z); l.z = x.z - h.z;
-            h.w = tf32_rn(x.w); l.w = x.w - h.w;
-            a_hi[e] = h; a_lo[e] = l;
-          }
-        }
-        float4* q_hi = reinterpret_cast<float4*>(st + 2 * A_RAW);
-        float4* q_lo = reinterpret_cast<float4*>(st + 2 * A_RAW + Q_RAW);
-#pragma unroll 4
-        for (int e = t; e < Q_RAW / 16; e += 128) {
-          const float4 x = q_hi[e];
+        for (int e = t; e < A_RAW / 16; e += 128) {
+          const float4 x = a_hi[e];
           float4 h, l;
           h.x = tf32_rn(x.x); l.x = x.x - h.x;
           h.y = tf32_rn(x.y); l.y = x.y - h.y;
           h.z = tf32_rn(x.z); l.z = x.z - h.z;
           h.w = tf32_rn(x.w); l.w = x.w - h.w;
-          q_hi[e] = h; q_lo[e] = l;
+          a_hi[e] = h; a_lo[e] = l;
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         bar_arrive(&split_done[s]);
-        if (u < 4 && t < 4) bar_arrive(&split_done[s]);          // round 0 has no drainers: arrivals 129-132
       }
     }
   } else if (warp >= 6) {
@@ -810,7 +817,7 @@ __global__ void __maxnreg__(72) panel_vchain_kernel(const __grid_constant__ CUte
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
-          if (lane == 0) bar_arrive(&split_done[s]);
+          if (lane == 0) bar_arrive(&drain_done[s]);
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
@@ -899,8 +906,9 @@ int panel_tc_prepare(PanelTc* h, float* G, float* H, float* V, const float* Qb0,
   if (int e = make_map_panel(&h->map_g, G, B, np)) return e;
   if (H != nullptr) { if (int e = make_map_panel(&h->map_h, H, B, np)) return e; }
   if (int e = make_map_panel(&h->map_v, V, B, np)) return e;
-  if (int e = make_map_q(&h->map_q[0], Qb0, B * h->nt * PM)) return e;
-  if (int e = make_map_q(&h->map_q[1], Qb1, B * h->nt * PM)) return e;
+  // Q^T buffers are pre-split by the inner solver: per task a hi plane and a lo plane of 64 rows each
+  if (int e = make_map_q(&h->map_q[0], Qb0, B * h->nt * 2 * PM)) return e;
+  if (int e = make_map_q(&h->map_q[1], Qb1, B * h->nt * 2 * PM)) return e;
   static bool attr_done[kMaxDevices] = {};
   if (per_device_once(attr_done)) {
     R3D_CUDA(cudaFuncSetAttribute(panel_update_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
@@ -920,7 +928,7 @@ int panel_tc_prepare_groups(PanelTc* h, const float* Pt0, const float* Pt1) {
 // Q^T buffers of the chained schedule: two slots of three rounds each
 int panel_tc_prepare_chain(PanelTc* h, float* const Qc[6]) {
   for (int i = 0; i < 6; ++i)
-    if (int e = make_map_q(&h->map_qc[i], Qc[i], h->B * h->nt * PM)) return e;
+    if (int e = make_map_q(&h->map_qc[i], Qc[i], h->B * h->nt * 2 * PM)) return e;
   return 0;
 }
 

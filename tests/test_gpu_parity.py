@@ -742,6 +742,66 @@ def test_alternative_kernel_paths_agree(opts, dev):
             _lib.set_option(k, v)
 
 
+def test_panel_round_matches_float64(dev):
+    """One Jacobi round on the tensor-core panel kernels against float64: G <- Q^T G Q (panel_sym_kernel, one in-place
+    pass) and V <- V Q (panel_update_tc_kernel), random 64 x 64 factors, circle-method and XOR pairings; repeated with a
+    capped grid so that every CTA walks several tiles (the mbarrier phases carry over from tile to tile)."""
+    from r3d_b200 import _lib
+    from r3d_b200.ops import _p, _stream
+    L = _lib.lib()
+
+    def pair(m, r, t):
+        if r < 0:
+            mask = -r
+            hb = mask.bit_length() - 1
+            a = ((t >> hb) << (hb + 1)) | (t & ((1 << hb) - 1))
+            return a, a ^ mask
+        if m == 2:
+            return 0, 1
+        x, y = (r, m - 1) if t == 0 else ((r + t) % (m - 1), (r - t + (m - 1)) % (m - 1))
+        return min(x, y), max(x, y)
+
+    for (B, npad, rnd) in ((1, 128, 0), (2, 256, 2), (3, 512, 4), (5, 384, 3), (2, 512, -5), (3, 256, -3)):
+        rng = np.random.default_rng(abs(rnd) * 100 + npad + B)
+        nb, nt = npad // 32, npad // 64
+        A = rng.standard_normal((B, npad, npad)).astype(np.float32)
+        G = (A + A.transpose(0, 2, 1)) / 2
+        V = rng.standard_normal((B, npad, npad)).astype(np.float32)
+        Q = rng.standard_normal((B, nt, 64, 64)).astype(np.float32) / 8
+
+        def blocked(M):
+            return torch.from_numpy(np.ascontiguousarray(M.reshape(B, npad, npad // 32, 32).transpose(0, 2, 1, 3))).to(dev)
+
+        def plain(t):
+            return t.cpu().numpy().reshape(B, npad // 32, npad, 32).transpose(0, 2, 1, 3).reshape(B, npad, npad)
+
+        Qd = torch.from_numpy(np.ascontiguousarray(Q.transpose(0, 1, 3, 2))).to(dev)
+        Qf = np.zeros((B, npad, npad))
+        for b in range(B):
+            for t in range(nt):
+                I, J = pair(nb, rnd, t)
+                ix = np.concatenate([np.arange(I * 32, I * 32 + 32), np.arange(J * 32, J * 32 + 32)])
+                Qf[b][np.ix_(ix, ix)] = Q[b, t]
+        Gref = Qf.transpose(0, 2, 1) @ G.astype(np.float64) @ Qf
+        Vref = V.astype(np.float64) @ Qf
+        outs = []
+        for cap in (0, 3):
+            Gd, Vd = blocked(G), blocked(V)
+            Hd = torch.zeros_like(Gd)
+            scratch = torch.zeros(B * 32 + B * nt, dtype=torch.int32, device=dev)
+            try:
+                _lib.set_option("panel_grid_cap", cap)
+                with torch.cuda.device(dev):
+                    _lib.check(L.r3d_debug_panel_round(_p(Gd), _p(Hd), _p(Vd), _p(Qd), B, npad, rnd, _p(scratch), _stream()))
+            finally:
+                _lib.set_option("panel_grid_cap", 0)
+            g, v = plain(Gd), plain(Vd)
+            assert np.abs(g - Gref).max() <= 1e-5 * np.abs(Gref).max(), (B, npad, rnd, cap)
+            assert np.abs(v - Vref).max() <= 1e-5 * np.abs(Vref).max(), (B, npad, rnd, cap)
+            outs.append((Gd, Vd))
+        assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
 def test_chained_v_update_matches_float64(dev):
     """panel_vchain_kernel (jacobi_schedule = 2): V <- V Q1 Q2 Q3 for three XOR rounds {a, b, a^b} in ONE pass over V,
     intermediate products on chip -- against the float64 product with random (non-orthogonal) 64 x 64 factors."""
@@ -763,8 +823,16 @@ def test_chained_v_update_matches_float64(dev):
         Vd = torch.from_numpy(np.ascontiguousarray(V.reshape(B, npad, npad // 32, 32).transpose(0, 2, 1, 3))).to(dev)
         Qd = torch.from_numpy(np.ascontiguousarray(Q.transpose(0, 1, 2, 4, 3))).to(dev)
         scratch = torch.zeros(B * 32 + 3 * B * nt, dtype=torch.int32, device=dev)
+        # second run with a capped grid: several tiles per CTA (barrier phases across tiles), as at the headline batch
+        Vd2 = Vd.clone()
         with torch.cuda.device(dev):
             _lib.check(L.r3d_debug_vchain(_p(Vd), _p(Qd), B, npad, ga, gb, _p(scratch), _stream()))
+            try:
+                _lib.set_option("panel_grid_cap", 3)
+                _lib.check(L.r3d_debug_vchain(_p(Vd2), _p(Qd), B, npad, ga, gb, _p(scratch), _stream()))
+            finally:
+                _lib.set_option("panel_grid_cap", 0)
+        assert torch.equal(Vd, Vd2)
         ref = V.astype(np.float64)
         for k, mask in enumerate((ga, gb, ga ^ gb)):
             Qf = np.zeros((B, npad, npad))
