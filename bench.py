@@ -637,7 +637,7 @@ def main_ours(args):
     # solver is bound by instruction issue and is reported under `stages` only
     dname, d = max(((k, v) for k, v in stages.items() if v.get("frac") is not None), key=lambda kv: kv[1]["ms_per_step"])
     traffic = None
-    tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    tp = os.path.join(ROOT, "profiles", "r02_traffic.json")
     if os.path.exists(tp):
         with open(tp) as f:
             traffic = json.load(f).get(dname)
