@@ -127,6 +127,7 @@ __device__ __forceinline__ void umma_commit_to(uint64_t* bar) {
 __device__ __forceinline__ float tf32_rn(float x) {
   return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
 }
+__device__ __forceinline__ float tf32_trunc(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -295,7 +296,7 @@ __global__ void __maxnreg__(72) panel_sym_kernel(const __grid_constant__ CUtenso
           }
           // per super tile every stage sees 2 uses of step 1 and 2 of step 2 (8 uses, 2 stages): the phase parities of
           // the two hand-over barriers follow from the use index alone
-          if (u < 4) bar_wait(&split_done[s], (u >> 1) & 1);            // A split (the Q planes landed before)
+          if (u < 4) bar_wait(&raw_full[s], (u >> 1) & 1);              // raw A slab (= hi operand) and Q planes landed
           else {
             bar_wait(&q_full[s], ((u - 4) >> 1) & 1);                   // pre-split Q^T planes landed (TMA)
             bar_wait(&tr_done[s], ((u - 4) >> 1) & 1);                  // A slab written by the transposer warp
@@ -306,6 +307,10 @@ __global__ void __maxnreg__(72) panel_sym_kernel(const __grid_constant__ CUtenso
           uint32_t first = (u & 1);                    // each accumulator takes two K slabs
 #pragma unroll
           for (int prod = 0; prod < 3; ++prod) {
+            if (prod == 2 && u < 4) {                  // A_lo comes from the splitters
+              bar_wait(&split_done[s], (u >> 1) & 1);
+              asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            }
             const uint32_t ab = (prod == 2) ? a_lo : a_hi;
             const uint32_t qb = (prod == 1) ? q_lo : q_hi;
 #pragma unroll
@@ -336,15 +341,18 @@ __global__ void __maxnreg__(72) panel_sym_kernel(const __grid_constant__ CUtenso
         uint8_t* st = smem + s * STAGE;
         float4* a_hi = reinterpret_cast<float4*>(st);
         float4* a_lo = reinterpret_cast<float4*>(st + A_RAW);
+        // kind::tf32 reads the upper 19 bits of each fp32 container, so the raw slab IS the hi operand (hi = x with the
+        // low 13 mantissa bits dropped); only lo = rn_tf32(x - hi) has to be written -- and the two products that do not
+        // involve lo can be issued as soon as the TMA has landed
 #pragma unroll 4
         for (int e = t; e < A_RAW / 16; e += 128) {
           const float4 x = a_hi[e];
-          float4 h, l;
-          h.x = tf32_rn(x.x); l.x = x.x - h.x;
-          h.y = tf32_rn(x.y); l.y = x.y - h.y;
-          h.z = tf32_rn(x.z); l.z = x.z - h.z;
-          h.w = tf32_rn(x.w); l.w = x.w - h.w;
-          a_hi[e] = h; a_lo[e] = l;
+          float4 l;
+          l.x = tf32_rn(x.x - tf32_trunc(x.x));
+          l.y = tf32_rn(x.y - tf32_trunc(x.y));
+          l.z = tf32_rn(x.z - tf32_trunc(x.z));
+          l.w = tf32_rn(x.w - tf32_trunc(x.w));
+          a_lo[e] = l;
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         bar_arrive(&split_done[s]);

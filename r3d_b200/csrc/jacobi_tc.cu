@@ -128,6 +128,8 @@ __device__ __forceinline__ void umma_commit_to(uint64_t* bar) {
 __device__ __forceinline__ float tf32_rn(float x) {
   return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
 }
+// what the tensor core sees of a raw fp32 container in kind::tf32: the low 13 mantissa bits dropped
+__device__ __forceinline__ float tf32_trunc(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
 
 // pairing of round r (same function as erank_kernels.cu): r >= 0 circle-method round robin over m blocks,
 // r < 0 the XOR matching with mask -r (task t pairs block i with i ^ mask, i = t with a zero inserted at the
@@ -370,7 +372,10 @@ __global__ void __maxnreg__(72) panel_update_tc_kernel(const __grid_constant__ C
         for (int slab = 0; slab < SLABS; ++slab, ++it) {
           const int s = it % NSTAGE;
           const uint32_t ph = (it / NSTAGE) & 1;
-          bar_wait(&split_done[s], ph);                // hi/lo operands of this K slab are in shared memory
+          // pair mode: the raw A slab is the hi operand (kind::tf32 reads the upper 19 bits of the container) and Q^T
+          // arrives pre-split, so two of the three products start when the TMA has landed; the lo product waits for the
+          // splitters.  Group mode: P^T is split in shared memory (hi rewritten), everything waits for the splitters.
+          bar_wait(SL == 2 ? &raw_full[s] : &split_done[s], ph);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t a_hi = s_u32(smem + s * STAGE), a_lo = a_hi + A_RAW;
           const uint32_t q_hi = a_hi + 2 * A_RAW, q_lo = q_hi + Q_RAW;
@@ -378,6 +383,10 @@ __global__ void __maxnreg__(72) panel_update_tc_kernel(const __grid_constant__ C
           for (int prod = 0; prod < 3; ++prod) {
             if ((debug & 1) && prod > 0) break;
             if (debug & 16) break;                    // timing experiment: no MMAs at all
+            if (SL == 2 && prod == 2) {
+              bar_wait(&split_done[s], ph);
+              asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            }
             const uint32_t ab = (prod == 2) ? a_lo : a_hi;
             const uint32_t qb = (prod == 1) ? q_lo : q_hi;
 #pragma unroll
@@ -416,12 +425,21 @@ __global__ void __maxnreg__(72) panel_update_tc_kernel(const __grid_constant__ C
 #pragma unroll 4
           for (int e = t; e < A_RAW / 16; e += 128) {
             const float4 x = a_hi[e];
-            float4 h, l;
-            h.x = tf32_rn(x.x); l.x = x.x - h.x;
-            h.y = tf32_rn(x.y); l.y = x.y - h.y;
-            h.z = tf32_rn(x.z); l.z = x.z - h.z;
-            h.w = tf32_rn(x.w); l.w = x.w - h.w;
-            a_hi[e] = h; a_lo[e] = l;
+            if (SL == 2) {                             // raw slab = hi operand: write lo only
+              float4 l;
+              l.x = tf32_rn(x.x - tf32_trunc(x.x));
+              l.y = tf32_rn(x.y - tf32_trunc(x.y));
+              l.z = tf32_rn(x.z - tf32_trunc(x.z));
+              l.w = tf32_rn(x.w - tf32_trunc(x.w));
+              a_lo[e] = l;
+            } else {
+              float4 h, l;
+              h.x = tf32_rn(x.x); l.x = x.x - h.x;
+              h.y = tf32_rn(x.y); l.y = x.y - h.y;
+              h.z = tf32_rn(x.z); l.z = x.z - h.z;
+              h.w = tf32_rn(x.w); l.w = x.w - h.w;
+              a_hi[e] = h; a_lo[e] = l;
+            }
           }
           if (SL != 2) {
 #pragma unroll 4
@@ -720,7 +738,7 @@ __global__ void __maxnreg__(72) panel_vchain_kernel(const __grid_constant__ CUte
             const uint32_t ph = (it / NSTAGE) & 1;
             // per tile every stage sees 2 uses of round 0 and 4 of rounds 1-2 (12 uses, 2 stages): the phase parities of
             // the two hand-over barriers follow from the use index alone
-            if (k == 0) bar_wait(&split_done[s], (ps >> 1) & 1);                 // A split (the Q planes landed before)
+            if (k == 0) bar_wait(&raw_full[s], (ps >> 1) & 1);                   // raw A slab (= hi operand) + Q planes landed
             else {
               bar_wait(&q_full[s], ((4 * (k - 1) + ps) >> 1) & 1);               // pre-split Q^T planes landed (TMA)
               bar_wait(&drain_done[s], ((4 * (k - 1) + ps) >> 1) & 1);           // A slab written by the drainers
@@ -732,6 +750,10 @@ __global__ void __maxnreg__(72) panel_vchain_kernel(const __grid_constant__ CUte
             uint32_t first = ps & 1;                             // the pair's accumulator takes two K slabs
 #pragma unroll
             for (int prod = 0; prod < 3; ++prod) {
+              if (prod == 2 && k == 0) {                         // A_lo of a TMA-fed slab comes from the splitters
+                bar_wait(&split_done[s], (ps >> 1) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+              }
               const uint32_t ab = (prod == 2) ? a_lo : a_hi;
               const uint32_t qb = (prod == 1) ? q_lo : q_hi;
 #pragma unroll
@@ -761,15 +783,17 @@ __global__ void __maxnreg__(72) panel_vchain_kernel(const __grid_constant__ CUte
         uint8_t* st = smem + s * STAGE;
         float4* a_hi = reinterpret_cast<float4*>(st);
         float4* a_lo = reinterpret_cast<float4*>(st + A_RAW);
+        // kind::tf32 reads the upper 19 bits of each fp32 container, so the raw slab IS the hi operand; only
+        // lo = rn_tf32(x - trunc_tf32(x)) is written, and the two products without lo start when the TMA has landed
 #pragma unroll 4
         for (int e = t; e < A_RAW / 16; e += 128) {
           const float4 x = a_hi[e];
-          float4 h, l;
-          h.x = tf32_rn(x.x); l.x = x.x - h.x;
-          h.y = tf32_rn(x.y); l.y = x.y - h.y;
-          h.z = tf32_rn(x.z); l.z = x.z - h.z;
-          h.w = tf32_rn(x.w); l.w = x.w - h.w;
-          a_hi[e] = h; a_lo[e] = l;
+          float4 l;
+          l.x = tf32_rn(x.x - tf32_trunc(x.x));
+          l.y = tf32_rn(x.y - tf32_trunc(x.y));
+          l.z = tf32_rn(x.z - tf32_trunc(x.z));
+          l.w = tf32_rn(x.w - tf32_trunc(x.w));
+          a_lo[e] = l;
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         bar_arrive(&split_done[s]);

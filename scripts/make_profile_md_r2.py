@@ -67,7 +67,7 @@ want = [("gpu__time_duration.sum", "time under ncu"), ("dram__bytes_read.sum", "
         ("lts__t_sector_hit_rate.pct", "L2 hit rate %")]
 out.append("## `ncu --set full --clock-control none --import-source on` captures (one working launch each, `python scripts/prof_erank.py`)\n")
 caps = [("r02_prof_panel_sym_kernel.ncu-rep", "panel_sym_kernel (G <- Q^T G Q, one pass)"),
-        ("r02_prof_panel_update_tc_kernel.ncu-rep", "panel_update_tc_kernel<2> (V <- V Q)"),
+        ("r02_prof_panel_vchain_kernel.ncu-rep", "panel_vchain_kernel (V <- V Q1 Q2 Q3, three rounds per pass)"),
         ("r02_prof_jacobi_inner_cross_kernel.ncu-rep", "jacobi_inner_cross_kernel")]
 tab = {}
 for rep, name in caps:

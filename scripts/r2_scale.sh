@@ -1,11 +1,12 @@
 #!/bin/bash
 # usage: r2_scale.sh N   -- weak (B=64/GPU) and strong (global batch 512) scaling runs on N GPUs of one box
+cd /root/repo
 N=$1
 mkdir -p gpurun_out
 nvidia-smi -L | wc -l
 run() {  # name, extra args
   name=$1; shift
-  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29520 \
+  timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29520 \
       bench.py --gpus $N --steps 10 --warmup 3 "$@" > gpurun_out/r02_bench_n${N}_$name.json 2> gpurun_out/r02_bench_n${N}_$name.err
   echo "n$N $name rc=$?"
 }
