@@ -168,15 +168,19 @@ __host__ __device__ __forceinline__ int64_t boff(int np, int r, int c) {
   return (int64_t(c >> 5) * np + r) * JB + (c & (JB - 1));
 }
 
-static size_t jacobi_ws_bytes(int64_t B, int64_t n) {   // includes slack so that two half-batch carvings fit
+static size_t jacobi_ws_bytes_one(int64_t B, int64_t n) {   // what jacobi_carve(ws, B, n) uses, plus alignment slack
   const size_t np = jacobi_np(n), nt = np / JM;
   size_t f = size_t(B) * (3 * np * np + 2 * nt * QSTR + 1);
-  size_t i = size_t(B) * (JMAX_SWEEPS + 2 * nt) + JMAX_SWEEPS + 2 * (2 * kPanelSyncGroups + 8);
-  if (np % 128 == 0) {                                  // spread schedule: Sg, Sh, Pv, Pt[2] + flags
+  size_t i = size_t(B) * (JMAX_SWEEPS + 2 * nt) + JMAX_SWEEPS + (2 * kPanelSyncGroups + 8);
+  if (np % 128 == 0) {                                  // spread / chained schedules: Sg, Sh, Pv, Pt[2], Ql[2], Qc[5] + flags
     f += size_t(B) * 8 * np * 128;
     i += size_t(B) * 8 * nt;
   }
   return f * 4 + i * 4 + 4096;
+}
+constexpr int kMaxChunksWs = 4;                         // == kMaxChunks (declared with the stream sets below)
+static size_t jacobi_ws_bytes(int64_t B, int64_t n) {   // room for up to kMaxChunks chunk carvings of the batch
+  return jacobi_ws_bytes_one(B, n) + size_t(kMaxChunksWs) * (jacobi_ws_bytes_one(0, n) + 512);
 }
 
 static JacobiWs jacobi_carve(void* ws, int64_t B, int64_t n) {
@@ -1511,11 +1515,12 @@ extern "C" int r3d_gram(const void* x, int64_t B, int64_t T, int64_t C, int dtyp
 // inner solve of round r+1 (which needs only G and leaves HBM idle).  (2) The batch is split into two chunks
 // whose Jacobi iterations run on two streams, so one chunk's issue-bound inner solve overlaps the other's
 // HBM-bound panel passes.  Fork/join with events only, so the pattern is also legal under stream capture.
-constexpr int kMaxChunks = 2;
+constexpr int kMaxChunks = 4;
+static_assert(kMaxChunks == kMaxChunksWs, "workspace slack is sized for kMaxChunks carvings");
 struct StreamSet {
   bool ready = false;
-  cudaStream_t chunk[kMaxChunks] = {nullptr, nullptr};     // chunk 0 uses the caller's stream
-  cudaStream_t vst[kMaxChunks] = {nullptr, nullptr};
+  cudaStream_t chunk[kMaxChunks] = {};     // chunk 0 uses the caller's stream
+  cudaStream_t vst[kMaxChunks] = {};
   cudaEvent_t ev_inner[kMaxChunks][2], ev_v[kMaxChunks][2], ev_fork, ev_join[kMaxChunks];
   cudaEvent_t ev_inner_c[kMaxChunks][2], ev_v_c[kMaxChunks][2];   // chained schedule: per slot
   int create() {
@@ -1781,22 +1786,28 @@ extern "C" int r3d_stream_sets_created(void) { return g_sets_created.load(); }
 static int jacobi_run_chunked(const float* G, int64_t B, int64_t n, void* workspace, float* lambda_out, float* U_out,
                               int32_t* sweeps_out, int max_sweeps, cudaStream_t st, float tol_override) {
   const int np = jacobi_np(n);
-  const bool split = options().jacobi_chunks >= 2 && B >= 2 && panel_tc_supported(np) &&
-                     options().jacobi_update_tc != 0 && (B / 2) * (np / JM) >= 2 * kNumSMs;
-  if (!split) return jacobi_run(G, B, n, workspace, lambda_out, U_out, sweeps_out, max_sweeps, st, 0, tol_override);
+  // chunks: as many as asked for (<= kMaxChunks) while every chunk still fills the GPU once with inner-solver CTAs
+  int nch = std::min(options().jacobi_chunks, kMaxChunks);
+  if (!(panel_tc_supported(np) && options().jacobi_update_tc != 0)) nch = 1;
+  while (nch > 1 && (B / nch) * (np / JM) < kNumSMs) --nch;
+  if (nch <= 1) return jacobi_run(G, B, n, workspace, lambda_out, U_out, sweeps_out, max_sweeps, st, 0, tol_override);
   StreamRef g_streams;
   if (int e = g_streams.ensure()) return e;
-  const int64_t B0 = (B + 1) / 2, B1 = B - B0;
-  char* ws1 = (char*)workspace + ((jacobi_ws_bytes(B0, n) + 255) & ~size_t(255));
-  cudaStream_t s1 = g_streams->chunk[1];
   R3D_CUDA(cudaEventRecord(g_streams->ev_fork, st));
-  R3D_CUDA(cudaStreamWaitEvent(s1, g_streams->ev_fork, 0));
-  if (int e = jacobi_run(G, B0, n, workspace, lambda_out, U_out, sweeps_out, max_sweeps, st, 0, tol_override)) return e;
-  if (int e = jacobi_run(G + B0 * n * n, B1, n, ws1, lambda_out ? lambda_out + B0 * n : nullptr,
-                         U_out ? U_out + B0 * n * n : nullptr, sweeps_out ? sweeps_out + B0 : nullptr, max_sweeps,
-                         s1, 1, tol_override)) return e;
-  R3D_CUDA(cudaEventRecord(g_streams->ev_join[1], s1));
-  R3D_CUDA(cudaStreamWaitEvent(st, g_streams->ev_join[1], 0));
+  char* ws = (char*)workspace;
+  int64_t b0 = 0;
+  for (int c = 0; c < nch; ++c) {
+    const int64_t Bc = B / nch + (c < B % nch ? 1 : 0);
+    cudaStream_t sc = c == 0 ? st : g_streams->chunk[c];
+    if (c > 0) R3D_CUDA(cudaStreamWaitEvent(sc, g_streams->ev_fork, 0));
+    if (int e = jacobi_run(G + b0 * n * n, Bc, n, ws, lambda_out ? lambda_out + b0 * n : nullptr,
+                           U_out ? U_out + b0 * n * n : nullptr, sweeps_out ? sweeps_out + b0 : nullptr, max_sweeps, sc, c,
+                           tol_override)) return e;
+    if (c > 0) R3D_CUDA(cudaEventRecord(g_streams->ev_join[c], sc));
+    ws += (jacobi_ws_bytes_one(Bc, n) + 255) & ~size_t(255);
+    b0 += Bc;
+  }
+  for (int c = 1; c < nch; ++c) R3D_CUDA(cudaStreamWaitEvent(st, g_streams->ev_join[c], 0));
   return 0;
 }
 

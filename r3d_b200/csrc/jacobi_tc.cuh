@@ -56,7 +56,11 @@ struct Options {
   float jacobi_tol = 1e-6f;     // relative rotation threshold |s_pq| > tol sqrt(s_pp s_qq) (1e-5 costs 0.3 ms less per step and
                                 // ~10x in gradient accuracy: 8e-5 vs 8e-6 on square samples)
   int jacobi_max_sweeps = 16;
-  int jacobi_chunks = 1;        // 2: run two half-batches on two streams (measured slower at the headline shape: 69.8 vs 65.9 ms)
+  int jacobi_chunks = 2;        // split the batch into this many chunks (<= 4) whose Jacobi iterations run on separate streams, so
+                                // that one chunk's issue-bound inner solve shares the SMs with another chunk's latency-bound
+                                // panel passes (a chunk must still fill the GPU once with inner-solver CTAs).  Headline shape:
+                                // 1 -> 34.8 ms, 2 -> 32.7 ms, 3 -> 33.4 ms, 4 -> 34.3 ms per step (round 1's kernels were
+                                // slower with 2: 69.8 vs 65.9 ms)
   float jacobi_tol_pass1 = 1e-6f; // first-pass relative threshold when a second pass follows (looser values are slower:
                                   // 1e-4 -> 56.7 ms, 1e-3 -> 59.5 ms vs 55.3 ms at 1e-5, measured before the raised floor)
   float jacobi_nu_pass1 = 2048.f; // first pass of the two-pass solver: absolute significance floor in units of 2^-23 max|diag|

@@ -714,7 +714,7 @@ def test_fuser_step_cuda_graph_capture(dev):
 
 @pytest.mark.parametrize("opts", [{"panel_merged": 1, "panel_sym": 0}, {"jacobi_inner_regs": 0},
                                   {"jacobi_update_tc": 0}, {"gemm_tc": 0}, {"jacobi_overlap_v": 0},
-                                  {"jacobi_chunks": 2}, {"panel_sym": 0}, {"jacobi_schedule": 1},
+                                  {"jacobi_chunks": 1}, {"jacobi_chunks": 4}, {"panel_sym": 0}, {"jacobi_schedule": 1},
                                   {"jacobi_schedule": 1, "panel_sym": 0},
                                   {"jacobi_schedule": 1, "jacobi_inner_regs": 0}, {"jacobi_schedule": 0},
                                   {"jacobi_schedule": 0, "jacobi_overlap_v": 0},
@@ -724,7 +724,7 @@ def test_alternative_kernel_paths_agree(opts, dev):
     no side stream, two chunks, two-pass panel update through H, spread schedule, round-robin schedule) must reproduce the default path's effective rank and gradient."""
     from r3d_b200 import ops, _lib
     defaults = {"panel_merged": 0, "jacobi_inner_regs": 1, "jacobi_update_tc": 1, "gemm_tc": 1, "jacobi_overlap_v": 1,
-                "jacobi_chunks": 1, "jacobi_schedule": 2, "panel_sym": 1}
+                "jacobi_chunks": 2, "jacobi_schedule": 2, "panel_sym": 1}
     x = _spectra("relu", 6, 256, 256, 77)
     ref = EO.erank(x)
     gref = EO.erank_bwd(x, np.ones(6, np.float32))
@@ -740,6 +740,27 @@ def test_alternative_kernel_paths_agree(opts, dev):
     finally:
         for k, v in defaults.items():
             _lib.set_option(k, v)
+
+
+def test_chunked_batches_are_bit_identical(dev):
+    """jacobi_chunks: the batch is cut into chunks that iterate on separate streams (default 2 when every chunk still
+    fills the GPU).  Matrices are independent, so the result must not depend on the chunking -- bit for bit."""
+    from r3d_b200 import ops, _lib
+    x = torch.from_numpy(_spectra("relu", 80, 256, 256, 5)).to(dev)
+    outs = []
+    try:
+        for nch in (1, 2, 4):
+            _lib.set_option("jacobi_chunks", nch)
+            xt = x.clone().requires_grad_(True)
+            er = ops.erank(xt)
+            er.sum().backward()
+            outs.append((er.detach().clone(), xt.grad.clone()))
+    finally:
+        _lib.set_option("jacobi_chunks", 2)
+    ref = EO.erank(x[:3].cpu().numpy())
+    np.testing.assert_allclose(outs[0][0][:3].cpu().numpy(), ref, rtol=1e-4)
+    for er, g in outs[1:]:
+        assert torch.equal(er, outs[0][0]) and torch.equal(g, outs[0][1])
 
 
 def test_panel_round_matches_float64(dev):
