@@ -563,7 +563,8 @@ __device__ __forceinline__ bool jacobi_rotation_fast(float spp, float sqq, float
   return rt;
 }
 
-__global__ void __launch_bounds__(256, 4) jacobi_inner_cross_kernel(float* __restrict__ Gp, int np, int nb, int nt,
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB) jacobi_inner_cross_kernel(float* __restrict__ Gp, int np, int nb, int nt,
                                                                     int round, int sweep, int* __restrict__ cnt,
                                                                     int* __restrict__ qflag, float* __restrict__ Qb,
                                                                     float tol, const float* __restrict__ nu,
@@ -1631,7 +1632,7 @@ static int jacobi_run(const float* G, int64_t B, int64_t n, void* workspace, flo
     {
       R3D_STAGE(ST_JACOBI_INNER, st);
       if (!generic && options().jacobi_inner_regs != 0)
-        jacobi_inner_cross_kernel<<<dim3(w.nt, (unsigned)B), 256, 0, st>>>(w.Gp, w.np, w.nb, w.nt, r, sweep, w.cnt,
+        (options().jacobi_inner_regs == 3 ? jacobi_inner_cross_kernel<3> : jacobi_inner_cross_kernel<4>)<<<dim3(w.nt, (unsigned)B), 256, 0, st>>>(w.Gp, w.np, w.nb, w.nt, r, sweep, w.cnt,
                                                                           w.qflag[qb], w.Qb[qb], tol, w.nu, w.psync, 1);
       else
         jacobi_inner_kernel<<<dim3(w.nt, (unsigned)B), 256, 0, st>>>(w.Gp, w.np, w.nb, w.nt, r, sweep, w.cnt,
@@ -1674,7 +1675,7 @@ static int jacobi_run(const float* G, int64_t B, int64_t n, void* workspace, flo
       {
         R3D_STAGE(ST_JACOBI_INNER, st);
         if (!generic && options().jacobi_inner_regs != 0)
-          jacobi_inner_cross_kernel<<<dim3(w.nt, (unsigned)B), 256, 0, st>>>(w.Gp, w.np, w.nb, w.nt, code, sweep, w.cnt,
+          (options().jacobi_inner_regs == 3 ? jacobi_inner_cross_kernel<3> : jacobi_inner_cross_kernel<4>)<<<dim3(w.nt, (unsigned)B), 256, 0, st>>>(w.Gp, w.np, w.nb, w.nt, code, sweep, w.cnt,
                                                                             w.qflagc[qi], w.Qc[qi], tol, w.nu, nullptr, 1);
         else
           jacobi_inner_kernel<<<dim3(w.nt, (unsigned)B), 256, 0, st>>>(w.Gp, w.np, w.nb, w.nt, code, sweep, w.cnt,
@@ -1719,7 +1720,7 @@ static int jacobi_run(const float* G, int64_t B, int64_t n, void* workspace, flo
       {
         R3D_STAGE(ST_JACOBI_INNER, st);
         if (!generic && options().jacobi_inner_regs != 0)
-          jacobi_inner_cross_kernel<<<dim3(2, (unsigned)(B * ng)), 256, 0, st>>>(w.Sg, 128, 4, 2, code, sweep, w.cnt, w.lflag[k],
+          jacobi_inner_cross_kernel<4><<<dim3(2, (unsigned)(B * ng)), 256, 0, st>>>(w.Sg, 128, 4, 2, code, sweep, w.cnt, w.lflag[k],
                                                                                 w.Ql[ql], tol, w.nu, nullptr, ng);
         else
           jacobi_inner_kernel<<<dim3(2, (unsigned)(B * ng)), 256, 0, st>>>(w.Sg, 128, 4, 2, code, sweep, w.cnt, w.lflag[k],
