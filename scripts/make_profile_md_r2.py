@@ -39,7 +39,9 @@ out.append("`python bench.py --steps 1 --warmup 3 --no-extras` exited 0 without 
            "gradient bucket are serialised here, they overlap in a real run): compare SHARES, not absolutes.  Window = the 4th step "
            f"(launches {lo}..{hi - 1} of {len(launches)}, delimited by the one `gram_bf16_kernel` launch per step): {len(win)} launches, "
            f"{tot / 1000:.2f} ms of kernel time.  'working' = launches of at least 10 us (the Jacobi launch sequence is fixed; launches after "
-           "convergence return in 3-4 us).\n")
+           "convergence return in 3-4 us).  The batch runs as two chunks on two streams (`jacobi_chunks=2`), so every Jacobi launch here covers HALF "
+           "the batch (64 matrices) -- in isolation, as ncu runs them, such a launch is less efficient than a full-batch one; in the real run "
+           "the two chunks' launches share the SMs.\n")
 out.append("| kernel | launches | total ms | share | avg us | working | avg us working |")
 out.append("|---|---:|---:|---:|---:|---:|---:|")
 for n, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
@@ -65,7 +67,7 @@ want = [("gpu__time_duration.sum", "time under ncu"), ("dram__bytes_read.sum", "
         ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps active %"),
         ("launch__registers_per_thread", "registers / thread"), ("launch__waves_per_multiprocessor", "waves / SM"),
         ("lts__t_sector_hit_rate.pct", "L2 hit rate %")]
-out.append("## `ncu --set full --clock-control none --import-source on` captures (one working launch each, `python scripts/prof_erank.py`)\n")
+out.append("## `ncu --set full --clock-control none --import-source on` captures (one working launch each, `R3D_OPTS=jacobi_chunks=1 python scripts/prof_erank.py`: full-batch launches of 128 matrices, as in the bench's stage table)\n")
 caps = [("r02_prof_panel_sym_kernel.ncu-rep", "panel_sym_kernel (G <- Q^T G Q, one pass)"),
         ("r02_prof_panel_vchain_kernel.ncu-rep", "panel_vchain_kernel (V <- V Q1 Q2 Q3, three rounds per pass)"),
         ("r02_prof_jacobi_inner_cross_kernel.ncu-rep", "jacobi_inner_cross_kernel")]
