@@ -558,12 +558,16 @@ def main_ours(args):
 
     # End to end the way a training loop with a prefetching loader runs it: the pinned-host -> device copy of step
     # i+1 is issued on a copy stream while step i computes (two staging buffers); every step's input still crosses
-    # PCIe inside the timed region and every step ends with the device -> host read of its statistic.
+    # PCIe inside the timed region and every step's statistic is read back to the host inside it.  The read of step i
+    # is waited for after step i+1 has been enqueued (the usual one-step lag of a logged loss), so the host stays one
+    # step ahead of the device; the last step's read is waited for before the region ends.
     copy_stream = torch.cuda.Stream(device=dev)
     stage = [stage_buf, torch.empty_like(stage_buf)]
     ev_copied = [torch.cuda.Event(), torch.cuda.Event()]
     ev_consumed = [torch.cuda.Event(), torch.cuda.Event()]
     e2e_state = {"steps": 0}
+    er_host2 = [er_host, torch.empty_like(er_host).pin_memory()]
+    ev_read = [torch.cuda.Event(), torch.cuda.Event()]
 
     def issue_copy(i):
         s_ = i % 2
@@ -581,8 +585,14 @@ def main_ours(args):
         main.wait_event(ev_copied[i % 2])
         _, er, _, _ = step(stage[i % 2], dev_g[i % NSETS])
         ev_consumed[i % 2].record(main)
-        er_host.copy_(er, non_blocking=True)                            # D2H of the step's statistic
-        main.synchronize()
+        er_host2[i % 2].copy_(er, non_blocking=True)                    # D2H of the step's statistic
+        ev_read[i % 2].record(main)
+        if i > 0:
+            ev_read[(i - 1) % 2].synchronize()                          # step i-1's statistic is on the host now
+            e2e_state["seen"] = float(er_host2[(i - 1) % 2][0])
+        if i + 1 == e2e_state["steps"]:
+            ev_read[i % 2].synchronize()                                # the last step: no successor to hide behind
+            e2e_state["seen"] = float(er_host2[i % 2][0])
 
     for i in range(max(args.warmup, 3)):
         resident(i)
