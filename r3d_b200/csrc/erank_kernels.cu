@@ -1328,6 +1328,7 @@ extern "C" int r3d_set_option(const char* key, double value) {
   else if (k == "panel_ring") options().panel_ring = (int)value;
   else if (k == "jacobi_v_after_g") options().jacobi_v_after_g = value != 0.0;
   else if (k == "jacobi_schedule") options().jacobi_schedule = (int)value;
+  else if (k == "jacobi_own_streams") options().jacobi_own_streams = (int)value;
   else if (k == "panel_sym") options().panel_sym = (int)value;
   else if (k == "lin_fast") options().lin_fast = (int)value;
   else if (k == "panel_debug") g_panel_debug = (int)value;
@@ -1526,8 +1527,12 @@ struct StreamSet {
   cudaEvent_t ev_inner_c[kMaxChunks][2], ev_v_c[kMaxChunks][2];   // chained schedule: per slot
   int create() {
     for (int c = 0; c < kMaxChunks; ++c) {
-      R3D_CUDA(cudaStreamCreateWithFlags(&chunk[c], cudaStreamNonBlocking));
-      R3D_CUDA(cudaStreamCreateWithFlags(&vst[c], cudaStreamNonBlocking));
+      // The chunk streams carry the critical path (inner solve -> G update -> inner solve ...); the V streams only have
+      // to be done two super-rounds later.  Higher priority for the former lets their CTAs take free SM slots first.
+      int lo = 0, hi = 0;
+      R3D_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      R3D_CUDA(cudaStreamCreateWithPriority(&chunk[c], cudaStreamNonBlocking, hi));
+      R3D_CUDA(cudaStreamCreateWithPriority(&vst[c], cudaStreamNonBlocking, lo));
       R3D_CUDA(cudaEventCreateWithFlags(&ev_join[c], cudaEventDisableTiming));
       for (int i = 0; i < 2; ++i) {
         R3D_CUDA(cudaEventCreateWithFlags(&ev_inner[c][i], cudaEventDisableTiming));
@@ -1799,16 +1804,18 @@ static int jacobi_run_chunked(const float* G, int64_t B, int64_t n, void* worksp
   int64_t b0 = 0;
   for (int c = 0; c < nch; ++c) {
     const int64_t Bc = B / nch + (c < B % nch ? 1 : 0);
-    cudaStream_t sc = c == 0 ? st : g_streams->chunk[c];
-    if (c > 0) R3D_CUDA(cudaStreamWaitEvent(sc, g_streams->ev_fork, 0));
+    const bool own = c > 0 || options().jacobi_own_streams != 0;   // chunk 0 may stay on the caller's stream
+    cudaStream_t sc = own ? g_streams->chunk[c] : st;
+    if (own) R3D_CUDA(cudaStreamWaitEvent(sc, g_streams->ev_fork, 0));
     if (int e = jacobi_run(G + b0 * n * n, Bc, n, ws, lambda_out ? lambda_out + b0 * n : nullptr,
                            U_out ? U_out + b0 * n * n : nullptr, sweeps_out ? sweeps_out + b0 : nullptr, max_sweeps, sc, c,
                            tol_override)) return e;
-    if (c > 0) R3D_CUDA(cudaEventRecord(g_streams->ev_join[c], sc));
+    if (own) R3D_CUDA(cudaEventRecord(g_streams->ev_join[c], sc));
     ws += (jacobi_ws_bytes_one(Bc, n) + 255) & ~size_t(255);
     b0 += Bc;
   }
-  for (int c = 1; c < nch; ++c) R3D_CUDA(cudaStreamWaitEvent(st, g_streams->ev_join[c], 0));
+  for (int c = options().jacobi_own_streams != 0 ? 0 : 1; c < nch; ++c)
+    R3D_CUDA(cudaStreamWaitEvent(st, g_streams->ev_join[c], 0));
   return 0;
 }
 

@@ -98,6 +98,10 @@ struct Options {
   int panel_sym = 1;            // 1: G <- Q^T G Q as ONE in-place pass over the upper block triangle with mirrored stores
                                 //    (jacobi_sym.cu: 0.56 n^2 read + n^2 written per round); 0: two passes through the scratch
                                 //    matrix H (jacobi_tc.cu: 2 n^2 read + 2 n^2 written)
+  int jacobi_own_streams = 1;   // 1: with several chunks, chunk 0 also runs on a library-owned stream (forked from / joined to the
+                                // caller's), so that all chunk streams have the same (high) priority and the V side streams the
+                                // low one: 32.73 -> 32.46 ms; 0: chunk 0 on the caller's stream (33.4 ms: the chunks get unequal
+                                // priorities)
   int jacobi_schedule = 2;      // 2 (default): where the block count is a power of two >= 8, the rounds of a sweep are the XOR
                                 //    matchings grouped three at a time into super-rounds {a, b, a^b} that stay inside 4-block
                                 //    (128-column) cosets; G is updated every round, the three V updates of a super-round run as
