@@ -27,6 +27,19 @@ inline bool per_device_once(bool (&done)[kMaxDevices]) {
   return true;
 }
 
+// The host-buffer entry points take their device arena from the stream-ordered allocator on every call.  By default
+// the pool hands unused memory back to the driver at every synchronisation, so each call would map several GB again
+// (tens of ms up to a second).  Keep it: raise the release threshold of the device's default pool once.
+inline void keep_async_pool() {
+  static bool done[kMaxDevices] = {};
+  if (!per_device_once(done)) return;
+  cudaMemPool_t pool = nullptr;
+  if (cudaDeviceGetDefaultMemPool(&pool, current_device_index()) == cudaSuccess && pool) {
+    unsigned long long keep = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
+}
+
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
 

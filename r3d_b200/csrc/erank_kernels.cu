@@ -1958,6 +1958,7 @@ extern "C" int r3d_fuser_step_host(const void* rgb_host, const void* depth_host,
   const size_t o_sws = take(r3d_score_workspace_floats(rows, C) * 4), o_pk = take(size_t(2 * C + 2) * 4);
   const size_t o_idx = take(size_t(2) * (k > 0 ? k : 1) * 8);
   char* buf = nullptr;
+  keep_async_pool();
   R3D_CUDA(cudaMallocAsync((void**)&buf, off + 256, st));
   int rc = 0;
   do {

@@ -1023,6 +1023,7 @@ extern "C" int r3d_token_fusion_host(const void* rgb_host, const void* depth_hos
   char* buf = nullptr;
   const size_t off_d = nb, off_o = 2 * nb, off_ws = 4 * nb, off_sc = off_ws + wsf * 4, off_idx = off_sc + 2 * C * 4;
   const size_t total = off_idx + 2 * size_t(k > 0 ? k : 1) * 8;
+  keep_async_pool();
   R3D_CUDA(cudaMallocAsync((void**)&buf, total, st));
   int rc = 0;
   do {
