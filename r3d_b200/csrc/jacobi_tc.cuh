@@ -63,11 +63,12 @@ struct Options {
                                 // slower with 2: 69.8 vs 65.9 ms)
   float jacobi_tol_pass1 = 1e-6f; // first-pass relative threshold when a second pass follows (looser values are slower:
                                   // 1e-4 -> 56.7 ms, 1e-3 -> 59.5 ms vs 55.3 ms at 1e-5, measured before the raised floor)
-  float jacobi_nu_pass1 = 2048.f; // first pass of the two-pass solver: absolute significance floor in units of 2^-23 max|diag|
-                                  // (single-pass solver and second pass: 4).  The second pass removes what the first leaves,
-                                  // so the first may stop ~2.5 sweeps earlier: 4 -> 55.1 ms, 1024 -> 50.7, 4096 -> 48.8 with
-                                  // unchanged gradients (<= 8e-5); from 16384 on the hardest spectrum (channel decay 512x512)
-                                  // loses its smallest directions (9e-3)
+  float jacobi_nu_pass1 = 8192.f; // first pass of the two-pass solver: absolute significance floor in units of 2^-23 max|diag|
+                                  // (single-pass solver: 4).  The second pass removes what the first leaves, so the first may stop
+                                  // early.  With the scale-free second pass (below), gradient error / step time on the hard inputs
+                                  // of scripts/dbg_floor_sweep.py: 2048 -> <= 1.6e-5 / 32.4 ms, 8192 -> <= 1.4e-5 / 31.5 ms,
+                                  // 16384 -> <= 1.9e-5 but two inputs reach the second pass's sweep cap, 32768 -> 7e-5,
+                                  // 65536 -> 3e-3 (the smallest directions are lost)
   float jacobi_nu_pass2 = -1e-10f; // second pass.  > 0: absolute floor in the same units.  < 0 (default): scale-free -- a rotation
                                   // is significant when it passes the relative test and at least one of its two directions has
                                   // a diagonal entry above |value| * max|diag| (1e-10 = (1e-4)^2 * 1e-2: below the numerical-rank

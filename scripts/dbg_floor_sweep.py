@@ -21,7 +21,7 @@ cases = [(k, T, C) for k in ("relu1", "relu3", "shift2", "shift8", "decay") for 
 data = [(k, T, C, mk(k, T, C)) for k, T, C in cases]
 refs = [(EO.erank(x), EO.erank_bwd(x, np.ones(1))) for _, _, _, x in data]
 _lib.set_option('erank_pass2_sweeps', 6)
-for nu1, nu2 in ((2048, -1e-10), (1024, -1e-10), (512, -1e-10), (4096, -1e-10), (1024, -1e-9), (1024, -1e-12), (1024, 0.25)):
+for nu1, nu2 in [(float(a), -1e-10) for a in (sys.argv[1:] or ["2048", "4096", "8192"])]:
     _lib.set_option("jacobi_nu_pass1", nu1); _lib.set_option("jacobi_nu_pass2", nu2)
     out = []
     for (k, T, C, x), (er_ref, g_ref) in zip(data, refs):
