@@ -79,7 +79,8 @@ int r3d_debug_vchain(float* V, float* Q3, int64_t B, int np, int ga, int gb, int
  * The launch sequence is fixed and launches after convergence exit at once, so the bytes a timed region really
  * moved are tiles x 65536, not launches x (one full pass).  Synchronises the device. */
 int r3d_panel_tiles(uint64_t* out3, int reset);
-/* Side-stream sets (4 streams + 11 events each) created in this process so far.  They are pooled per device and
+/* Side-stream sets (8 streams: per batch chunk one high-priority stream and one low-priority V stream; 41 events each) created
+ * in this process so far.  They are pooled per device and
  * lent to host threads, so the count stays flat when short-lived threads (nn.DataParallel replicas,
  * main_utkinects.py:129) call the effective-rank entry points. */
 int r3d_stream_sets_created(void);
