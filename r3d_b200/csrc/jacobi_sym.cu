@@ -21,10 +21,13 @@
 //
 // Pipeline per CTA (persistent over a strided list of super tiles, 2 CTAs per SM); a super tile makes 8 uses of a
 // 2-stage ring of 48 KB stages (one 32-wide K slab of both operands, hi + lo):
-//   warp 0      TMA producer: uses 0-3 the four 32x32 row blocks of G[(a1,a2), column block] + the K slab of Q_c^T;
-//               uses 4-7 only the K slab of Q_a^T (the A part comes from the transposers)
-//   warps 2-5   splitters: hi/lo split in shared memory, in place
-//   warp 1      MMA issuer: 12 x tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=64, K=8) per use
+//   warp 0      TMA producer: uses 0-3 the four 32x32 row blocks of G[(a1,a2), column block] + the hi and lo planes of the
+//               K slab of Q_c^T (the inner solver emits Q^T pre-split); uses 4-7 only the planes of Q_a^T (the A part comes
+//               from the transposers; these uses complete on a TMA barrier of their own, q_full)
+//   warps 2-5   splitters (uses 0-3 only): the raw slab is the hi operand (kind::tf32 reads the upper 19 bits of the
+//               container), they write lo = rn_tf32(x - trunc_tf32(x)) next to it
+//   warp 1      MMA issuer: 12 x tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=64, K=8) per use; in uses 0-3 the eight that
+//               need no lo plane of G go out when the TMA barrier fires, the other four after the splitters
 //   warps 6-9   transposers + epilogue: W -> operand slabs of step 2 (warp q owns TMEM lanes 32q.. = K slab q of step 2),
 //               then D_a -> global: direct tile by transposed stores (one 128-byte line per instruction), mirror tile
 //               through the shared-memory staging of tc_store.cuh

@@ -9,19 +9,22 @@
 // because G' = (G Q)^T Q for symmetric G: pass 1 writes H^T = (G Q)^T (transposed
 // store), pass 2 applies the same panel update to H^T.  V is updated in place.
 //
-// fp32 accuracy on TF32 tensor cores comes from the 3xTF32 split: x = hi + lo with
-// hi = round-to-nearest TF32 of x (exact in TF32), lo = x - hi, and D = A_hi B_hi + A_hi B_lo + A_lo B_hi
-// accumulated in fp32 in TMEM (error ~2^-22 per product).
+// fp32 accuracy on TF32 tensor cores comes from the 3xTF32 split: x = hi + lo with hi exact in TF32 and
+// D = A_hi B_hi + A_hi B_lo + A_lo B_hi accumulated in fp32 in TMEM (error ~2^-21 per product).  The rotation products
+// Q^T arrive PRE-SPLIT from the inner solver (hi = round-to-nearest TF32, lo = Q^T - hi, two planes per block pair).
+// A slab that comes from HBM is its own hi operand: kind::tf32 reads the upper 19 bits of each fp32 container, so only
+// lo = rn_tf32(x - trunc_tf32(x)) is computed and written next to it.
 //
 // Pipeline per CTA (persistent over a strided tile list); the unit that travels through the 2-stage shared-memory
 // ring is one 32-column K slab of a tile, not the tile:
-//   warp 0      TMA producer: per slab one 32-column box of 128 panel rows + one 32-column box of the 64 rows of
-//               Q^T (both K-major SWIZZLE_128B)
-//   warps 2-5   splitters: hi/lo split in shared memory (same swizzled addresses)
-//   warp 1      MMA issuer: per slab 12 x tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=64, K=8), the two slabs of a
-//               tile accumulate into the same TMEM tile
-//   warps 6-9   epilogue: tcgen05.ld 32x32b.x64 -> (transposed) global stores
+//   warp 0      TMA producer: per slab one 32-column box of 128 panel rows + the hi and lo boxes of the 64 rows of Q^T
+//               (all K-major SWIZZLE_128B)
+//   warps 2-5   splitters: write the lo plane of the panel slab (group mode: also split P^T, which is plain fp32)
+//   warp 1      MMA issuer: per slab 12 x tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=64, K=8); the eight that do not
+//               read a lo plane written by the splitters are issued as soon as the TMA barrier fires
+//   warps 6-9   epilogue: tcgen05.ld 32x32b.x32 -> (transposed) global stores
 //   (warp 0 also allocates TMEM: 2 accumulator stages x 64 columns)
+// panel_vchain_kernel (further down) chains the V updates of three XOR rounds on chip: one pass over V per three rounds.
 // SASS evidence: UTCHMMA/UTCMMA (tcgen05.mma), UTMALDG (TMA), LDTM (tcgen05.ld).
 #include <cuda.h>
 
