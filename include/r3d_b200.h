@@ -73,6 +73,13 @@ int r3d_debug_panel_round(float* G, float* H, float* V, const float* Qb, int64_t
 /* Test hook: the chained V update  V <- V Q1 Q2 Q3  of three XOR rounds (masks ga, gb, ga ^ gb); Q3 = the three rounds'
  * Q^T buffers back to back, scratch = B * 32 + 3 * B * np/64 ints. */
 int r3d_debug_vchain(float* V, float* Q3, int64_t B, int np, int ga, int gb, int* scratch, void* stream);
+/* Host-only test hooks of the eigensolver's schedule (no GPU work).  r3d_debug_round_plan: the rounds of one sweep for nb
+ * blocks as (a, b) entries -- b == 0: a single XOR round with mask a; else the super-round {a, b, a ^ b} whose three V
+ * updates run as one chained pass; returns the entry count (0: this block count uses the circle method).
+ * r3d_debug_chain_plan: tile bookkeeping of that pass for group g: out22[0..3] global blocks of the coset,
+ * out22[4 + 4k + pos] local block at accumulator position pos in round k, out22[16 + 2k + p] task of pair p in round k. */
+int r3d_debug_round_plan(int nb, int32_t* out_pairs, int cap);
+int r3d_debug_chain_plan(int ga, int gb, int g, int32_t* out22);
 /* Measurement hook: panel tiles (128 rows x 64 output columns: 32 KB read + 32 KB written) the Jacobi panel kernel
  * has actually processed on the current device since the last reset -- out3[0] G passes, out3[1] V passes, out3[2]
  * tiles of the group-local 128 x 128 problems of the spread schedule (an L2-resident working set, not HBM traffic).

@@ -24,6 +24,8 @@ SIGNATURES = {
     "r3d_debug_panel_round": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p,
                                       c_void_p]),
     "r3d_debug_vchain": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "r3d_debug_round_plan": (c_int, [c_int, c_void_p, c_int]),
+    "r3d_debug_chain_plan": (c_int, [c_int, c_int, c_int, c_void_p]),
     "r3d_profile_enable": (c_int, [c_int]),
     "r3d_profile_num_stages": (c_int, []),
     "r3d_profile_stage_name": (c_char_p, [c_int]),

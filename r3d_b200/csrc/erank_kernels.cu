@@ -1295,6 +1295,22 @@ extern "C" int r3d_debug_vchain(float* V, float* Q3, int64_t B, int np, int ga, 
   return rc;
 }
 
+// Host-only test hooks (no GPU work): the round plan of a sweep for nb blocks -- entries (a, b): b == 0 a single XOR round
+// with mask a, else the super-round {a, b, a ^ b}; returns the number of entries (0: the block count gets the circle
+// method) -- and the chained V update's tile bookkeeping for group g of the super-round (ga, gb).
+extern "C" int r3d_debug_round_plan(int nb, int32_t* out_pairs, int cap) {
+  const std::vector<SuperRound> plan = spread_plan(nb);
+  for (size_t i = 0; i < plan.size() && (int)i < cap; ++i) { out_pairs[2 * i] = plan[i].a; out_pairs[2 * i + 1] = plan[i].b; }
+  return (int)plan.size();
+}
+extern "C" int r3d_debug_chain_plan(int ga, int gb, int g, int32_t* out22) {
+  R3D_CHECK(ga > 0 && gb > 0 && ga != gb && out22 != nullptr, "bad arguments");
+  int tmp[22];
+  panel_chain_plan_host(groups_of(SuperRound{ga, gb}), g, tmp);
+  for (int i = 0; i < 22; ++i) out22[i] = tmp[i];
+  return 0;
+}
+
 extern "C" int r3d_panel_tiles(uint64_t* out3, int reset) {
   R3D_CHECK(out3 != nullptr, "null pointer");
   unsigned long long v[3];

@@ -566,10 +566,17 @@ struct ChainJob {
 // ([pair 0: I, J | pair 1: I, J]); task = the rounds' task indices of the two pairs (8 bits each)
 struct ChainPlan { int x; uint32_t sig; uint64_t task; };
 
-__device__ __forceinline__ int chain_blk(const ChainJob& cj, int x, int j) {
+__host__ __device__ __forceinline__ int top_bit(int v) {
+#ifdef __CUDA_ARCH__
+  return 31 - __clz(v);
+#else
+  return 31 - __builtin_clz((unsigned)v);
+#endif
+}
+__host__ __device__ __forceinline__ int chain_blk(const ChainJob& cj, int x, int j) {
   return x ^ ((j & 1) ? cj.ga : 0) ^ ((j & 2) ? cj.gb : 0);
 }
-__device__ __forceinline__ ChainPlan chain_plan(const ChainJob& cj, int g) {
+__host__ __device__ __forceinline__ ChainPlan chain_plan(const ChainJob& cj, int g) {
   ChainPlan cp;
   int x = g;
   x = ((x >> cj.plo) << (cj.plo + 1)) | (x & ((1 << cj.plo) - 1));
@@ -579,7 +586,7 @@ __device__ __forceinline__ ChainPlan chain_plan(const ChainJob& cj, int g) {
   for (int k = 0; k < 3; ++k) {
     const int lm = k + 1;
     const int mk = ((lm & 1) ? cj.ga : 0) ^ ((lm & 2) ? cj.gb : 0);
-    const int hb = 31 - __clz(mk);
+    const int hb = top_bit(mk);
 #pragma unroll
     for (int p = 0; p < 2; ++p) {
       const int j = p == 0 ? 0 : (lm == 1 ? 2 : 1), jj = j ^ lm;
@@ -593,10 +600,10 @@ __device__ __forceinline__ ChainPlan chain_plan(const ChainJob& cj, int g) {
   }
   return cp;
 }
-__device__ __forceinline__ int chain_sig(const ChainPlan& cp, int k, int pos) { return (cp.sig >> (8 * k + 2 * pos)) & 3; }
-__device__ __forceinline__ int chain_task(const ChainPlan& cp, int k, int p) { return int((cp.task >> (16 * k + 8 * p)) & 0xff); }
+__host__ __device__ __forceinline__ int chain_sig(const ChainPlan& cp, int k, int pos) { return (cp.sig >> (8 * k + 2 * pos)) & 3; }
+__host__ __device__ __forceinline__ int chain_task(const ChainPlan& cp, int k, int p) { return int((cp.task >> (16 * k + 8 * p)) & 0xff); }
 // accumulator column position of local block l after round k
-__device__ __forceinline__ int chain_pos(const ChainPlan& cp, int k, int l) {
+__host__ __device__ __forceinline__ int chain_pos(const ChainPlan& cp, int k, int l) {
   int pos = 0;
 #pragma unroll
   for (int q = 1; q < 4; ++q) if (chain_sig(cp, k, q) == l) pos = q;
@@ -957,6 +964,20 @@ int panel_tc_prepare_chain(PanelTc* h, float* const Qc[6]) {
   for (int i = 0; i < 6; ++i)
     if (int e = make_map_q(&h->map_qc[i], Qc[i], h->B * h->nt * 2 * PM)) return e;
   return 0;
+}
+
+// Host mirror of the tile bookkeeping of panel_vchain_kernel for the CPU tests: group g of the coset structure `grp` ->
+// out[0..3] the four global blocks, out[4 + 4 k + pos] the local block at accumulator position pos in round k,
+// out[16 + 2 k + p] the task index (in the round's Q^T buffer) of pair p in round k.
+void panel_chain_plan_host(const PanelGroups& grp, int g, int out[22]) {
+  ChainJob cj{};
+  cj.ga = grp.ga; cj.gb = grp.gb; cj.plo = grp.plo; cj.phi = grp.phi;
+  const ChainPlan cp = chain_plan(cj, g);
+  for (int j = 0; j < 4; ++j) out[j] = chain_blk(cj, cp.x, j);
+  for (int k = 0; k < 3; ++k) {
+    for (int pos = 0; pos < 4; ++pos) out[4 + 4 * k + pos] = chain_sig(cp, k, pos);
+    for (int p = 0; p < 2; ++p) out[16 + 2 * k + p] = chain_task(cp, k, p);
+  }
 }
 
 bool panel_chain_supported(int np) {

@@ -43,6 +43,7 @@ int panel_tc_update_v_groups(PanelTc* h, int pbuf, const PanelGroups& grp, int s
 
 // Chained V update (jacobi_schedule = 2): V <- V Q1 Q2 Q3 for three XOR rounds inside 4-block cosets, one pass over V.
 bool panel_chain_supported(int np);
+void panel_chain_plan_host(const PanelGroups& grp, int g, int out[22]);   // host mirror of the kernel's tile bookkeeping (tests)
 int panel_tc_prepare_chain(PanelTc* h, float* const Qc[6]);
 int panel_tc_update_v_chain(PanelTc* h, int slot, const PanelGroups& grp, int sweep, const int* cnt,
                             const int* const qflag[3], cudaStream_t st);

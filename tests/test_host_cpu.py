@@ -234,3 +234,65 @@ def test_header_is_plain_c_and_links(tmp_path):
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
     assert "null" in out.stdout.lower()
+
+
+# ------------------------------------------------------------------ eigensolver schedule (host logic, no GPU)
+def _round_plan(nb):
+    from r3d_b200 import _lib
+    out = np.zeros(2 * 512, np.int32)
+    n = _lib.lib().r3d_debug_round_plan(nb, out.ctypes.data, 512)
+    return [tuple(int(v) for v in out[2 * i:2 * i + 2]) for i in range(n)]
+
+
+@pytest.mark.parametrize("nb", [8, 16, 32, 64, 128, 256])
+def test_round_plan_covers_every_mask_exactly_once(nb):
+    """The rounds of a sweep are the XOR matchings i <-> i ^ mask; a super-round {a, b, a ^ b} keeps three of them inside
+    4-block cosets (csrc/erank_kernels.cu: spread_plan).  Every mask 1..nb-1 must occur exactly once per sweep -- then every
+    block pair meets exactly once, as in the circle method."""
+    plan = _round_plan(nb)
+    masks = []
+    for a, b in plan:
+        assert 0 < a < nb and 0 <= b < nb
+        masks += [a] if b == 0 else [a, b, a ^ b]
+        if b:
+            assert a != b and (a ^ b) not in (0, a, b)
+    assert sorted(masks) == list(range(1, nb))
+    k = nb.bit_length() - 1
+    if k % 2 == 0:                       # GF(2^k) over GF(4): a full spread, no single rounds left over
+        assert all(b != 0 for _, b in plan) and len(plan) == (nb - 1) // 3
+    assert plan[0][1] != 0               # the first entry of a sweep carries the generic (within-block) round
+
+
+@pytest.mark.parametrize("nb", [2, 4, 6, 12, 24])
+def test_round_plan_falls_back_to_circle_method(nb):
+    assert _round_plan(nb) == []
+
+
+@pytest.mark.parametrize("nb", [8, 16, 32, 64])
+def test_chain_plan_matches_the_xor_pairing(nb):
+    """Tile bookkeeping of the chained V update (csrc/jacobi_tc.cu: chain_plan) against the pairing the inner solver uses
+    (rr_pair with a negative round code): the cosets partition the blocks; in round k the accumulator holds the coset's
+    blocks as [pair 0: I, J | pair 1: I, J] with J = I ^ mask_k, I the block with the mask's top bit clear, and the task
+    index is I with that bit removed -- the row of the round's Q^T buffer the inner solver wrote for (I, J)."""
+    from r3d_b200 import _lib
+    L = _lib.lib()
+    for a, b in _round_plan(nb):
+        if b == 0:
+            continue
+        seen = []
+        for g in range(nb // 4):
+            o = np.zeros(22, np.int32)
+            assert L.r3d_debug_chain_plan(a, b, g, o.ctypes.data) == 0
+            blk = [int(v) for v in o[:4]]
+            assert sorted(blk) == sorted({blk[0], blk[0] ^ a, blk[0] ^ b, blk[0] ^ a ^ b}) and len(set(blk)) == 4
+            seen += blk
+            for k, mask in enumerate((a, b, a ^ b)):
+                sig = [int(v) for v in o[4 + 4 * k:8 + 4 * k]]
+                assert sorted(sig) == [0, 1, 2, 3]
+                hb = mask.bit_length() - 1
+                for p in range(2):
+                    I, J = blk[sig[2 * p]], blk[sig[2 * p + 1]]
+                    assert J == I ^ mask and (I >> hb) & 1 == 0
+                    task = ((I >> (hb + 1)) << hb) | (I & ((1 << hb) - 1))
+                    assert int(o[16 + 2 * k + p]) == task
+        assert sorted(seen) == list(range(nb))
