@@ -45,9 +45,12 @@ int64_t r3d_launch_count(int reset);
  *                         samples; 1 = single pass (erank unchanged, gradients 1e-3 .. 5e-2 on square samples)
  *   "jacobi_tol"          relative rotation threshold |s_pq| > tol sqrt(s_pp s_qq), default 1e-6
  *   "jacobi_tol_pass1"    the same for the first pass of the two-pass solver, default 1e-6
- *   "jacobi_nu_pass1"     first-pass absolute significance floor in units of 2^-23 max|diag|, default 2048 (the first
- *                         pass stops early, the second finishes; single-pass solver and second pass use 4)
- *   "jacobi_max_sweeps"   sweep cap, default 16, at most 32; "erank_pass1_sweeps" (12) / "erank_pass2_sweeps" (4)
+ *   "jacobi_nu_pass1"     first-pass absolute significance floor in units of 2^-23 max|diag|, default 8192 (the first
+ *                         pass stops early, the second finishes; the single-pass solver uses 4)
+ *   "jacobi_nu_pass2"     second pass: < 0 (default -1e-10) = scale-free test, a rotation is significant when it passes
+ *                         the relative test and one of its two diagonal entries exceeds |value| max|diag|; > 0 = absolute
+ *                         floor in the units of "jacobi_nu_pass1"
+ *   "jacobi_max_sweeps"   sweep cap, default 16, at most 32; "erank_pass1_sweeps" (12) / "erank_pass2_sweeps" (6)
  *                         are the caps of the two passes
  * Kernel selection (defaults are the fast paths; the alternatives exist for A/B measurements and as fallbacks):
  *   "jacobi_update_tc"    1 = tcgen05 3xTF32 panel update, 0 = SIMT fp32 tile update
@@ -55,7 +58,13 @@ int64_t r3d_launch_count(int reset);
  *   "gemm_tc"             1 = refinement / backward / fp32-Gram GEMMs on tcgen05 through bf16 planes, 0 = SIMT
  *   "jacobi_overlap_v"    1 = eigenvector update on a library-owned side stream; "jacobi_v_after_g" 0 = it starts
  *                         right after the inner solve (default), 1 = after the G passes of the round
- *   "jacobi_chunks"       1 (default); 2 = two half-batches on two streams (measured slower)
+ *   "jacobi_chunks"       2 (default; up to 4): the batch is cut into chunks whose Jacobi iterations run on separate
+ *                         library-owned streams, so that one chunk's issue-bound inner solve shares the SMs with another
+ *                         chunk's latency-bound panel passes (only while every chunk still fills the GPU); 1 = one sequence.
+ *                         Results do not depend on the chunk count.  "jacobi_own_streams" 1 (default) = all chunks on
+ *                         library streams of high priority (V streams: low), 0 = chunk 0 on the caller's stream
+ *   "panel_sym"           1 (default) = G <- Q^T G Q as one in-place pass over the upper block triangle (jacobi_sym.cu);
+ *                         0 = two passes through the scratch matrix H
  *   "panel_merged"        0 (default); 1 = both G passes in one launch with H in an L2-resident ring, sized by
  *                         "panel_group_mb" (8) and "panel_ring" (6) (less DRAM traffic, measured slower)
  *   "jacobi_schedule"     0 = circle-method round robin, one panel update of G and V per round;
