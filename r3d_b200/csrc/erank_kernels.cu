@@ -1440,6 +1440,13 @@ static int jacobi_run_chunked(const float* G, int64_t B, int64_t n, void* worksp
 // absolute error of an fp32 Gram (eps * lambda_max), which is large relative to the smallest singular directions.
 // G2 = Y Y^T is nearly diagonal and GRADED (its small entries are represented to fp32 relative accuracy), which
 // two-sided Jacobi resolves to relative accuracy (Demmel-Veselic): G2 = V2^T diag V2, then U <- V2 U, Y <- V2 Y.
+// sweep cap of the second pass: the option, or (negative = automatic, the default) 6 up to n = 1024 and 8 beyond --
+// with the first-pass floor at 8192 ulps the second pass takes 3-5 sweeps at n <= 1024 and 7 at n = 2048 (decay spectrum)
+static int pass2_cap(int64_t n) {
+  const int o = options().erank_pass2_sweeps;
+  return o >= 0 ? o : (n <= 1024 ? 6 : 8);
+}
+
 static int second_pass_tc(const ErankWs& w, int64_t B, int64_t n, int64_t m, float* U, float* Y, int32_t* sweeps2,
                           cudaStream_t st) {
   if (int e = split_planes(Y, R3D_F32, w.Ypl, B * n * m, 3, m, nullptr, st)) return e;
@@ -1452,7 +1459,7 @@ static int second_pass_tc(const ErankWs& w, int64_t B, int64_t n, int64_t m, flo
     g.out_mode = 0; g.C = w.G; g.ldc = n; g.strideC = n * n;
     if (int e = pgemm_launch(g, st)) return e;
   }
-  if (int e = jacobi_run_chunked(w.G, B, n, w.jws, nullptr, w.U2, sweeps2, options().erank_pass2_sweeps, st, -1.f)) return e;
+  if (int e = jacobi_run_chunked(w.G, B, n, w.jws, nullptr, w.U2, sweeps2, pass2_cap(n), st, -1.f)) return e;
   R3D_STAGE(ST_REFINE_Y, st);
   if (int e = split_planes(w.U2, R3D_F32, w.U2pl, B * n * n, 3, n, nullptr, st)) return e;
   if (int e = split_planes(U, R3D_F32, w.Upl, B * n * n, 3, n, nullptr, st)) return e;
@@ -1476,7 +1483,7 @@ static int second_pass_simt(const ErankWs& w, int64_t B, int64_t n, int64_t m, f
     if (int e = sgemm_launch<float, float, float>(false, true, Y, Y, w.G, int(n), int(n), int(m), m, m, n, n * m, n * m,
                                                   n * n, nullptr, 0, 0, int(B), st)) return e;
   }
-  if (int e = jacobi_run_chunked(w.G, B, n, w.jws, nullptr, w.U2, sweeps2, options().erank_pass2_sweeps, st, -1.f)) return e;
+  if (int e = jacobi_run_chunked(w.G, B, n, w.jws, nullptr, w.U2, sweeps2, pass2_cap(n), st, -1.f)) return e;
   R3D_STAGE(ST_REFINE_Y, st);
   float* Un = reinterpret_cast<float*>(w.Upl);
   float* Yn = reinterpret_cast<float*>(w.Ypl);
