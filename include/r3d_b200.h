@@ -50,7 +50,7 @@ int64_t r3d_launch_count(int reset);
  *   "jacobi_nu_pass2"     second pass: < 0 (default -1e-10) = scale-free test, a rotation is significant when it passes
  *                         the relative test and one of its two diagonal entries exceeds |value| max|diag|; > 0 = absolute
  *                         floor in the units of "jacobi_nu_pass1"
- *   "jacobi_max_sweeps"   sweep cap, default 16, at most 32; "erank_pass1_sweeps" (12) / "erank_pass2_sweeps" (-1 = 6 up to n = 1024, 8 beyond)
+ *   "jacobi_max_sweeps"   sweep cap, default 16, at most 32; "erank_pass1_sweeps" (12) / "erank_pass2_sweeps" (-1 = 6 up to n = 512, 8 beyond)
  *                         are the caps of the two passes
  * Kernel selection (defaults are the fast paths; the alternatives exist for A/B measurements and as fallbacks):
  *   "jacobi_update_tc"    1 = tcgen05 3xTF32 panel update, 0 = SIMT fp32 tile update

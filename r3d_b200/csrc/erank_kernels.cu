@@ -1440,11 +1440,11 @@ static int jacobi_run_chunked(const float* G, int64_t B, int64_t n, void* worksp
 // absolute error of an fp32 Gram (eps * lambda_max), which is large relative to the smallest singular directions.
 // G2 = Y Y^T is nearly diagonal and GRADED (its small entries are represented to fp32 relative accuracy), which
 // two-sided Jacobi resolves to relative accuracy (Demmel-Veselic): G2 = V2^T diag V2, then U <- V2 U, Y <- V2 Y.
-// sweep cap of the second pass: the option, or (negative = automatic, the default) 6 up to n = 1024 and 8 beyond --
-// with the first-pass floor at 8192 ulps the second pass takes 3-5 sweeps at n <= 1024 and 7 at n = 2048 (decay spectrum)
+// sweep cap of the second pass: the option, or (negative = automatic, the default) 6 up to n = 512 and 8 beyond --
+// with the first-pass floor at 8192 ulps the second pass takes 3-5 sweeps at n <= 512 and 7 at n = 2048 (decay spectrum)
 static int pass2_cap(int64_t n) {
   const int o = options().erank_pass2_sweeps;
-  return o >= 0 ? o : (n <= 1024 ? 6 : 8);
+  return o >= 0 ? o : (n <= 512 ? 6 : 8);
 }
 
 static int second_pass_tc(const ErankWs& w, int64_t B, int64_t n, int64_t m, float* U, float* Y, int32_t* sweeps2,

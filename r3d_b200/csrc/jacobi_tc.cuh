@@ -80,8 +80,8 @@ struct Options {
                                   // scripts/dbg_floor_sweep.py); scale-free: <= 1.6e-5 on every input tried, +1.5 ms per step
   int erank_pass1_sweeps = 12;  // sweep cap of the first pass of the two-pass solver (it converges in 8-11 with the raised floor;
                                 // whatever a capped matrix still needs, the second pass does); 0 = jacobi_max_sweeps
-  int erank_pass2_sweeps = -1;  // sweep cap of the second pass: < 0 (default) = automatic, 6 up to n = 1024 and 8 beyond (the second
-                                // pass takes 3-5 sweeps at n <= 1024, 7 at n = 2048 with a decaying spectrum; each spare sweep costs
+  int erank_pass2_sweeps = -1;  // sweep cap of the second pass: < 0 (default) = automatic, 6 up to n = 512 and 8 beyond (the second
+                                // pass takes 3-5 sweeps at n <= 512, 7 at n = 2048 with a decaying spectrum; each spare sweep costs
                                 // ~35 launches per chunk that return at once); 0 = jacobi_max_sweeps; > 0 = that many
   int erank_passes = 2;         // 2: second refinement pass (G2 = Y Y^T -> Jacobi -> U, Y updated): relative accuracy for the
                                 //    smallest singular directions (gradients <= 1e-4 on square samples), +15 % time;
